@@ -1,0 +1,319 @@
+// K5/K6 — decoder-side kernels: sine position embedding, multi-head self-attention core
+// with warp-shuffle online softmax, and the UniCrossAtten sampling block (sigmoid gate +
+// trilinear gather from the NDHWC voxel volume).
+//
+// Reference: projects/mmdet3d_plugin/models/utils/uni3detr_transformer.py
+//   get_sine_pos_embed :33-65 (called :180), UniCrossAtten.forward :271-360, and the
+//   nn.MultiheadAttention self-attention of mmcv's BaseTransformerLayer.
+#include "common.cuh"
+
+namespace u3d {
+
+// ------------------------------------------------------------ sine embedding ---
+// out[r, c*128 + i] = i even ? sin(v_i) : cos(v_i),  v_i = sigmoid(ref[r,c]) * 2pi / T^(2*floor(i/2)/128)
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_sine_embed(const float* __restrict__ ref, int rows, T* __restrict__ out) {
+  const int i = threadIdx.x;  // 0..127
+  // dim_t = 10000 ** (2*(i//2)/128), evaluated like torch (fp32 pow)
+  const float dim_t = powf(10000.f, (float)(2 * (i / 2)) / 128.f);
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = __ldg(&ref[(size_t)r * 3 + c]);
+      float s = 1.f / (1.f + expf(-x));
+      float v = s * 6.283185307179586f / dim_t;
+      float e = (i & 1) ? cosf(v) : sinf(v);
+      out[(size_t)r * 384 + c * 128 + i] = from_f32<T>(e);
+    }
+  }
+}
+
+// ------------------------------------------------------ self-attention core ---
+// One CTA per (sequence, head, query block). K^T and V of the whole sequence tile are staged in shared
+// memory (fp32); each warp processes QPW queries at a time: lane <-> key for the score
+// pass (K^T laid out [d][key], conflict-free), warp-shuffle max/sum (online softmax over
+// key tiles), lane <-> head-dim for the P.V pass.
+constexpr int kHd = 32;
+constexpr int kTK = 64;   // keys per smem tile
+constexpr int kQPW = 4;   // queries per warp pass
+constexpr int kPasses = 4;
+constexpr int kMhaWarps = 8;
+constexpr int kQPerWarp = kQPW * kPasses;          // 16
+constexpr int kQBlock = kMhaWarps * kQPerWarp;     // queries per CTA = 128
+
+template <typename T>
+__global__ void __launch_bounds__(kMhaWarps * 32)
+k_mha_core(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int ldq,
+           int ldk, int ldv, int seq_len, int heads, T* __restrict__ out) {
+  __shared__ float s_kt[kHd][kTK + 1];
+  __shared__ float s_v[kTK][kHd];
+  __shared__ float s_q[kMhaWarps][kQPerWarp][kHd];
+  __shared__ float s_p[kMhaWarps][kQPW][kTK];
+
+  const int head = blockIdx.y, seq = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qw = blockIdx.x * kQBlock + warp * kQPerWarp;  // first query of this warp
+  const size_t row0 = (size_t)seq * seq_len;
+  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
+  const int out_ld = heads * kHd;
+
+  // pre-scaled queries of this warp (lane <-> dim)
+#pragma unroll
+  for (int j = 0; j < kQPerWarp; ++j) {
+    int qi = qw + j;
+    float x = 0.f;
+    if (qi < seq_len) x = to_f32<T>(__ldg(&q[(row0 + qi) * ldq + head * kHd + lane])) * scale;
+    s_q[warp][j][lane] = x;
+  }
+  float m[kQPerWarp], l[kQPerWarp], acc[kQPerWarp];
+#pragma unroll
+  for (int j = 0; j < kQPerWarp; ++j) { m[j] = -INFINITY; l[j] = 0.f; acc[j] = 0.f; }
+
+  for (int kt = 0; kt < seq_len; kt += kTK) {
+    __syncthreads();  // previous tile fully consumed by every warp
+    for (int e = threadIdx.x; e < kTK * kHd; e += blockDim.x) {
+      int key = e / kHd, d = e % kHd;
+      int ki = kt + key;
+      float kv = 0.f, vv = 0.f;
+      if (ki < seq_len) {
+        kv = to_f32<T>(__ldg(&k[(row0 + ki) * ldk + head * kHd + d]));
+        vv = to_f32<T>(__ldg(&v[(row0 + ki) * ldv + head * kHd + d]));
+      }
+      s_kt[d][key] = kv;
+      s_v[key][d] = vv;
+    }
+    __syncthreads();
+    const int nkeys = min(kTK, seq_len - kt);
+#pragma unroll
+    for (int pass = 0; pass < kPasses; ++pass) {
+      if (qw + pass * kQPW >= seq_len) break;  // warp-uniform
+      // scores: lane <-> key
+      float sc[kQPW][kTK / 32];
+#pragma unroll
+      for (int g = 0; g < kTK / 32; ++g) {
+        float a[kQPW];
+#pragma unroll
+        for (int j = 0; j < kQPW; ++j) a[j] = 0.f;
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) {
+          float kv = s_kt[d][g * 32 + lane];
+#pragma unroll
+          for (int j = 0; j < kQPW; ++j) a[j] = fmaf(s_q[warp][pass * kQPW + j][d], kv, a[j]);
+        }
+        bool valid = (g * 32 + lane) < nkeys;
+#pragma unroll
+        for (int j = 0; j < kQPW; ++j) sc[j][g] = valid ? a[j] : -INFINITY;
+      }
+      // online softmax update per query
+#pragma unroll
+      for (int j = 0; j < kQPW; ++j) {
+        const int jj = pass * kQPW + j;
+        float tmax = sc[j][0];
+#pragma unroll
+        for (int g = 1; g < kTK / 32; ++g) tmax = fmaxf(tmax, sc[j][g]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        float mnew = fmaxf(m[jj], tmax);
+        float corr = __expf(m[jj] - mnew);  // m=-inf on the first tile -> 0
+        float psum = 0.f;
+#pragma unroll
+        for (int g = 0; g < kTK / 32; ++g) {
+          float p = __expf(sc[j][g] - mnew);
+          s_p[warp][j][g * 32 + lane] = p;
+          psum += p;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        l[jj] = l[jj] * corr + psum;
+        acc[jj] *= corr;
+        m[jj] = mnew;
+      }
+      __syncwarp();
+      // P.V: lane <-> dim
+      for (int key = 0; key < nkeys; ++key) {
+        float vv = s_v[key][lane];
+#pragma unroll
+        for (int j = 0; j < kQPW; ++j)
+          acc[pass * kQPW + j] = fmaf(s_p[warp][j][key], vv, acc[pass * kQPW + j]);
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kQPerWarp; ++j) {
+    int qi = qw + j;
+    if (qi < seq_len) out[(row0 + qi) * out_ld + head * kHd + lane] = from_f32<T>(acc[j] / l[j]);
+  }
+}
+
+// ----------------------------------------------------- cross-attention sample ---
+// one warp per query; lanes stride the channel dimension in vectors of 8 (bf16) / 4 (f32)
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  typedef float4 type;
+  static __device__ __forceinline__ void unpack(const float4& v, float* f) {
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ float4 pack(const float* f) {
+    return make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  typedef uint4 type;
+  static __device__ __forceinline__ void unpack(const uint4& v, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return v;
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_cross_sample(const T* __restrict__ value, int D, int H, int W, int C,
+               const float* __restrict__ ref, const T* __restrict__ query,
+               const T* __restrict__ query_pos, const float* __restrict__ gate_w, float gate_b,
+               int Q, int rows, T* __restrict__ out) {
+  typedef Vec<T> V;
+  typedef typename V::type vec_t;
+  constexpr int VN = V::N;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int b = r / Q;
+    // gate = sigmoid((query + query_pos) . w + bias)
+    float dot = 0.f;
+    for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
+      float qf[VN], pf[VN];
+      V::unpack(__ldg(reinterpret_cast<const vec_t*>(query + (size_t)r * C + c0)), qf);
+      if (query_pos) {
+        V::unpack(__ldg(reinterpret_cast<const vec_t*>(query_pos + (size_t)r * C + c0)), pf);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) qf[i] = to_f32<T>(from_f32<T>(qf[i] + pf[i]));
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) dot = fmaf(qf[i], __ldg(&gate_w[c0 + i]), dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float gate = 1.f / (1.f + __expf(-(dot + gate_b)));
+
+    // grid_sample(align_corners=False): g = 2*sigmoid(ref)-1 ; i = ((g+1)*S-1)/2
+    float fx, fy, fz;
+    {
+      float sx = 1.f / (1.f + expf(-__ldg(&ref[(size_t)r * 3 + 0])));
+      float sy = 1.f / (1.f + expf(-__ldg(&ref[(size_t)r * 3 + 1])));
+      float sz = 1.f / (1.f + expf(-__ldg(&ref[(size_t)r * 3 + 2])));
+      float gx = (sx - 0.5f) * 2.f, gy = (sy - 0.5f) * 2.f, gz = (sz - 0.5f) * 2.f;
+      fx = ((gx + 1.f) * (float)W - 1.f) * 0.5f;
+      fy = ((gy + 1.f) * (float)H - 1.f) * 0.5f;
+      fz = ((gz + 1.f) * (float)D - 1.f) * 0.5f;
+    }
+    const float x0f = floorf(fx), y0f = floorf(fy), z0f = floorf(fz);
+    const int x0 = (int)x0f, y0 = (int)y0f, z0 = (int)z0f;
+    const float tx = fx - x0f, ty = fy - y0f, tz = fz - z0f;
+    float wgt[8];
+    long long off[8];
+#pragma unroll
+    for (int cidx = 0; cidx < 8; ++cidx) {
+      int dz = cidx >> 2, dy = (cidx >> 1) & 1, dx = cidx & 1;
+      int x = x0 + dx, y = y0 + dy, z = z0 + dz;
+      bool inb = x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D;
+      float wv = (dx ? tx : 1.f - tx) * (dy ? ty : 1.f - ty) * (dz ? tz : 1.f - tz);
+      wgt[cidx] = inb ? wv : 0.f;
+      off[cidx] = inb ? ((((long long)b * D + z) * H + y) * W + x) * C : 0;
+    }
+    for (int c0 = lane * VN; c0 < C; c0 += 32 * VN) {
+      float acc[VN];
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int cidx = 0; cidx < 8; ++cidx) {
+        if (wgt[cidx] != 0.f) {
+          float f[VN];
+          V::unpack(__ldg(reinterpret_cast<const vec_t*>(value + off[cidx] + c0)), f);
+#pragma unroll
+          for (int i = 0; i < VN; ++i) acc[i] = fmaf(wgt[cidx], f[i], acc[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[i] *= gate;
+      *reinterpret_cast<vec_t*>(out + (size_t)r * C + c0) = V::pack(acc);
+    }
+  }
+}
+
+}  // namespace u3d
+
+using namespace u3d;
+
+extern "C" int u3d_sine_embed(const float* ref, int rows, void* out, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  U3D_CHECK_ARG(ref && out && rows >= 0, "u3d_sine_embed: bad argument");
+  U3D_CHECK_ARG(dtype == U3D_F32 || dtype == U3D_BF16, "u3d_sine_embed: bad dtype");
+  if (rows == 0) return U3D_OK;
+  int grid = rows < kNumSMs * 16 ? rows : kNumSMs * 16;
+  if (dtype == U3D_F32) k_sine_embed<float><<<grid, 128, 0, st>>>(ref, rows, (float*)out);
+  else k_sine_embed<__nv_bfloat16><<<grid, 128, 0, st>>>(ref, rows, (__nv_bfloat16*)out);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+extern "C" int u3d_mha_core(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv,
+                            int n_seq, int seq_len, int heads, void* out, int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  U3D_CHECK_ARG(q && k && v && out, "u3d_mha_core: null buffer");
+  U3D_CHECK_ARG(n_seq >= 1 && seq_len >= 1 && heads >= 1 && ldq >= heads * kHd && ldk >= heads * kHd &&
+                    ldv >= heads * kHd,
+                "u3d_mha_core: bad shape");
+  U3D_CHECK_ARG(n_seq <= 65535 && heads <= 65535, "u3d_mha_core: grid too large");
+  U3D_CHECK_ARG(dtype == U3D_F32 || dtype == U3D_BF16, "u3d_mha_core: bad dtype");
+  dim3 grid(cdiv(seq_len, kQBlock), heads, n_seq);
+  if (dtype == U3D_F32)
+    k_mha_core<float><<<grid, kMhaWarps * 32, 0, st>>>((const float*)q, (const float*)k,
+                                                       (const float*)v, ldq, ldk, ldv, seq_len, heads,
+                                                       (float*)out);
+  else
+    k_mha_core<__nv_bfloat16><<<grid, kMhaWarps * 32, 0, st>>>(
+        (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldq, ldk, ldv,
+        seq_len, heads, (__nv_bfloat16*)out);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+extern "C" int u3d_cross_sample(const void* value, int B, int D, int H, int W, int C,
+                                const float* ref, const void* query, const void* query_pos,
+                                const float* gate_w, float gate_b, int Q, void* out, int dtype,
+                                void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  U3D_CHECK_ARG(value && ref && query && gate_w && out, "u3d_cross_sample: null buffer");
+  U3D_CHECK_ARG(dtype == U3D_F32 || dtype == U3D_BF16, "u3d_cross_sample: bad dtype");
+  int vn = dtype == U3D_BF16 ? 8 : 4;
+  U3D_CHECK_ARG(C % vn == 0, "u3d_cross_sample: C=%d must be a multiple of %d", C, vn);
+  int rows = B * Q;
+  if (rows == 0) return U3D_OK;
+  int grid = cdiv(rows, 8);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (dtype == U3D_F32)
+    k_cross_sample<float><<<grid, 256, 0, st>>>((const float*)value, D, H, W, C, ref,
+                                                (const float*)query, (const float*)query_pos,
+                                                gate_w, gate_b, Q, rows, (float*)out);
+  else
+    k_cross_sample<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        (const __nv_bfloat16*)value, D, H, W, C, ref, (const __nv_bfloat16*)query,
+        (const __nv_bfloat16*)query_pos, gate_w, gate_b, Q, rows, (__nv_bfloat16*)out);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}

@@ -1,0 +1,296 @@
+"""Tensor-level wrappers over the C ABI (include/u3d.h).
+
+PyTorch is plumbing here: it owns device memory and the stream. Every function
+enqueues on ``torch.cuda.current_stream()`` and never synchronises; data-dependent
+sizes stay on the device (int32 counters), buffers are sized by capacity.
+There is no CPU path: tensors must live on a CUDA device.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+U3D_F32, U3D_BF16 = 0, 1
+ORDER_FIRST_APPEARANCE, ORDER_LINEAR = 0, 1
+_DT = {torch.float32: U3D_F32, torch.bfloat16: U3D_BF16}
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _farr(vals):
+    arr = (ctypes.c_float * len(vals))(*[float(v) for v in vals])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+def _iarr(vals):
+    arr = (ctypes.c_int32 * len(vals))(*[int(v) for v in vals])
+    return arr, ctypes.cast(arr, ctypes.c_void_p)
+
+
+def _req(t: torch.Tensor, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.U3DError(f"{name} must be a CUDA tensor: libu3d_b200 has no CPU path")
+    if not t.is_contiguous():
+        raise _lib.U3DError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.U3DError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+@dataclass
+class VoxelMap:
+    """Coordinate index of one resolution level (see include/u3d.h)."""
+    words: torch.Tensor            # (nwords, 2) int32 = uint2 {bits, prefix}
+    perm: Optional[torch.Tensor]   # (ranks,) int32 rank -> row, or None
+    B: int
+    dims: Sequence[int]            # (D, H, W)
+
+
+def voxmap_words(B, D, H, W):
+    n = _lib.load().u3d_voxmap_words(B, D, H, W)
+    if n == 0:
+        raise _lib.U3DError("B*D*H*W exceeds the 32-bit linear cell index; split the batch")
+    return n
+
+
+def _scan_scratch(words, device):
+    n = _lib.load().u3d_scan_scratch_ints(words)
+    return torch.empty(n, dtype=torch.int32, device=device)
+
+
+@dataclass
+class Voxels:
+    coors: torch.Tensor        # (cap,4) int32 [b,z,y,x]
+    feats: torch.Tensor        # (cap,C) f32 VFE mean
+    num_points: Optional[torch.Tensor]
+    voxels: Optional[torch.Tensor]
+    scene_rows: torch.Tensor   # (B+1,) int32 device; [B] = M
+    vmap: VoxelMap
+    cap: int
+    pt_coors: Optional[torch.Tensor] = None  # dynamic mode: (N,4) per-point coords
+
+    @property
+    def n_rows(self):
+        return self.scene_rows[-1:]
+
+
+def voxelize_hard(points, pt_off, B, pc_range, voxel_size, grid_zyx, max_pts, max_voxels,
+                  deterministic=True, want_voxels=False) -> Voxels:
+    lib = _lib.load()
+    _req(points, torch.float32, "points")
+    _req(pt_off, torch.int32, "pt_off")
+    Ntot, C = points.shape
+    D, H, W = [int(v) for v in grid_zyx]
+    dev = points.device
+    words = voxmap_words(B, D, H, W)
+    cap = Ntot if max_voxels <= 0 else min(Ntot, B * max_voxels)
+    cap = max(cap, 1)
+    vm = torch.empty((words, 2), dtype=torch.int32, device=dev)
+    scratch = _scan_scratch(words, dev)
+    pt_lin = torch.empty(max(Ntot, 1), dtype=torch.int32, device=dev)
+    slots = torch.empty(max(Ntot, 1) * max_pts, dtype=torch.int32, device=dev)
+    row_of_rank = torch.empty(max(Ntot, 1), dtype=torch.int32, device=dev)
+    coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    num_points = torch.empty(cap, dtype=torch.int32, device=dev)
+    voxels = torch.empty((cap, max_pts, C), dtype=torch.float32, device=dev) if want_voxels else None
+    feats = torch.empty((cap, C), dtype=torch.float32, device=dev)
+    scene_rows = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    pr, prp = _farr(pc_range)
+    vs, vsp = _farr(voxel_size)
+    order = ORDER_FIRST_APPEARANCE if deterministic else ORDER_LINEAR
+    _lib.check(lib.u3d_voxelize_hard(_p(points), _p(pt_off), Ntot, B, C, prp, vsp, D, H, W, max_pts,
+                                     int(max_voxels), order, _p(vm), _p(scratch), _p(pt_lin),
+                                     _p(slots), _p(row_of_rank), _p(coors), _p(num_points),
+                                     _p(voxels), _p(feats), _p(scene_rows), cap, _stream()))
+    return Voxels(coors, feats, num_points, voxels, scene_rows,
+                  VoxelMap(vm, row_of_rank, B, (D, H, W)), cap)
+
+
+def voxelize_dynamic(points, pt_off, B, pc_range, voxel_size, grid_zyx) -> Voxels:
+    lib = _lib.load()
+    _req(points, torch.float32, "points")
+    _req(pt_off, torch.int32, "pt_off")
+    Ntot, C = points.shape
+    D, H, W = [int(v) for v in grid_zyx]
+    dev = points.device
+    words = voxmap_words(B, D, H, W)
+    cap = max(Ntot, 1)
+    vm = torch.empty((words, 2), dtype=torch.int32, device=dev)
+    scratch = _scan_scratch(words, dev)
+    pt_lin = torch.empty(cap, dtype=torch.int32, device=dev)
+    pt_coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    coors = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    feats = torch.empty((cap, C), dtype=torch.float32, device=dev)
+    cnt = torch.empty(cap, dtype=torch.int32, device=dev)
+    scene_rows = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    pr, prp = _farr(pc_range)
+    vs, vsp = _farr(voxel_size)
+    _lib.check(lib.u3d_voxelize_dynamic(_p(points), _p(pt_off), Ntot, B, C, prp, vsp, D, H, W,
+                                        _p(vm), _p(scratch), _p(pt_lin), _p(pt_coors), _p(coors),
+                                        _p(feats), _p(cnt), _p(scene_rows), cap, _stream()))
+    return Voxels(coors, feats, cnt, None, scene_rows, VoxelMap(vm, None, B, (D, H, W)), cap,
+                  pt_coors=pt_coors)
+
+
+def voxmap_build(coors, n_rows, cap, B, dims) -> VoxelMap:
+    """VoxelMap of an arbitrary (cap,4) int32 coordinate list with a device-side row count."""
+    lib = _lib.load()
+    _req(coors, torch.int32, "coors")
+    D, H, W = [int(v) for v in dims]
+    words = voxmap_words(B, D, H, W)
+    vm = torch.empty((words, 2), dtype=torch.int32, device=coors.device)
+    scratch = _scan_scratch(words, coors.device)
+    perm = torch.empty(max(cap, 1), dtype=torch.int32, device=coors.device)
+    _lib.check(lib.u3d_voxmap_build(_p(coors), _p(n_rows), cap, B, D, H, W, _p(vm), _p(scratch),
+                                    _p(perm), _stream()))
+    return VoxelMap(vm, perm, B, (D, H, W))
+
+
+def rulebook_subm(coors, n_rows, cap, vmap: VoxelMap, nbr=None):
+    lib = _lib.load()
+    _req(coors, torch.int32, "coors")
+    if nbr is None:
+        nbr = torch.empty((27, cap), dtype=torch.int32, device=coors.device)
+    D, H, W = vmap.dims
+    _lib.check(lib.u3d_rulebook_subm(_p(coors), _p(n_rows), cap, _p(vmap.words), _p(vmap.perm),
+                                     vmap.B, D, H, W, _p(nbr), nbr.stride(0), _stream()))
+    return nbr
+
+
+def conv_out_dims(in_dims, stride, pad, k=3):
+    return tuple((int(d) + 2 * int(p) - k) // int(s) + 1 for d, s, p in zip(in_dims, stride, pad))
+
+
+def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=None):
+    lib = _lib.load()
+    _req(coors, torch.int32, "coors")
+    dev = coors.device
+    in_dims = tuple(int(v) for v in vmap.dims)
+    out_dims = conv_out_dims(in_dims, stride, pad)
+    words = voxmap_words(vmap.B, *out_dims)
+    if out_cap is None:
+        out_cap = min(8 * in_cap, vmap.B * out_dims[0] * out_dims[1] * out_dims[2])
+    out_cap = max(int(out_cap), 1)
+    out_vm = torch.empty((words, 2), dtype=torch.int32, device=dev)
+    scratch = _scan_scratch(words, dev)
+    out_coors = torch.empty((out_cap, 4), dtype=torch.int32, device=dev)
+    n_out = torch.empty(1, dtype=torch.int32, device=dev)
+    nbr = torch.empty((27, out_cap), dtype=torch.int32, device=dev)
+    a1, p1 = _iarr(in_dims)
+    a2, p2 = _iarr(out_dims)
+    a3, p3 = _iarr(stride)
+    a4, p4 = _iarr(pad)
+    _lib.check(lib.u3d_rulebook_down(_p(coors), _p(n_rows), in_cap, _p(vmap.words), _p(vmap.perm),
+                                     vmap.B, p1, p2, p3, p4, _p(out_vm), _p(scratch), _p(out_coors),
+                                     _p(n_out), out_cap, _p(nbr), nbr.stride(0), _stream()))
+    return out_coors, n_out, VoxelMap(out_vm, None, vmap.B, out_dims), nbr, out_cap
+
+
+def rulebook_pairs(nbr, n_out):
+    """spconv-1.x style (indice_pairs (2,K,N), indice_num (K)) from a neighbour table."""
+    lib = _lib.load()
+    K, cap = nbr.shape
+    pairs = torch.empty((2, K, cap), dtype=torch.int32, device=nbr.device)
+    num = torch.empty(K, dtype=torch.int32, device=nbr.device)
+    _lib.check(lib.u3d_rulebook_pairs(_p(nbr), nbr.stride(0), _p(n_out), K, _p(pairs[0]),
+                                      _p(pairs[1]), cap, _p(num), _stream()))
+    return pairs, num
+
+
+def spconv_fwd(x, nbr, n_out, out_cap, w, scale=None, shift=None, residual=None, relu=False,
+               out=None, impl=0):
+    """out = act((sum_k x[nbr[k]] @ w[k]) * scale + shift (+ residual)); w is (K,Cin,Cout)."""
+    lib = _lib.load()
+    _req(x, None, "x")
+    dt = _DT[x.dtype]
+    K, Cin, Cout = w.shape
+    _req(w, x.dtype, "w")
+    if out is None:
+        out = torch.empty((out_cap, Cout), dtype=x.dtype, device=x.device)
+    stride = nbr.stride(0) if nbr is not None else 0
+    _lib.check(lib.u3d_spconv_fwd(_p(x), _p(nbr), stride, _p(n_out), out_cap, K, _p(w), _p(scale),
+                                  _p(shift), _p(residual), int(bool(relu)), _p(out), Cin, Cout, dt,
+                                  impl, _stream()))
+    return out
+
+
+def sparse_to_dense(feats, coors, n_rows, cap, B, dims, channels_last=True, out=None):
+    lib = _lib.load()
+    D, H, W = [int(v) for v in dims]
+    C = feats.shape[1]
+    if out is None:
+        shape = (B, D, H, W, C) if channels_last else (B, C, D, H, W)
+        out = torch.empty(shape, dtype=feats.dtype, device=feats.device)
+    _lib.check(lib.u3d_sparse_to_dense(_p(feats), _p(coors), _p(n_rows), cap, B, D, H, W, C,
+                                       _DT[feats.dtype], int(bool(channels_last)), _p(out),
+                                       _stream()))
+    return out
+
+
+def fps(dist_src, dist_stride, dist_seg_stride, gather_src, gather_stride, seg, B, max_n, nq,
+        reverse=False):
+    """Batched D-FPS + gather + min-max normalise. Returns (idx (B,nq) int32, pts (B,nq,3) f32)."""
+    lib = _lib.load()
+    _req(dist_src, torch.float32, "dist_src")
+    _req(gather_src, torch.float32, "gather_src")
+    _req(seg, torch.int32, "seg")
+    idx = torch.empty((B, nq), dtype=torch.int32, device=dist_src.device)
+    out = torch.empty((B, nq, 3), dtype=torch.float32, device=dist_src.device)
+    _lib.check(lib.u3d_fps(_p(dist_src), dist_stride, dist_seg_stride, _p(gather_src),
+                           gather_stride, _p(seg), B, int(max_n), nq, int(bool(reverse)), _p(idx),
+                           _p(out), _stream()))
+    return idx, out
+
+
+def coors_to_float(coors, rows=None):
+    lib = _lib.load()
+    rows = coors.shape[0] if rows is None else rows
+    out = torch.empty((coors.shape[0], 3), dtype=torch.float32, device=coors.device)
+    _lib.check(lib.u3d_coors_to_float(_p(coors), rows, _p(out), _stream()))
+    return out
+
+
+def sine_embed(ref, dtype=torch.float32):
+    lib = _lib.load()
+    _req(ref, torch.float32, "ref")
+    rows = ref.numel() // 3
+    out = torch.empty(ref.shape[:-1] + (384,), dtype=dtype, device=ref.device)
+    _lib.check(lib.u3d_sine_embed(_p(ref), rows, _p(out), _DT[dtype], _stream()))
+    return out
+
+
+def mha_core(q, k, v, n_seq, seq_len, heads):
+    """q,k,v: 2-D views (n_seq*seq_len, heads*32), unit stride in dim 1 (row strides may differ,
+    e.g. column slices of a packed QK projection). Returns (n_seq*seq_len, heads*32)."""
+    lib = _lib.load()
+    for t in (q, k, v):
+        if t.stride(1) != 1 or t.dtype != q.dtype or not t.is_cuda:
+            raise _lib.U3DError("mha_core: q,k,v must be CUDA, same dtype, unit-stride in dim 1")
+    out = torch.empty((n_seq * seq_len, heads * 32), dtype=q.dtype, device=q.device)
+    _lib.check(lib.u3d_mha_core(_p(q), _p(k), _p(v), q.stride(0), k.stride(0), v.stride(0), n_seq,
+                                seq_len, heads, _p(out), _DT[q.dtype], _stream()))
+    return out
+
+
+def cross_sample(value_ndhwc, ref, query, query_pos, gate_w, gate_b, Q):
+    lib = _lib.load()
+    B, D, H, W, C = value_ndhwc.shape
+    _req(value_ndhwc, None, "value")
+    _req(ref, torch.float32, "ref")
+    _req(query, value_ndhwc.dtype, "query")
+    out = torch.empty((B * Q, C), dtype=value_ndhwc.dtype, device=value_ndhwc.device)
+    _lib.check(lib.u3d_cross_sample(_p(value_ndhwc), B, D, H, W, C, _p(ref), _p(query),
+                                    _p(query_pos), _p(gate_w), float(gate_b), Q, _p(out),
+                                    _DT[value_ndhwc.dtype], _stream()))
+    return out

@@ -1,0 +1,152 @@
+"""Uni3DETR detector drop-in (reference: projects/mmdet3d_plugin/models/detectors/uni3detr.py).
+
+Same registry name, constructor keys and call convention
+(``model(return_loss=False, points=[[...]], img_metas=[[...]])``). ``extract_pts_feat``
+follows uni3detr.py:143-190 step for step but batched and without host round trips:
+one voxelization launch sequence for the whole batch (VFE mean fused), the sparse encoder
+on shared rulebooks, the dense CNN on cuDNN, and both furthest-point samplings of all
+scenes in two cluster launches that run on a side stream concurrently with the encoder.
+"""
+import torch
+from torch import nn
+
+from .. import ops
+from ..compat import (BACKBONES, DETECTORS, HEADS, MIDDLE_ENCODERS, NECKS, VOXEL_ENCODERS,
+                      build_from_cfg)
+from .voxel import Voxelization
+
+
+@DETECTORS.register_module()
+class Uni3DETR(nn.Module):
+    def __init__(self, dynamic_voxelization=False, use_grid_mask=False, pts_voxel_layer=None,
+                 pts_voxel_encoder=None, pts_middle_encoder=None, pts_fusion_layer=None,
+                 pts_backbone=None, pts_neck=None, pts_bbox_head=None, train_cfg=None,
+                 test_cfg=None, pretrained=None, init_cfg=None):
+        super().__init__()
+        if pts_fusion_layer is not None:
+            raise NotImplementedError("pts_fusion_layer belongs to the multi-modal family")
+        self.dynamic_voxelization = dynamic_voxelization
+        self.pts_voxel_layer = Voxelization(**pts_voxel_layer)
+        self.pts_voxel_encoder = build_from_cfg(dict(pts_voxel_encoder), VOXEL_ENCODERS)
+        self.pts_middle_encoder = build_from_cfg(dict(pts_middle_encoder), MIDDLE_ENCODERS)
+        self.pts_backbone = build_from_cfg(dict(pts_backbone), BACKBONES) if pts_backbone else None
+        self.pts_neck = build_from_cfg(dict(pts_neck), NECKS) if pts_neck else None
+        head = dict(pts_bbox_head)
+        head.setdefault("train_cfg", train_cfg.get("pts") if train_cfg else None)
+        head.setdefault("test_cfg", test_cfg.get("pts") if test_cfg else None)
+        self.pts_bbox_head = build_from_cfg(head, HEADS)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.pts_fp16 = hasattr(self.pts_middle_encoder, "fp16_enabled")
+        self.num_query = pts_bbox_head["num_query"]
+        # the reference hands the (1,N,C) cloud to a sampler that strides by 3.
+        self.fps_stride_quirk = True
+        self._fps_stream = None
+        self.compute_dtype = torch.float32
+
+    # ------------------------------------------------------------------ config ---
+    @property
+    def with_pts_backbone(self):
+        return self.pts_backbone is not None
+
+    @property
+    def with_pts_neck(self):
+        return self.pts_neck is not None
+
+    def init_weights(self):
+        return
+
+    def set_compute_dtype(self, dtype):
+        """fp32 (parity, BASELINE config 3/5) or bf16 (config 2/4) for everything after the VFE."""
+        self.compute_dtype = dtype
+        self.pts_middle_encoder.compute_dtype = dtype
+        self.pts_middle_encoder.invalidate()
+        for m in (self.pts_backbone, self.pts_neck):
+            if m is not None:
+                m.compute_dtype = dtype
+                m.invalidate()
+        self.pts_bbox_head.set_compute_dtype(dtype)
+        return self
+
+    # ---------------------------------------------------------------- hot path ---
+    @torch.no_grad()
+    def extract_pts_feat(self, pts):
+        """list[B] of (N_i,C) f32 -> x (B,256,D,H,W), fpsbpts (B,2nq,3) in [0,1]."""
+        B = len(pts)
+        nq = self.num_query
+        points, pt_off, lens, vox = self.pts_voxel_layer.batched(pts)
+        C = points.shape[1]
+        cur = torch.cuda.current_stream()
+        if self._fps_stream is None:
+            self._fps_stream = torch.cuda.Stream(device=points.device)
+        side = self._fps_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            # FPS #1 on the raw points (uni3detr.py:178-181)
+            ds = 3 if self.fps_stride_quirk else C
+            _, fps1 = ops.fps(points, ds, C, points, C, pt_off, B, max(lens), nq, reverse=False)
+            # FPS #2 on voxel coordinates (uni3detr.py:183-187): hard -> input voxel coords;
+            # dynamic -> the per-point coords (including -1 rows), as the reference does
+            if self.dynamic_voxelization:
+                cf = ops.coors_to_float(vox.pt_coors)
+                seg, max_n = pt_off, max(lens)
+            else:
+                cf = ops.coors_to_float(vox.coors)
+                seg = vox.scene_rows
+                mv = self.pts_voxel_layer.current_max_voxels()
+                max_n = max(min(n, mv) if mv > 0 else n for n in lens)
+            _, fps2 = ops.fps(cf, 3, 3, cf, 3, seg, B, max_n, nq, reverse=True)
+            fpsbpts = torch.cat([fps1, fps2], 1)
+        x = self.pts_middle_encoder.forward_voxels(vox.feats, vox.coors, vox.n_rows, vox.cap,
+                                                   vox.vmap, B)
+        if self.with_pts_backbone:
+            x = self.pts_backbone(x)
+        if self.with_pts_neck:
+            x = self.pts_neck(x)
+        cur.wait_stream(side)
+        for t in (points, pt_off, vox.coors, vox.scene_rows, vox.pt_coors):
+            if t is not None:
+                t.record_stream(side)   # allocated on `cur`, read on the side stream
+        fpsbpts.record_stream(cur)      # allocated on the side stream, read on `cur`
+        return x, fpsbpts
+
+    def forward(self, return_loss=True, **kwargs):
+        if return_loss:
+            return self.forward_train(**kwargs)
+        return self.forward_test(**kwargs)
+
+    def forward_train(self, points=None, img_metas=None, gt_bboxes_3d=None, gt_labels_3d=None,
+                      **kwargs):
+        raise NotImplementedError(
+            "Uni3DETR.forward_train: backward kernels, matcher and losses are 'next' rows "
+            "(SURVEY.md 8f ranks 2-3); this build covers the inference forward")
+
+    def forward_test(self, img_metas, points=None, **kwargs):
+        if not isinstance(img_metas, list):
+            raise TypeError("img_metas must be a list, but got {}".format(type(img_metas)))
+        num_augs = len(img_metas)
+        if points is not None and num_augs != len(points):
+            raise ValueError("num of augmentations ({}) != num of image meta ({})".format(
+                len(points), len(img_metas)))
+        if num_augs != 1:
+            raise NotImplementedError("aug_test is unfinished in the reference (uni3detr.py:318)")
+        if not isinstance(img_metas[0], list):
+            img_metas = [img_metas]
+        return self.simple_test(img_metas[0], points[0] if isinstance(points[0], (list, tuple))
+                                else points, **kwargs)
+
+    @torch.no_grad()
+    def simple_test(self, img_metas, points=None, rescale=False):
+        pts_feat, fpsbpts = self.extract_pts_feat(points)
+        outs = self.pts_bbox_head(pts_feat, img_metas, fpsbpts)
+        bbox_list = self.pts_bbox_head.get_bboxes(outs, img_metas, rescale=rescale)
+        results = []
+        for bboxes, scores, labels in bbox_list:
+            boxes = bboxes.to("cpu") if hasattr(bboxes, "to") else bboxes
+            results.append(dict(boxes_3d=boxes, scores_3d=scores.cpu(), labels_3d=labels.cpu()))
+        return results
+
+    @torch.no_grad()
+    def forward_raw(self, points, random_point=None):
+        """Hot path only (no CPU post-processing): returns the head's prediction dict."""
+        pts_feat, fpsbpts = self.extract_pts_feat(points)
+        return self.pts_bbox_head(pts_feat, None, fpsbpts, random_point=random_point), fpsbpts

@@ -1,0 +1,253 @@
+"""Uni3DETRHead + NMSFreeCoder drop-ins.
+
+References: projects/mmdet3d_plugin/models/dense_heads/uni3detr_head.py:311-508 (forward),
+projects/mmdet3d_plugin/core/bbox/coders/nms_free_coder.py:9-136,
+projects/mmdet3d_plugin/core/bbox/util.py:44-80 (denormalize_bbox, mmdet3d>=1.0 branch).
+Loss / assigner / NMS post-processing are "next" rows and not built here.
+"""
+import copy
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..compat import BBOX_CODERS, HEADS, TRANSFORMER, build_from_cfg
+from .transformer import _run_mlp, _wb, inverse_sigmoid
+
+
+def denormalize_bbox(normalized_bboxes, pc_range=None):
+    """core/bbox/util.py:44-80 with __mmdet3d_version__ >= 1.0 (the pinned v1.0.0rc5)."""
+    rot = torch.atan2(normalized_bboxes[..., 6:7], normalized_bboxes[..., 7:8])
+    rot = -rot - np.pi / 2
+    cx, cy, cz = normalized_bboxes[..., 0:1], normalized_bboxes[..., 1:2], normalized_bboxes[..., 4:5]
+    w = normalized_bboxes[..., 2:3].exp()
+    l = normalized_bboxes[..., 3:4].exp()
+    h = normalized_bboxes[..., 5:6].exp()
+    if normalized_bboxes.size(-1) > 8:
+        vx, vy = normalized_bboxes[..., 8:9], normalized_bboxes[..., 9:10]
+        return torch.cat([cx, cy, cz, l, w, h, rot, vx, vy], dim=-1)
+    return torch.cat([cx, cy, cz, l, w, h, rot], dim=-1)
+
+
+@BBOX_CODERS.register_module()
+class NMSFreeCoder:
+    def __init__(self, pc_range, voxel_size=None, post_center_range=None, max_num=100,
+                 score_threshold=None, alpha=0.5, num_classes=10):
+        self.pc_range = pc_range
+        self.voxel_size = voxel_size
+        self.post_center_range = post_center_range
+        self.max_num = max_num
+        self.score_threshold = score_threshold
+        self.num_classes = num_classes
+        self.alpha = alpha
+
+    def encode(self):
+        pass
+
+    def decode_single(self, cls_scores, bbox_preds, all_iou_preds):
+        cls_scores = cls_scores.sigmoid()
+        scores, indexs = cls_scores.view(-1).topk(self.max_num)
+        labels = indexs % self.num_classes
+        bbox_index = torch.div(indexs, self.num_classes, rounding_mode="floor")
+        bbox_preds = bbox_preds[bbox_index]
+        final_box_preds = denormalize_bbox(bbox_preds, self.pc_range)
+        final_ious = all_iou_preds.sigmoid()[bbox_index]
+        if self.post_center_range is None:
+            raise NotImplementedError("Need to reorganize output as a batch, only support "
+                                      "post_center_range is not None for now!")
+        pcr = scores.new_tensor(self.post_center_range)
+        mask = (final_box_preds[..., :3] >= pcr[:3]).all(1)
+        mask &= (final_box_preds[..., :3] <= pcr[3:]).all(1)
+        if self.score_threshold:
+            mask &= scores > self.score_threshold
+        ious = final_ious[mask].reshape(-1)
+        s = scores[mask]
+        return {"bboxes": final_box_preds[mask],
+                "scores": s ** self.alpha * ious ** (1 - self.alpha),
+                "labels": labels[mask], "ious": ious}
+
+    def decode(self, preds_dicts):
+        cls = torch.mean(preds_dicts["all_cls_scores"][1:].float(), 0)
+        box = torch.mean(preds_dicts["all_bbox_preds"][1:].float(), 0)
+        iou = torch.mean(preds_dicts["all_iou_preds"][1:].float(), 0)
+        return [self.decode_single(cls[i], box[i], iou[i]) for i in range(cls.size(0))]
+
+
+@HEADS.register_module()
+class Uni3DETRHead(nn.Module):
+    def __init__(self, num_classes, in_channels, num_query=100, num_reg_fcs=2, transformer=None,
+                 sync_cls_avg_factor=False, positional_encoding=None, loss_cls=None, loss_bbox=None,
+                 loss_iou=None, train_cfg=None, test_cfg=None, init_cfg=None,
+                 with_box_refine=False, as_two_stage=False, bbox_coder=None, num_cls_fcs=2,
+                 code_weights=None, post_processing=None, gt_repeattimes=1, code_size=None, **kwargs):
+        super().__init__()
+        if as_two_stage:
+            raise NotImplementedError("as_two_stage is not used by any Uni3DETR config")
+        self.with_box_refine, self.as_two_stage = with_box_refine, as_two_stage
+        self.code_size = code_size if code_size is not None else 10
+        cw = code_weights if code_weights is not None else \
+            [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.2, 0.2]
+        self.bbox_coder = build_from_cfg(dict(bbox_coder), BBOX_CODERS)
+        self.pc_range = self.bbox_coder.pc_range
+        self.num_cls_fcs = num_cls_fcs - 1
+        self.num_classes, self.in_channels, self.num_query = num_classes, in_channels, num_query
+        self.num_reg_fcs = num_reg_fcs
+        self.sync_cls_avg_factor = sync_cls_avg_factor
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.loss_cfgs = dict(loss_cls=loss_cls, loss_bbox=loss_bbox, loss_iou=loss_iou)
+        use_sigmoid = bool((loss_cls or {}).get("use_sigmoid", False))
+        self.cls_out_channels = num_classes if use_sigmoid else num_classes + 1
+        self.use_sigmoid_cls = use_sigmoid
+        self.transformer = build_from_cfg(dict(transformer), TRANSFORMER)
+        self.embed_dims = self.transformer.embed_dims
+        self.code_weights = nn.Parameter(torch.tensor(cw), requires_grad=False)
+        self.fp16_enabled = False
+        self.post_processing = post_processing
+        self.gt_repeattimes = gt_repeattimes
+        self.compute_dtype = torch.float32
+        self._plan = None
+        self._rng = None  # optional torch.Generator for the test-time random query group
+        self._init_layers()
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
+
+    def _init_layers(self):
+        E = self.embed_dims
+        cls_branch = []
+        for _ in range(self.num_reg_fcs):
+            cls_branch += [nn.Linear(E, E), nn.LayerNorm(E), nn.ReLU(inplace=True)]
+        cls_branch.append(nn.Linear(E, self.cls_out_channels))
+        fc_cls = nn.Sequential(*cls_branch)
+        reg_branch = []
+        for _ in range(self.num_reg_fcs):
+            reg_branch += [nn.Linear(E, E), nn.ReLU()]
+        reg_branch.append(nn.Linear(E, self.code_size))
+        reg_branch = nn.Sequential(*reg_branch)
+        iou_branch = []
+        for _ in range(self.num_reg_fcs):
+            iou_branch += [nn.Linear(E, E), nn.ReLU()]
+        iou_branch.append(nn.Linear(E, 1))
+        iou_branch = nn.Sequential(*iou_branch)
+        num_pred = self.transformer.decoder.num_layers
+        if self.with_box_refine:
+            clone = lambda m: nn.ModuleList([copy.deepcopy(m) for _ in range(num_pred)])
+            self.cls_branches, self.reg_branches, self.iou_branches = \
+                clone(fc_cls), clone(reg_branch), clone(iou_branch)
+        else:
+            self.cls_branches = nn.ModuleList([fc_cls for _ in range(num_pred)])
+            self.reg_branches = nn.ModuleList([reg_branch for _ in range(num_pred)])
+            self.iou_branches = nn.ModuleList([iou_branch for _ in range(num_pred)])
+        self.tgt_embed = nn.Embedding(self.num_query * 2, E)
+        self.refpoint_embed = nn.Embedding(self.num_query, 3)
+
+    def init_weights(self):
+        self.transformer.init_weights()
+        if self.use_sigmoid_cls:
+            bias_init = float(-math.log((1 - 0.01) / 0.01))
+            for m in self.cls_branches:
+                nn.init.constant_(m[-1].bias, bias_init)
+
+    def invalidate(self):
+        self._plan = None
+
+    def train(self, mode=True):
+        self._plan = None
+        return super().train(mode)
+
+    def set_compute_dtype(self, dtype):
+        self.compute_dtype = dtype
+        self.transformer.decoder.compute_dtype = dtype
+        self.invalidate()
+        self.transformer.decoder.invalidate()
+
+    @torch.no_grad()
+    def prepare(self):
+        dt = self.compute_dtype
+        lin = lambda br: [_wb(m, dt) for m in br if isinstance(m, nn.Linear)]
+        cls = []
+        for br in self.cls_branches:
+            lns = [(m.weight.detach().to(dt), m.bias.detach().to(dt), m.eps)
+                   for m in br if isinstance(m, nn.LayerNorm)]
+            cls.append(dict(lin=lin(br), ln=lns))
+        self._plan = dict(dtype=dt, cls=cls, reg=[lin(b) for b in self.reg_branches],
+                          iou=[lin(b) for b in self.iou_branches])
+        return self._plan
+
+    def build_queries(self, fpsbpts, train_mode, random_point=None):
+        """uni3detr_head.py:437-449 - mixed queries: learned + 2 FPS groups (+ random at test)."""
+        nq, bs = self.num_query, fpsbpts.shape[0]
+        tgt = self.tgt_embed.weight
+        refanchor = self.refpoint_embed.weight
+        if train_mode:
+            tgt = torch.cat([tgt[0:nq], tgt[nq:], tgt[nq:]])
+            refs = torch.cat([refanchor.unsqueeze(0).expand(bs, -1, -1), inverse_sigmoid(fpsbpts)], 1)
+        else:
+            if random_point is None:
+                random_point = torch.rand(fpsbpts.shape, device=fpsbpts.device,
+                                          generator=self._rng)[:, :nq, :]
+            tgt = torch.cat([tgt[0:nq], tgt[nq:], tgt[nq:], tgt[nq:]])
+            refs = torch.cat([refanchor.unsqueeze(0).expand(bs, -1, -1), inverse_sigmoid(fpsbpts),
+                              inverse_sigmoid(random_point)], 1)
+        return torch.cat([tgt.unsqueeze(0).expand(bs, -1, -1), refs], -1)
+
+    @torch.no_grad()
+    def forward(self, pts_feats, img_metas, fpsbpts, random_point=None):
+        """pts_feats (B,C,D,H,W); fpsbpts (B,2nq,3) in [0,1]. Returns the reference's dict of
+        all_cls_scores (L,B,Q,cls), all_bbox_preds (L,B,Q,code), all_iou_preds (L,B,Q,1), fp32."""
+        p = self._plan
+        if p is None or p["dtype"] != self.compute_dtype:
+            p = self.prepare()
+        dt = p["dtype"]
+        query_embeds = self.build_queries(fpsbpts.float(), pts_feats.requires_grad, random_point)
+        if pts_feats.dim() == 5:
+            pts_feats = pts_feats.unsqueeze(1)
+        hs, init_reference, inter_references = self.transformer(
+            pts_feats, query_embeds, self.num_query,
+            reg_plans=p["reg"] if self.with_box_refine else None, img_metas=img_metas)
+        hs = hs.permute(0, 2, 1, 3)  # (L,B,Q,E)
+        E = self.embed_dims
+        pc = self.pc_range
+        classes, coords, ious = [], [], []
+        for lvl in range(hs.shape[0]):
+            reference = init_reference if lvl == 0 else inter_references[lvl - 1]
+            reference = inverse_sigmoid(reference)
+            x = hs[lvl]
+            c = x
+            cp = p["cls"][lvl]
+            for i, (w, b) in enumerate(cp["lin"][:-1]):
+                c = torch.relu_(F.layer_norm(F.linear(c, w, b), (E,), *cp["ln"][i]))
+            outputs_class = F.linear(c, *cp["lin"][-1]).float()
+            tmp = _run_mlp(x, p["reg"][lvl]).float()
+            outputs_iou = _run_mlp(x, p["iou"][lvl]).float()
+            assert reference.shape[-1] == 3
+            xy = (tmp[..., 0:2] + reference[..., 0:2]).sigmoid()
+            z = (tmp[..., 4:5] + reference[..., 2:3]).sigmoid()
+            cx = xy[..., 0:1] * (pc[3] - pc[0]) + pc[0]
+            cy = xy[..., 1:2] * (pc[4] - pc[1]) + pc[1]
+            cz = z * (pc[5] - pc[2]) + pc[2]
+            coords.append(torch.cat([cx, cy, tmp[..., 2:4], cz, tmp[..., 5:]], dim=-1))
+            classes.append(outputs_class)
+            ious.append(outputs_iou)
+        return {"all_cls_scores": torch.stack(classes), "all_bbox_preds": torch.stack(coords),
+                "all_iou_preds": torch.stack(ious)}
+
+    def loss(self, *args, **kwargs):
+        raise NotImplementedError("Uni3DETRHead.loss (Hungarian matching + SoftFocal/IoU3D losses) "
+                                  "is a 'next' row, SURVEY.md 8f rank 3")
+
+    @torch.no_grad()
+    def get_bboxes(self, preds_dicts, img_metas, rescale=False):
+        """NMSFreeCoder.decode + gravity-centre -> bottom-centre shift (uni3detr_head.py:827-843).
+        The per-class NMS / box-merging that follows in the reference is a 'next' row."""
+        preds = self.bbox_coder.decode(preds_dicts)
+        ret = []
+        for i, pr in enumerate(preds):
+            bboxes = pr["bboxes"].clone()
+            bboxes[:, 2] = bboxes[:, 2] - bboxes[:, 5] * 0.5
+            meta = img_metas[i] if img_metas is not None and i < len(img_metas) else {}
+            box_type = meta.get("box_type_3d") if isinstance(meta, dict) else None
+            if box_type is not None:
+                bboxes = box_type(bboxes, bboxes.shape[-1])
+            ret.append([bboxes, pr["scores"], pr["labels"]])
+        return ret

@@ -1,0 +1,226 @@
+"""SECOND3D / SECOND3DFPN drop-ins (reference: models/backbones/second_3d.py,
+models/necks/second3d_fpn.py).
+
+The dense 3-D CNN between the sparse encoder and the decoder stays on the library path
+(cuDNN through torch), as SURVEY.md §0.4 / §8a rows a9-a10 prescribe; what changes is how it
+is driven: eval-mode BatchNorm3d folded into the conv weights, bf16 (or fp32) NDHWC
+(`channels_last_3d`) activations end to end so no layout transposes are inserted, and the
+(1,3,3) convs of SECOND3D issued as NHWC 2-D convs over (B*D) slices (same memory, no copy).
+Parameter names match the reference (``blocks.{i}.{0,3,..}.weight``, ``deblocks.{i}.0.weight``,
+``extra_blocks.{0,3,6}.weight``).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..compat import BACKBONES, NECKS
+
+
+def _norm(norm_cfg, ch):
+    t = norm_cfg.get("type", "BN3d")
+    if t not in ("BN3d", "BN", "naiveSyncBN3d"):
+        raise NotImplementedError(f"norm type {t}")
+    return nn.BatchNorm3d(ch, eps=norm_cfg.get("eps", 1e-5), momentum=norm_cfg.get("momentum", 0.1))
+
+
+def _fold(conv_w, bn, transposed=False):
+    scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    shift = bn.bias.float() - bn.running_mean.float() * scale
+    w = conv_w.float()
+    w = w * (scale.view(1, -1, 1, 1, 1) if transposed else scale.view(-1, 1, 1, 1, 1))
+    return w, shift
+
+
+class _FoldedConv:
+    """conv(+folded BN)+ReLU on channels_last_3d tensors."""
+
+    def __init__(self, conv, bn, dtype, as2d):
+        transposed = isinstance(conv, nn.ConvTranspose3d)
+        w, b = _fold(conv.weight.detach(), bn, transposed)
+        self.transposed = transposed
+        self.stride, self.padding = conv.stride, conv.padding
+        self.b = b.to(dtype).contiguous()
+        k = conv.kernel_size
+        self.as2d = bool(as2d and k[0] == 1 and conv.stride[0] == 1 and conv.padding[0] == 0)
+        if self.as2d:
+            self.w = w[:, :, 0].to(dtype).contiguous(memory_format=torch.channels_last)
+        else:
+            self.w = w.to(dtype).contiguous(memory_format=torch.channels_last_3d)
+
+    def __call__(self, x):
+        if self.as2d:
+            B, C, D, H, W = x.shape
+            x2 = x.permute(0, 2, 1, 3, 4).reshape(B * D, C, H, W)  # view on NDHWC memory
+            if self.transposed:
+                y = F.conv_transpose2d(x2, self.w, self.b, stride=self.stride[1:])
+            else:
+                y = F.conv2d(x2, self.w, self.b, stride=self.stride[1:], padding=self.padding[1:])
+            y = torch.relu_(y)
+            return y.reshape(B, D, y.shape[1], y.shape[2], y.shape[3]).permute(0, 2, 1, 3, 4)
+        if self.transposed:
+            y = F.conv_transpose3d(x, self.w, self.b, stride=self.stride)
+        else:
+            y = F.conv3d(x, self.w, self.b, stride=self.stride, padding=self.padding)
+        return torch.relu_(y)
+
+
+def _fold_sequential(seq, dtype, as2d):
+    mods = list(seq)
+    out, i = [], 0
+    while i < len(mods):
+        conv = mods[i]
+        assert isinstance(conv, (nn.Conv3d, nn.ConvTranspose3d)), type(conv)
+        assert isinstance(mods[i + 1], nn.BatchNorm3d) and isinstance(mods[i + 2], nn.ReLU)
+        out.append(_FoldedConv(conv, mods[i + 1], dtype, as2d))
+        i += 3
+    return out
+
+
+class _PlanMixin:
+    compute_dtype = torch.float32
+    conv2d_trick = True
+
+    def invalidate(self):
+        self._plan = None
+
+    def train(self, mode=True):
+        self._plan = None
+        return super().train(mode)
+
+
+@BACKBONES.register_module()
+class SECOND3D(_PlanMixin, nn.Module):
+    def __init__(self, in_channels=128, out_channels=[128, 128, 256], layer_nums=[3, 5, 5],
+                 layer_strides=[2, 2, 2], is_cascade=True,
+                 norm_cfg=dict(type="BN3d", eps=1e-3, momentum=0.01),
+                 conv_cfg=dict(type="Conv3d", bias=False), init_cfg=None, pretrained=None):
+        super().__init__()
+        assert len(layer_strides) == len(layer_nums) == len(out_channels)
+        conv_cfg = dict(conv_cfg)
+        self.kernel_type = conv_cfg.get("type", "Conv3d")
+        if self.kernel_type != "Conv3d":
+            raise NotImplementedError("SECOND3D: only conv_cfg.type='Conv3d' (all shipped configs)")
+        kernel = tuple(conv_cfg.pop("kernel", (1, 3, 3)))
+        bias = conv_cfg.get("bias", False)
+        in_filters = list(in_channels) if isinstance(in_channels, (list, tuple)) \
+            else [in_channels, *out_channels[:-1]]
+        padding = tuple((k - 1) // 2 for k in kernel)
+        self.is_cascade = is_cascade
+        blocks = []
+        for i, layer_num in enumerate(layer_nums):
+            block = [nn.Conv3d(in_filters[i], out_channels[i], kernel,
+                               stride=(1, layer_strides[i], layer_strides[i]), padding=padding,
+                               bias=bias),
+                     _norm(norm_cfg, out_channels[i]), nn.ReLU(inplace=True)]
+            for _ in range(layer_num):
+                block += [nn.Conv3d(out_channels[i], out_channels[i], kernel, padding=padding,
+                                    bias=bias),
+                          _norm(norm_cfg, out_channels[i]), nn.ReLU(inplace=True)]
+            blocks.append(nn.Sequential(*block))
+        self.blocks = nn.ModuleList(blocks)
+        self._plan = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    @torch.no_grad()
+    def prepare(self):
+        self._plan = dict(dtype=self.compute_dtype, as2d=self.conv2d_trick,
+                          blocks=[_fold_sequential(b, self.compute_dtype, self.conv2d_trick)
+                                  for b in self.blocks])
+        return self._plan
+
+    @torch.no_grad()
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError("SECOND3D: training-mode BN is a 'next' row; call .eval()")
+        p = self._plan
+        if p is None or p["dtype"] != self.compute_dtype or p["as2d"] != self.conv2d_trick:
+            p = self.prepare()
+        x = x.to(self.compute_dtype).contiguous(memory_format=torch.channels_last_3d)
+        outs = []
+        for blk in p["blocks"]:
+            y = x
+            for conv in blk:
+                y = conv(y)
+            outs.append(y)
+            if self.is_cascade:
+                x = y
+        return tuple(outs)
+
+
+@NECKS.register_module()
+class SECOND3DFPN(_PlanMixin, nn.Module):
+    def __init__(self, in_channels=[128, 128, 256], out_channels=[256, 256, 256],
+                 upsample_strides=[1, 2, 4], norm_cfg=dict(type="BN3d", eps=1e-3, momentum=0.01),
+                 upsample_cfg=dict(type="deconv3d", bias=False),
+                 conv_cfg=dict(type="Conv3d", bias=False), extra_conv=None,
+                 use_conv_for_no_stride=False, use_for_distill=False, init_cfg=None):
+        super().__init__()
+        assert len(out_channels) == len(upsample_strides) == len(in_channels)
+        if "3d" not in upsample_cfg.get("type", "deconv3d") or "3d" not in conv_cfg.get("type", "Conv3d"):
+            raise NotImplementedError("SECOND3DFPN: only the 3-D layer types of the shipped configs")
+        if use_for_distill:
+            raise NotImplementedError("use_for_distill belongs to the OV-Uni3DETR family (out of scope)")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.fp16_enabled = False
+        deblocks = []
+        for i, oc in enumerate(out_channels):
+            stride = upsample_strides[i]
+            if stride > 1 or (stride == 1 and not use_conv_for_no_stride):
+                layer = nn.ConvTranspose3d(in_channels[i], oc, (1, stride, stride),
+                                           stride=(1, stride, stride),
+                                           bias=upsample_cfg.get("bias", False))
+            else:
+                s = int(np.round(1 / stride))
+                layer = nn.Conv3d(in_channels[i], oc, (1, s, s), stride=(1, s, s),
+                                  bias=conv_cfg.get("bias", False))
+            deblocks.append(nn.Sequential(layer, _norm(norm_cfg, oc), nn.ReLU(inplace=True)))
+        self.deblocks = nn.ModuleList(deblocks)
+        self.extra_conv = dict(extra_conv) if extra_conv is not None else None
+        if self.extra_conv is not None:
+            ec = dict(self.extra_conv)
+            self.layer_num = ec.pop("num_conv")
+            kernel = tuple(ec.pop("kernel", (3, 3, 3)))
+            if "sep_kernel" in ec:
+                raise NotImplementedError("sep_kernel is not used by any Uni3DETR config")
+            padding = tuple((k - 1) // 2 for k in kernel)
+            blocks = []
+            for _ in range(self.layer_num):
+                blocks += [nn.Conv3d(out_channels[-1], out_channels[-1], kernel, padding=padding,
+                                     bias=ec.get("bias", False)),
+                           _norm(norm_cfg, out_channels[-1]), nn.ReLU(inplace=True)]
+            self.extra_blocks = nn.Sequential(*blocks)
+        self._plan = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
+        for m in self.modules():
+            if isinstance(m, (nn.Conv3d, nn.ConvTranspose3d)):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    @torch.no_grad()
+    def prepare(self):
+        dt, a2 = self.compute_dtype, self.conv2d_trick
+        self._plan = dict(dtype=dt, as2d=a2,
+                          deblocks=[_fold_sequential(d, dt, a2)[0] for d in self.deblocks],
+                          extra=_fold_sequential(self.extra_blocks, dt, a2)
+                          if self.extra_conv is not None else [])
+        return self._plan
+
+    @torch.no_grad()
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError("SECOND3DFPN: training-mode BN is a 'next' row; call .eval()")
+        assert len(x) == len(self.in_channels)
+        p = self._plan
+        if p is None or p["dtype"] != self.compute_dtype or p["as2d"] != self.conv2d_trick:
+            p = self.prepare()
+        ups = [d(xi.to(self.compute_dtype).contiguous(memory_format=torch.channels_last_3d))
+               for d, xi in zip(p["deblocks"], x)]
+        out = ups[0]
+        for u in ups[1:]:
+            out = out + u
+        for conv in p["extra"]:
+            out = conv(out)
+        return out

@@ -1,0 +1,276 @@
+"""SparseEncoderHD drop-in (reference: projects/mmdet3d_plugin/models/pts_encoder/sparse_encoder_hd.py).
+
+Same registry name, constructor keys and parameter names
+(``conv_input.0.weight``, ``encoder_layers.encoder_layer{i}.{j}.conv1.weight`` ...,
+SURVEY.md Appendix B; weights in the spconv-1.x layout (kz,ky,kx,Cin,Cout), the 2.x layout
+(Cout,kz,ky,kx,Cin) is converted on load). The forward is a different program:
+
+* geometry phase - one rulebook per *resolution* (4 SubM neighbour tables + 3 strided
+  rulebooks) instead of one per conv (the reference rebuilds it for each of the 17 SubM
+  convs because SparseBasicBlock carries no indice_key);
+* feature phase - 21 fused gather-GEMM launches (BN(eval) folded to scale/shift, ReLU and
+  the basic-block identity add in the epilogue), no per-layer host sync;
+* ``dense()`` writes NDHWC directly (what the dense CNN and the cross-attention read).
+"""
+import math
+
+import torch
+from torch import nn
+
+from .. import ops
+from ..compat import MIDDLE_ENCODERS
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == 3
+        return tuple(int(x) for x in v)
+    return (int(v),) * 3
+
+
+class _SparseConvBase(nn.Module):
+    subm = False
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=False,
+                 indice_key=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = _triple(kernel_size)
+        self.stride, self.padding = _triple(stride), _triple(padding)
+        self.indice_key = indice_key
+        if self.kernel_size not in ((3, 3, 3), (1, 1, 1)):
+            raise NotImplementedError("sparse conv kernel sizes other than 1 and 3")
+        self.weight = nn.Parameter(torch.empty(*self.kernel_size, in_channels, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        fan_in = in_channels * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        bound = math.sqrt(6.0 / ((1 + 5.0) * fan_in))  # kaiming_uniform(a=sqrt(5))
+        nn.init.uniform_(self.weight, -bound, bound)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key = prefix + "weight"
+        w = state_dict.get(key)
+        if w is not None and tuple(w.shape) != tuple(self.weight.shape) and w.dim() == 5 and \
+                w.shape[0] == self.out_channels and w.shape[-1] == self.in_channels:
+            state_dict[key] = w.permute(1, 2, 3, 4, 0).contiguous()  # spconv 2.x -> 1.x layout
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class SubMConv3d(_SparseConvBase):
+    subm = True
+
+
+class SparseConv3d(_SparseConvBase):
+    subm = False
+
+
+def make_sparse_convmodule(in_channels, out_channels, kernel_size, indice_key, stride=1,
+                           padding=0, conv_type="SubMConv3d", norm_cfg=None,
+                           order=("conv", "norm", "act")):
+    """mmdet3d.ops.make_sparse_convmodule: Sequential(conv[, BN1d][, ReLU])."""
+    norm_cfg = norm_cfg or dict(type="BN1d", eps=1e-3, momentum=0.01)
+    layers = []
+    for name in order:
+        if name == "conv":
+            cls = SubMConv3d if conv_type == "SubMConv3d" else SparseConv3d
+            layers.append(cls(in_channels, out_channels, kernel_size, stride=stride,
+                              padding=padding, bias=False, indice_key=indice_key))
+        elif name == "norm":
+            layers.append(nn.BatchNorm1d(out_channels, eps=norm_cfg.get("eps", 1e-5),
+                                         momentum=norm_cfg.get("momentum", 0.1)))
+        elif name == "act":
+            layers.append(nn.ReLU(inplace=True))
+    return nn.Sequential(*layers)
+
+
+class SparseBasicBlock(nn.Module):
+    """mmdet3d.ops.SparseBasicBlock: conv1-norm1-relu-conv2-norm2-(+identity)-relu, SubM 3^3."""
+
+    def __init__(self, inplanes, planes, norm_cfg=None, conv_cfg=None):
+        super().__init__()
+        norm_cfg = norm_cfg or dict(type="BN1d", eps=1e-3, momentum=0.01)
+        eps, mom = norm_cfg.get("eps", 1e-5), norm_cfg.get("momentum", 0.1)
+        self.conv1 = SubMConv3d(inplanes, planes, 3, padding=1, bias=False)
+        self.norm1 = nn.BatchNorm1d(planes, eps=eps, momentum=mom)
+        self.conv2 = SubMConv3d(planes, planes, 3, padding=1, bias=False)
+        self.norm2 = nn.BatchNorm1d(planes, eps=eps, momentum=mom)
+        self.relu = nn.ReLU(inplace=True)
+
+
+def _fold_bn(bn, conv_bias=None):
+    if bn is None:
+        return None, (conv_bias.float() if conv_bias is not None else None)
+    scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
+    shift = bn.bias.float() - bn.running_mean.float() * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+@MIDDLE_ENCODERS.register_module()
+class SparseEncoderHD(nn.Module):
+    def __init__(self, in_channels, sparse_shape, order=("conv", "norm", "act"),
+                 norm_cfg=dict(type="BN1d", eps=1e-3, momentum=0.01), base_channels=16,
+                 output_channels=128,
+                 encoder_channels=((16,), (32, 32, 32), (64, 64, 64), (64, 64, 64)),
+                 encoder_paddings=((1,), (1, 1, 1), (1, 1, 1), ((0, 1, 1), 1, 1)),
+                 encoder_strides=(2, 2, 2, 1), block_type="conv_module", keep_depth=True,
+                 fp16_enabled=False):
+        super().__init__()
+        assert block_type in ["conv_module", "basicblock"]
+        order = tuple(order)
+        assert len(order) == 3 and set(order) == {"conv", "norm", "act"}
+        if order[0] != "conv":
+            raise NotImplementedError("pre-activation order is not used by any Uni3DETR config")
+        self.sparse_shape = [int(v) for v in sparse_shape]
+        self.in_channels = in_channels
+        self.order = order
+        self.base_channels = base_channels
+        self.output_channels = output_channels
+        self.encoder_channels = encoder_channels
+        self.encoder_paddings = encoder_paddings
+        self.encoder_strides = encoder_strides
+        self.stage_num = len(self.encoder_channels)
+        self.keep_depth = keep_depth
+        if fp16_enabled:
+            self.fp16_enabled = fp16_enabled
+        self.compute_dtype = torch.float32
+        self.conv_impl = 0  # 0 auto, 1 SIMT, 2 tcgen05 (see u3d_spconv_fwd)
+
+        self.conv_input = make_sparse_convmodule(in_channels, base_channels, 3, norm_cfg=norm_cfg,
+                                                 padding=1, indice_key="subm1",
+                                                 conv_type="SubMConv3d")
+        out_ch = self.make_encoder_layers(make_sparse_convmodule, norm_cfg, base_channels,
+                                          block_type=block_type)
+        self.conv_out = make_sparse_convmodule(out_ch, output_channels, kernel_size=(1, 1, 1),
+                                               stride=(1, 1, 1), norm_cfg=norm_cfg, padding=0,
+                                               indice_key="spconv_down2", conv_type="SparseConv3d")
+        self._plan = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
+
+    # same construction logic as the reference (sparse_encoder_hd.py:140-214)
+    def make_encoder_layers(self, make_block, norm_cfg, in_channels, block_type="conv_module",
+                            conv_cfg=dict(type="SubMConv3d")):
+        self.encoder_layers = nn.Sequential()
+        for i, blocks in enumerate(self.encoder_channels):
+            blocks_list = []
+            for j, out_channels in enumerate(tuple(blocks)):
+                padding = tuple(self.encoder_paddings[i])[j]
+                strided = dict(norm_cfg=norm_cfg, stride=self.encoder_strides[i], padding=padding,
+                               indice_key=f"spconv{i + 1}", conv_type="SparseConv3d")
+                if i != 0 and j == 0 and block_type == "conv_module":
+                    blocks_list.append(make_block(in_channels, out_channels, 3, **strided))
+                elif block_type == "basicblock":
+                    if j == len(blocks) - 1 and i != len(self.encoder_channels) - 1:
+                        blocks_list.append(make_block(in_channels, out_channels, 3, **strided))
+                    else:
+                        blocks_list.append(SparseBasicBlock(out_channels, out_channels,
+                                                            norm_cfg=norm_cfg, conv_cfg=conv_cfg))
+                else:
+                    blocks_list.append(make_block(in_channels, out_channels, 3, norm_cfg=norm_cfg,
+                                                  padding=padding, indice_key=f"subm{i + 1}",
+                                                  conv_type="SubMConv3d"))
+                in_channels = out_channels
+            self.encoder_layers.add_module(f"encoder_layer{i + 1}", nn.Sequential(*blocks_list))
+        return out_channels
+
+    # ------------------------------------------------------------------ plan ----
+    def invalidate(self):
+        self._plan = None
+
+    def train(self, mode=True):
+        self.invalidate()
+        return super().train(mode)
+
+    def layer_specs(self):
+        """Flat list of conv steps: dict(conv, bn, relu, save, add)."""
+        specs = []
+
+        def add_module_seq(seq):
+            conv = seq[0]
+            bn = seq[1] if len(seq) > 1 and isinstance(seq[1], nn.BatchNorm1d) else None
+            relu = any(isinstance(m, nn.ReLU) for m in seq)
+            specs.append(dict(conv=conv, bn=bn, relu=relu, save=False, add=False))
+
+        add_module_seq(self.conv_input)
+        for stage in self.encoder_layers:
+            for blk in stage:
+                if isinstance(blk, SparseBasicBlock):
+                    specs.append(dict(conv=blk.conv1, bn=blk.norm1, relu=True, save=True, add=False))
+                    specs.append(dict(conv=blk.conv2, bn=blk.norm2, relu=True, save=False, add=True))
+                else:
+                    add_module_seq(blk)
+        add_module_seq(self.conv_out)
+        return specs
+
+    @torch.no_grad()
+    def prepare(self, dtype=None):
+        dtype = dtype or self.compute_dtype
+        steps = []
+        for s in self.layer_specs():
+            conv = s["conv"]
+            k = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
+            w = conv.weight.detach().reshape(k, conv.in_channels, conv.out_channels)
+            scale, shift = _fold_bn(s["bn"], conv.bias)
+            steps.append(dict(w=w.to(dtype).contiguous(), scale=scale, shift=shift, relu=s["relu"],
+                              save=s["save"], add=s["add"], subm=conv.subm, k=k,
+                              stride=conv.stride, pad=conv.padding))
+        self._plan = dict(dtype=dtype, steps=steps)
+        return self._plan
+
+    # --------------------------------------------------------------- forward ----
+    @torch.no_grad()
+    def forward_voxels(self, feats, coors, n_rows, cap, vmap, B, channels_last=True):
+        """feats (cap,Cin) f32/bf16, coors (cap,4) int32, n_rows device int32 (1,), vmap level-0
+        VoxelMap. Returns the dense volume (B,C,D,H,W) (channels_last_3d strides by default)."""
+        if self.training:
+            raise NotImplementedError("SparseEncoderHD: training-mode BN is a 'next' row "
+                                      "(SURVEY.md 8f); call .eval()")
+        plan = self._plan
+        if plan is None or plan["dtype"] != self.compute_dtype:
+            plan = self.prepare()
+        dtype = plan["dtype"]
+        x = feats.to(dtype).contiguous()
+        dims = tuple(self.sparse_shape)
+        level = dict(coors=coors, n=n_rows, cap=cap, vmap=vmap, nbr=None, dims=dims)
+        saved = None
+        for st in plan["steps"]:
+            if st["k"] == 1:
+                nbr, out_level = None, level
+            elif st["subm"]:
+                if level["nbr"] is None:
+                    level["nbr"] = ops.rulebook_subm(level["coors"], level["n"], level["cap"],
+                                                     level["vmap"])
+                nbr, out_level = level["nbr"], level
+            else:
+                oc, on, ovm, nbr, ocap = ops.rulebook_down(level["coors"], level["n"],
+                                                           level["cap"], level["vmap"],
+                                                           st["stride"], st["pad"])
+                out_level = dict(coors=oc, n=on, cap=ocap, vmap=ovm, nbr=None, dims=ovm.dims)
+            if st["save"]:
+                saved = x
+            x = ops.spconv_fwd(x, nbr, out_level["n"], out_level["cap"], st["w"], st["scale"],
+                               st["shift"], residual=saved if st["add"] else None, relu=st["relu"],
+                               impl=self.conv_impl)
+            if st["add"]:
+                saved = None
+            level = out_level
+        dense = ops.sparse_to_dense(x, level["coors"], level["n"], level["cap"], B, level["dims"],
+                                    channels_last=True)          # (B,D,H,W,C)
+        out = dense.permute(0, 4, 1, 2, 3)                       # logical (B,C,D,H,W)
+        if not channels_last:
+            out = out.contiguous()
+        if not self.keep_depth:
+            out = out.sum(dim=2)
+        self.last_level = level
+        return out
+
+    @torch.no_grad()
+    def forward(self, voxel_features, coors, batch_size):
+        """Reference API (sparse_encoder_hd.py:106-138): exact-size (N,C) features and (N,4)
+        int32 [b,z,y,x] coordinates -> (B,C,D,H,W)."""
+        coors = coors.int().contiguous()
+        n = coors.shape[0]
+        B = int(batch_size)
+        n_rows = torch.tensor([n], dtype=torch.int32, device=coors.device)
+        vmap = ops.voxmap_build(coors, n_rows, n, B, self.sparse_shape)
+        return self.forward_voxels(voxel_features, coors, n_rows, max(n, 1), vmap, B)

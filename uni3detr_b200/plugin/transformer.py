@@ -1,0 +1,329 @@
+"""Uni3DETRTransformer / Uni3DETRTransformerDecoder / UniCrossAtten drop-ins
+(reference: projects/mmdet3d_plugin/models/utils/uni3detr_transformer.py) plus the mmcv bricks
+the configs name (BaseTransformerLayer, MultiheadAttention, FFN - SURVEY.md A.8).
+
+Parameter names follow SURVEY.md Appendix B so reference checkpoints load. The forward is
+restructured for the GPU: the G query groups the reference decodes serially
+(uni3detr_transformer.py:115-125) share all weights and never interact, so they are folded
+into the batch (sequence s = b*G + g) and every layer runs once over all B*G*nq rows:
+sine embedding, self-attention core and the cross-attention sampling block are libu3d_b200
+kernels, the plain linear layers are library GEMMs.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from ..compat import (ATTENTION, FEEDFORWARD_NETWORK, TRANSFORMER, TRANSFORMER_LAYER,
+                      TRANSFORMER_LAYER_SEQUENCE, build_from_cfg)
+
+
+def inverse_sigmoid(x, eps=1e-5):
+    """mmdet.models.utils.transformer.inverse_sigmoid."""
+    x = x.clamp(min=0, max=1)
+    x1 = x.clamp(min=eps)
+    x2 = (1 - x).clamp(min=eps)
+    return torch.log(x1 / x2)
+
+
+class MLP(nn.Module):
+    """uni3detr_transformer.py:18-30."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+
+
+@ATTENTION.register_module()
+class MultiheadAttention(nn.Module):
+    """mmcv MultiheadAttention wrapper: parameters live in ``self.attn`` (nn.MultiheadAttention)."""
+
+    def __init__(self, embed_dims, num_heads, attn_drop=0., proj_drop=0., dropout=None,
+                 dropout_layer=None, init_cfg=None, batch_first=False, **kwargs):
+        super().__init__()
+        if dropout is not None:
+            attn_drop = dropout
+        self.embed_dims, self.num_heads, self.batch_first = embed_dims, num_heads, batch_first
+        if embed_dims // num_heads != 32:
+            raise NotImplementedError("u3d_mha_core is specialised for head_dim == 32")
+        self.attn = nn.MultiheadAttention(embed_dims, num_heads, attn_drop)
+
+
+@FEEDFORWARD_NETWORK.register_module()
+class FFN(nn.Module):
+    """mmcv FFN: layers = Sequential(Sequential(Linear, act, drop), ..., Linear, drop)."""
+
+    def __init__(self, embed_dims=256, feedforward_channels=1024, num_fcs=2,
+                 act_cfg=dict(type="ReLU", inplace=True), ffn_drop=0., dropout_layer=None,
+                 add_identity=True, init_cfg=None, **kwargs):
+        super().__init__()
+        assert num_fcs == 2 and act_cfg.get("type", "ReLU") == "ReLU" and add_identity
+        self.embed_dims = embed_dims
+        self.layers = nn.Sequential(
+            nn.Sequential(nn.Linear(embed_dims, feedforward_channels), nn.ReLU(inplace=True),
+                          nn.Dropout(ffn_drop)),
+            nn.Linear(feedforward_channels, embed_dims), nn.Dropout(ffn_drop))
+
+
+@ATTENTION.register_module()
+class UniCrossAtten(nn.Module):
+    """uni3detr_transformer.py:215-360 - single-point trilinear sample of the voxel volume,
+    sigmoid gate, output projection, positional MLP of the (logit) reference point."""
+
+    def __init__(self, embed_dims=256, num_heads=8, num_points=1, num_sweeps=1, cam_sweep_feq=12,
+                 voxel_range=(0, 0, 0), im2col_step=64, dropout=0.1, norm_cfg=None, init_cfg=None,
+                 batch_first=False, fp16_enabled=False):
+        super().__init__()
+        if embed_dims % num_heads != 0:
+            raise ValueError(f"embed_dims must be divisible by num_heads, but got {embed_dims} "
+                             f"and {num_heads}")
+        if num_points != 1:
+            raise NotImplementedError("num_points != 1 is not used by any Uni3DETR config")
+        self.embed_dims, self.num_heads, self.num_points = embed_dims, num_heads, num_points
+        self.dropout = nn.Dropout(dropout)
+        self.attention_weights = nn.Linear(embed_dims, num_points)
+        self.output_proj = nn.Linear(embed_dims, embed_dims)
+        self.position_encoder = nn.Sequential(
+            nn.Linear(3, embed_dims), nn.LayerNorm(embed_dims), nn.ReLU(inplace=True),
+            nn.Linear(embed_dims, embed_dims), nn.LayerNorm(embed_dims), nn.ReLU(inplace=True))
+        self.batch_first = batch_first
+        if fp16_enabled:
+            self.fp16_enabled = fp16_enabled
+        self.init_weight()
+
+    def init_weight(self):
+        nn.init.constant_(self.attention_weights.weight, 0.)
+        nn.init.constant_(self.attention_weights.bias, 0.)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.constant_(self.output_proj.bias, 0.)
+
+    @torch.no_grad()
+    def forward(self, query, key, value, residual=None, query_pos=None, key_padding_mask=None,
+                reference_points=None, spatial_shapes=None, level_start_index=None, **kwargs):
+        """Reference layout: query (nq,B,C), value (B,1,C,D,H,W) or (B,C,D,H,W),
+        reference_points (B,nq,3) logits. Returns (nq,B,C)."""
+        if self.training:
+            raise NotImplementedError("UniCrossAtten: autograd is a 'next' row; call .eval()")
+        nq, B, C = query.shape
+        v = value[:, 0] if value.dim() == 6 else value
+        if v.dim() != 5:
+            raise NotImplementedError("the 4-D BEV branch is not used by any Uni3DETR config")
+        dt = v.dtype
+        vol = v.permute(0, 2, 3, 4, 1).contiguous()                       # NDHWC (free if channels_last_3d)
+        q = query.permute(1, 0, 2).reshape(B * nq, C).to(dt).contiguous()
+        qp = None if query_pos is None else \
+            query_pos.permute(1, 0, 2).reshape(B * nq, C).to(dt).contiguous()
+        ref = reference_points.reshape(B * nq, 3).float().contiguous()
+        s = ops.cross_sample(vol, ref, q, qp, self.attention_weights.weight.float().reshape(-1).contiguous(),
+                             float(self.attention_weights.bias.item()), nq)
+        out = F.linear(s, self.output_proj.weight.to(dt), self.output_proj.bias.to(dt))
+        pe = self.position_encoder
+        pf = ref.to(dt)
+        for i in (0, 3):
+            pf = F.linear(pf, pe[i].weight.to(dt), pe[i].bias.to(dt))
+            pf = F.relu(F.layer_norm(pf, (C,), pe[i + 1].weight.to(dt), pe[i + 1].bias.to(dt),
+                                     pe[i + 1].eps))
+        res = q if residual is None else residual.permute(1, 0, 2).reshape(B * nq, C).to(dt)
+        out = out + res + pf
+        return out.reshape(B, nq, C).permute(1, 0, 2)
+
+
+@TRANSFORMER_LAYER.register_module()
+class BaseTransformerLayer(nn.Module):
+    """mmcv BaseTransformerLayer restricted to the operation order every Uni3DETR config uses:
+    ('self_attn','norm','cross_attn','norm','ffn','norm'), post-norm."""
+
+    def __init__(self, attn_cfgs=None, ffn_cfgs=None, operation_order=None,
+                 norm_cfg=dict(type="LN"), init_cfg=None, batch_first=False, **kwargs):
+        super().__init__()
+        expect = ("self_attn", "norm", "cross_attn", "norm", "ffn", "norm")
+        if tuple(operation_order) != expect:
+            raise NotImplementedError(f"operation_order {operation_order}; supported: {expect}")
+        assert norm_cfg.get("type", "LN") == "LN"
+        self.operation_order = tuple(operation_order)
+        self.attentions = nn.ModuleList([build_from_cfg(dict(c), ATTENTION) for c in attn_cfgs])
+        self.embed_dims = self.attentions[0].embed_dims
+        ffn = dict(ffn_cfgs)
+        ffn.setdefault("type", "FFN")
+        ffn.setdefault("embed_dims", self.embed_dims)
+        self.ffns = nn.ModuleList([build_from_cfg(ffn, FEEDFORWARD_NETWORK)])
+        self.norms = nn.ModuleList([nn.LayerNorm(self.embed_dims) for _ in range(3)])
+
+
+def _wb(lin, dtype):
+    return (lin.weight.detach().to(dtype).contiguous(), lin.bias.detach().to(dtype).contiguous())
+
+
+def _mlp_plan(mlp_layers, dtype):
+    return [_wb(l, dtype) for l in mlp_layers]
+
+
+def _run_mlp(x, plan):
+    for i, (w, b) in enumerate(plan):
+        x = F.linear(x, w, b)
+        if i < len(plan) - 1:
+            x = torch.relu_(x)
+    return x
+
+
+@TRANSFORMER_LAYER_SEQUENCE.register_module()
+class Uni3DETRTransformerDecoder(nn.Module):
+    """uni3detr_transformer.py:133-212."""
+
+    def __init__(self, transformerlayers=None, num_layers=None, return_intermediate=False,
+                 init_cfg=None):
+        super().__init__()
+        if isinstance(transformerlayers, dict):
+            transformerlayers = [dict(transformerlayers) for _ in range(num_layers)]
+        self.num_layers = num_layers
+        self.layers = nn.ModuleList([build_from_cfg(dict(c), TRANSFORMER_LAYER)
+                                     for c in transformerlayers])
+        self.embed_dims = self.layers[0].embed_dims
+        self.return_intermediate = return_intermediate
+        self.d_model = d_model = 256
+        self.query_scale = MLP(d_model, d_model, d_model, 3)
+        self.ref_point_head = MLP(384, d_model, d_model, 3)
+        self.compute_dtype = torch.float32
+        self._plan = None
+        self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
+
+    def invalidate(self):
+        self._plan = None
+
+    def train(self, mode=True):
+        self._plan = None
+        return super().train(mode)
+
+    @torch.no_grad()
+    def prepare(self):
+        dt = self.compute_dtype
+        E = self.embed_dims
+        layers = []
+        for layer in self.layers:
+            mha = layer.attentions[0].attn
+            ca = layer.attentions[1]
+            w, b = mha.in_proj_weight.detach(), mha.in_proj_bias.detach()
+            ffn = layer.ffns[0].layers
+            layers.append(dict(
+                heads=mha.num_heads,
+                in_qk=(w[:2 * E].to(dt).contiguous(), b[:2 * E].to(dt).contiguous()),
+                in_v=(w[2 * E:].to(dt).contiguous(), b[2 * E:].to(dt).contiguous()),
+                out=_wb(mha.out_proj, dt),
+                ln=[(n.weight.detach().to(dt), n.bias.detach().to(dt), n.eps) for n in layer.norms],
+                gate_w=ca.attention_weights.weight.detach().float().reshape(-1).contiguous(),
+                gate_b=float(ca.attention_weights.bias.detach().float().item()),
+                oproj=_wb(ca.output_proj, dt),
+                pe=[_wb(ca.position_encoder[0], dt), _wb(ca.position_encoder[3], dt)],
+                pe_ln=[(ca.position_encoder[i].weight.detach().to(dt),
+                        ca.position_encoder[i].bias.detach().to(dt), ca.position_encoder[i].eps)
+                       for i in (1, 4)],
+                ffn=[_wb(ffn[0][0], dt), _wb(ffn[1], dt)]))
+        self._plan = dict(dtype=dt, layers=layers,
+                          query_scale=_mlp_plan(self.query_scale.layers, dt),
+                          ref_point_head=_mlp_plan(self.ref_point_head.layers, dt))
+        return self._plan
+
+    @torch.no_grad()
+    def forward_batched(self, query, value_ndhwc, reference_points, nq, reg_plans=None):
+        """query (B,Q,E), value (B,D,H,W,E) NDHWC, reference_points (B,Q,3) logits with
+        Q = G*nq (G independent groups). Returns (L,B,Q,E) states and (L,B,Q,3) logits."""
+        if self.training:
+            raise NotImplementedError("decoder autograd is a 'next' row; call .eval()")
+        p = self._plan
+        if p is None or p["dtype"] != self.compute_dtype:
+            p = self.prepare()
+        dt = p["dtype"]
+        B, Q, E = query.shape
+        assert Q % nq == 0
+        R, n_seq = B * Q, B * (Q // nq)
+        out = query.reshape(R, E).to(dt).contiguous()
+        ref = reference_points.reshape(R, 3).float().contiguous()
+        value = value_ndhwc.to(dt).contiguous()
+        inter, inter_ref = [], []
+        for lid, L in enumerate(p["layers"]):
+            sine = ops.sine_embed(ref, dt)
+            qpos = _run_mlp(sine, p["ref_point_head"])
+            if lid != 0:
+                qpos = _run_mlp(out, p["query_scale"]) * qpos
+            # self attention (q = k = x + pos, v = x), post-norm
+            qk = F.linear(out + qpos, *L["in_qk"])
+            v = F.linear(out, *L["in_v"])
+            attn = ops.mha_core(qk[:, :E], qk[:, E:], v, n_seq, nq, L["heads"])
+            x = out + F.linear(attn, *L["out"])
+            x = F.layer_norm(x, (E,), *L["ln"][0])
+            # cross attention: sample * gate -> proj, + residual + positional MLP
+            s = ops.cross_sample(value, ref, x, qpos, L["gate_w"], L["gate_b"], Q)
+            o = F.linear(s, *L["oproj"])
+            pf = ref.to(dt)
+            for (w, b), ln in zip(L["pe"], L["pe_ln"]):
+                pf = torch.relu_(F.layer_norm(F.linear(pf, w, b), (E,), *ln))
+            x = F.layer_norm(o + x + pf, (E,), *L["ln"][1])
+            # FFN
+            h = torch.relu_(F.linear(x, *L["ffn"][0]))
+            x = F.layer_norm(x + F.linear(h, *L["ffn"][1]), (E,), *L["ln"][2])
+            out = x
+            if reg_plans is not None:
+                tmp = _run_mlp(out, reg_plans[lid]).float()
+                ref = ref + torch.stack((tmp[:, 0], tmp[:, 1], tmp[:, 4]), dim=1)
+            if self.return_intermediate:
+                inter.append(out.view(B, Q, E))
+                inter_ref.append(ref.view(B, Q, 3))
+        if self.return_intermediate:
+            return torch.stack(inter), torch.stack(inter_ref)
+        return out.view(1, B, Q, E), ref.view(1, B, Q, 3)
+
+    def forward(self, query, key, value, query_pos, reference_points=None, reg_branches=None,
+                attn_masks=None, **kwargs):
+        """Reference layout: query (nq,B,E) seq-first, value (B,1,C,D,H,W), one group."""
+        assert query_pos is None
+        nq, B, E = query.shape
+        v = value[:, 0] if value.dim() == 6 else value
+        vol = v.permute(0, 2, 3, 4, 1)
+        reg = None
+        if reg_branches is not None:
+            reg = [[_wb(m, self.compute_dtype) for m in br if isinstance(m, nn.Linear)]
+                   for br in reg_branches]
+        hs, refs = self.forward_batched(query.permute(1, 0, 2), vol, reference_points, nq, reg)
+        return hs.permute(0, 2, 1, 3), refs  # (L,nq,B,E), (L,B,nq,3)
+
+
+@TRANSFORMER.register_module()
+class Uni3DETRTransformer(nn.Module):
+    """uni3detr_transformer.py:68-130."""
+
+    def __init__(self, decoder=None, fp16_enabled=False, init_cfg=None, **kwargs):
+        super().__init__()
+        self.decoder = build_from_cfg(dict(decoder), TRANSFORMER_LAYER_SEQUENCE)
+        self.embed_dims = self.decoder.embed_dims
+        self.d_model = 256
+        if fp16_enabled:
+            self.fp16_enabled = fp16_enabled
+
+    def init_weights(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, UniCrossAtten):
+                m.init_weight()
+
+    @torch.no_grad()
+    def forward(self, pts_value, query_embed, num_query, reg_branches=None, reg_plans=None,
+                **kwargs):
+        """pts_value (B,1,C,D,H,W) / (B,C,D,H,W); query_embed (B,Q,256+3).
+        Returns inter_states (L,Q,B,256), init_reference (B,Q,3), inter_references (L,B,Q,3)."""
+        assert query_embed is not None
+        v = pts_value[:, 0] if pts_value.dim() == 6 else pts_value
+        vol = v.permute(0, 2, 3, 4, 1)
+        reference_points = query_embed[..., self.d_model:]
+        query = query_embed[..., :self.d_model]
+        init_reference_out = reference_points.float().sigmoid()
+        if reg_plans is None and reg_branches is not None:
+            dt = self.decoder.compute_dtype
+            reg_plans = [[_wb(m, dt) for m in br if isinstance(m, nn.Linear)] for br in reg_branches]
+        hs, refs = self.decoder.forward_batched(query, vol, reference_points, num_query, reg_plans)
+        return hs.permute(0, 2, 1, 3), init_reference_out, refs.sigmoid()
