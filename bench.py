@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py - scenes/sec of the Uni3DETR per-scene forward hot path (BASELINE.json metric) on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--dtype bf16|fp32]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+  python bench.py --impl reference      # CPU arm: the oracle port on the host cores
+
+One "step" = one pass of the hot path (voxelize -> sparse encoder -> dense CNN -> 2x FPS -> decoder
+-> heads -> NMSFreeCoder top-k) over a batch of B synthetic 20k-point SUN-RGBD-shaped scenes
+(BASELINE config 2: uni3detr_sunrgbd.py, 300 queries x 4 groups, 3 decoder layers, bf16).
+Scenes are sharded whole across ranks (weak scaling: B scenes per rank per step, no data-path
+collective); one all-reduce of the metrics vector ends the job.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "sunrgbd"
+RIDGE_NOTE = "bound = tensor if FLOP/byte of the launch exceeds measured bf16 peak / measured HBM peak, else hbm"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm ----
+def cpu_port_rate(n_scenes, threads, seed=0, warm=0):
+    """Oracle (CPU port of the reference path, oracle/model.py) on `n_scenes` 20k-point scenes.
+    Returns (scenes/sec, seconds). bench.py is one of the places allowed to execute oracle/."""
+    import torch
+    from oracle import model as M
+    from uni3detr_b200 import synth
+    torch.set_num_threads(threads)
+    model, cfg = synth.build_model(WORKLOAD, seed=0)
+    sd = model.state_dict()
+    rp = torch.rand(1, cfg["pts_bbox_head"]["num_query"], 3, generator=torch.Generator().manual_seed(seed))
+    scenes = [synth.make_scene(WORKLOAD, 100 + i) for i in range(n_scenes + warm)]
+    for s in scenes[:warm]:
+        M.forward(sd, cfg, [s], random_point=rp)
+    t0 = time.perf_counter()
+    for s in scenes[warm:]:
+        outs, _, _ = M.forward(sd, cfg, [s], random_point=rp)
+        M.nms_free_decode(outs, cfg["pts_bbox_head"]["bbox_coder"])
+    dt = time.perf_counter() - t0
+    return n_scenes / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path. Its arithmetic lives in
+    mmcv/mmdet3d/spconv, which cannot be installed here, so this arm times the oracle
+    port with every host thread, one scene per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    steps, warm = max(1, args.steps), min(args.warmup, 1)
+    rate, dt = cpu_port_rate(steps, cores, warm=warm)
+    line = {"impl": "reference", "metric": "scenes/sec", "value": rate, "unit": "scenes/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": "uni3detr_sunrgbd.py synthetic 20k-pt scenes, 300 queries x4 groups, full forward",
+                       "scenes_per_step": 1},
+            "cpu_baseline": {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} scene(s), one per step, oracle/model.py full forward + decode"},
+            "e2e": {"value": rate, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm ----
+def spconv_cost(info):
+    """Algorithmic bytes / FLOPs of one sparse-conv launch:
+    (N_in*Cin + N_out*Cout)*sizeof(act) + K*Cin*Cout*sizeof(w) + pairs*8 B; 2*pairs*Cin*Cout FLOP."""
+    n_out = int(info["n_out"])
+    if info["nbr"] is None:
+        pairs = n_out
+    else:
+        pairs = int((info["nbr"][:, :n_out] >= 0).sum())
+    es = info["esize"]
+    by = (info["n_in"] * info["Cin"] + n_out * info["Cout"]) * es + info["K"] * info["Cin"] * info["Cout"] * es + pairs * 8
+    return by, 2.0 * pairs * info["Cin"] * info["Cout"], pairs
+
+
+def roofline_pass(step_fn, peaks, reps=3):
+    """Per-op device times (CUDA events on the launching stream) of the libu3d kernels inside the
+    step, then the roofline of the dominant one."""
+    import torch
+    from uni3detr_b200 import ops
+    step_fn()
+    torch.cuda.synchronize()
+    agg = {}
+    for _ in range(reps):
+        ops.profile_begin()
+        step_fn()
+        for name, info, ms in ops.profile_end():
+            if name == "spconv_fwd":
+                key = f"spconv_fwd[{info['K']}x{info['Cin']}->{info['Cout']}]"
+            elif name == "fps":
+                key = f"fps[n<={info['max_n']},nq={info['nq']}]"
+            else:
+                key = name
+            a = agg.setdefault(key, dict(ms=0.0, calls=0, bytes=0.0, flops=0.0, name=name))
+            a["ms"] += ms
+            a["calls"] += 1
+            if name == "spconv_fwd":
+                by, fl, _ = spconv_cost(info)
+                a["bytes"] += by
+                a["flops"] += fl
+            elif name in ("voxelize_hard", "voxelize_dynamic"):
+                m = int(info["out"].scene_rows[-1])
+                a["bytes"] += info["n_points"] * info["C"] * 4 + m * (info["C"] * 4 + 16)
+            elif name in ("rulebook_subm", "rulebook_down"):
+                n = int(info.get("n_out", info["n_rows"]))
+                nin = int(info["n_rows"])
+                pairs = int((info["nbr"][:, :n] >= 0).sum())
+                a["bytes"] += nin * 16 + pairs * 8 + 2 * nin * 8
+            elif name == "sparse_to_dense":
+                a["bytes"] += info["bytes"]
+            elif name == "fps":
+                a["bytes"] += info["B"] * (info["max_n"] * 12 + info["nq"] * 16)
+            elif name == "cross_sample":
+                a["bytes"] += info["rows"] * info["C"] * info["esize"] * (8 + 2)
+            elif name == "sine_embed":
+                a["bytes"] += info["bytes"]
+            elif name == "mha_core":
+                r = info["n_seq"] * info["seq_len"]
+                a["bytes"] += r * info["heads"] * 32 * info["esize"] * 4
+                a["flops"] += 4.0 * info["n_seq"] * info["heads"] * info["seq_len"] ** 2 * 32
+    kernels = []
+    for key, a in agg.items():
+        per_ms = a["ms"] / a["calls"]
+        kernels.append({"kernel": key, "calls_per_step": a["calls"] // reps, "ms_per_step": a["ms"] / reps,
+                        "avg_launch_ms": per_ms, "gbs": a["bytes"] / a["ms"] / 1e6 if a["ms"] else 0.0,
+                        "tflops": a["flops"] / a["ms"] / 1e9 if a["ms"] else 0.0,
+                        "bytes_per_launch": a["bytes"] / a["calls"], "flops_per_launch": a["flops"] / a["calls"]})
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    top = kernels[0]
+    ridge = peaks["tf_sustained"] * 1e12 / (peaks["hbm"] * 1e9)
+    intensity = top["flops_per_launch"] / max(top["bytes_per_launch"], 1.0)
+    if intensity > ridge:
+        roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": top["tflops"] / peaks["tf_sustained"]}
+    else:
+        roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": top["gbs"] / peaks["hbm"]}
+    roof.update({"traffic": None, "kernel": top["kernel"], "avg_launch_ms": top["avg_launch_ms"],
+                 "algorithmic_bytes_per_launch": top["bytes_per_launch"],
+                 "algorithmic_flops_per_launch": top["flops_per_launch"],
+                 "peak_source": peaks["source"] + " (sustained bf16 / copy bandwidth)", "rule": RIDGE_NOTE})
+    ours_ms = sum(k["ms_per_step"] for k in kernels)
+    return roof, kernels[:12], ours_ms
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from uni3detr_b200 import ops, sharding, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback); use --impl reference")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    peaks = load_peaks()
+
+    model, cfg = synth.build_model(WORKLOAD, seed=0)
+    model = model.to(dev)
+    model.set_compute_dtype(dtype)
+    nq = cfg["pts_bbox_head"]["num_query"]
+    coder = model.pts_bbox_head.bbox_coder
+    # rank r owns scenes {i : i mod world == r} of the job's B*world scene pool (weak scaling)
+    mine = sharding.scene_indices(B * world, rank, world)
+    host_pts = [torch.from_numpy(synth.make_scene(WORKLOAD, i)).pin_memory() for i in mine]
+    dev_pts = [p.to(dev) for p in host_pts]
+    rp = torch.rand(B, nq, 3, generator=torch.Generator().manual_seed(1234 + rank)).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(points):
+        outs, _ = model.forward_raw(points, random_point=rp)
+        return coder.decode_fixed(outs)
+
+    # ---- device-resident throughput ("value")
+    for _ in range(W):
+        step(dev_pts)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    n0 = ops.launch_count()
+    torch.cuda.synchronize()
+    for s, e in evs:
+        flush.zero_()                      # untimed L2 flush between timed iterations
+        s.record()
+        res = step(dev_pts)
+        e.record()
+    torch.cuda.synchronize()
+    launches = ops.launch_count() - n0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    dev_s = sum(s.elapsed_time(e) for s, e in evs) / 1e3
+    checksum = float(res[1].float().sum())
+    scenes, t_max, checksum = sharding.reduce_metrics(B * K, dev_s, checksum, device=dev)
+
+    # ---- end to end through the reference-facing call with HOST buffers ("e2e")
+    out_host = None
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        pts = [p.to(dev, non_blocking=True) for p in host_pts]
+        boxes, scores, labels, mask = step(pts)
+        out_host = [t.cpu() for t in (boxes, scores, labels, mask)]      # D2H read of the step's result
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    _, e2e_max, _ = sharding.reduce_metrics(B * K, e2e_s, 0.0, device=dev)
+    h2d = sum(p.numel() * p.element_size() for p in host_pts)
+    d2h = sum(t.numel() * t.element_size() for t in out_host)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- rank 0 only: roofline of the dominant libu3d kernel + CPU baseline
+    roof, kernels, ours_ms = roofline_pass(lambda: step(dev_pts), peaks)
+    cores = os.cpu_count() or 1
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt = cpu_port_rate(args.cpu_scenes, cores)
+        cpu = {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_scenes} scene(s) of the same workload, oracle/model.py full forward + decode, {dt:.1f} s"}
+    line = {"metric": "scenes/sec", "value": scenes / t_max, "unit": "scenes/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "uni3detr_sunrgbd.py synthetic 20k-pt scenes, 300 queries x4 groups, 3 decoder "
+                                   "layers, full forward (voxelize+sparse encoder+dense CNN+FPS+decoder+top-k)",
+                       "scenes_per_step_per_gpu": B, "points_per_scene": 20000, "parallelism": f"scenes sharded x{world}",
+                       "l2": "256 MiB flush write between timed steps (untimed)", "timing": "CUDA events per step, max over ranks"},
+            "e2e": {"value": scenes / e2e_max, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "kernels": kernels, "libu3d_ms_per_step": ours_ms, "checksum": checksum}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="scenes per step per GPU")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-scenes", type=int, default=2, help="bounded CPU-baseline sample (scenes)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 20:
+            args.steps = 3
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,8 @@ extern "C" {
 
 const char* u3d_last_error(void);
 int u3d_version(void);
+/* number of CUDA kernels this library has launched in this process (host-side counter) */
+unsigned long long u3d_launch_count(void);
 
 /* number of uint2 words a VoxelMap for B scenes of a (D,H,W) grid needs; 0 on overflow */
 size_t u3d_voxmap_words(int B, int D, int H, int W);
@@ -62,7 +64,10 @@ size_t u3d_scan_scratch_ints(size_t words);
  * MVXTwoStageDetector.voxelize at projects/mmdet3d_plugin/models/detectors/uni3detr.py:148
  * and HardSimpleVFE at uni3detr.py:149 (config uni3detr_sunrgbd.py:28-31).
  *   points      (Ntot, C) f32, scenes concatenated; pt_off (B+1) int32 DEVICE offsets
- *   pc_range    6 floats HOST (x0,y0,z0,x1,y1,z1); voxel_size 3 floats HOST (x,y,z)
+ *   pc_range    6 floats HOST (x0,y0,z0,x1,y1,z1); voxel_size 3 floats HOST (x,y,z); the
+ *               voxel grid is round((hi-lo)/voxel_size) like mmcv; (D,H,W) is the index space
+ *               of the VoxelMap (= the encoder's sparse_shape, which SECOND-style configs
+ *               declare one cell deeper than the grid) and must contain the grid
  *   map         u3d_voxmap_words(B,D,H,W) uint2           (out)
  *   pt_lin      (Ntot) uint32 scratch; slots (Ntot*max_pts) int32 scratch
  *   row_of_rank (Ntot) int32 (out: VoxelMap perm, -1 = voxel dropped by max_voxels)

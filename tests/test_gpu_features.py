@@ -1,0 +1,275 @@
+"""GPU parity, floating-point half of the path: sparse conv (+BN/ReLU/residual epilogue), dense(),
+sine embedding, self-attention core, UniCrossAtten sampling, decoder/head, dense CNN.
+CUDA (C ABI) vs oracle/model.py and vs the golden vectors produced by the reference's own files.
+Tolerances (BASELINE.json north_star): 1e-3 relative fp32, 1e-2 bf16 - measured here as
+max|a-b| / max|b| per tensor, the number each assert states."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gen_weights import gen_state_dict
+from oracle import geometry as G
+from oracle import model as M
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+T = torch.from_numpy
+
+
+def relerr(a, b):
+    a = a.detach().float().cpu()
+    b = torch.as_tensor(b).detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def rand_coors(n, dims, B, seed):
+    rng = np.random.default_rng(seed)
+    D, H, W = dims
+    lin = np.sort(rng.choice(B * D * H * W, size=n, replace=False))
+    return np.stack([lin // (D * H * W), (lin // (H * W)) % D, (lin // W) % H, lin % W], 1).astype(np.int32)
+
+
+def conv_case(n, dims, B, cin, cout, seed, K=27):
+    g = torch.Generator().manual_seed(seed)
+    coors = rand_coors(n, dims, B, seed)
+    x = torch.randn(n, cin, generator=g)
+    w = torch.randn(3 if K == 27 else 1, 3 if K == 27 else 1, 3 if K == 27 else 1, cin, cout, generator=g) / (cin * K / 4) ** 0.5
+    scale = 0.5 + torch.rand(cout, generator=g)
+    shift = 0.1 * torch.randn(cout, generator=g)
+    return coors, x, w, scale, shift
+
+
+def oracle_conv(x, nbr, w, n_out, scale, shift, residual, relu):
+    y = M.sparse_conv(x, nbr, w, n_out) * scale + shift
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+CONV_SHAPES = [(4, 16), (5, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)]
+
+
+@pytest.mark.parametrize("cin,cout", CONV_SHAPES)
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
+def test_spconv_subm(cin, cout, dtype, tol):
+    from uni3detr_b200 import ops
+    dims, B, n = (8, 24, 24), 2, 3000
+    coors, x, w, scale, shift = conv_case(n, dims, B, cin, cout, cin * 1000 + cout)
+    if dtype == torch.bfloat16:                      # same rounded operands on both sides
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    nbr_ref = G.subm_rulebook(coors, dims)
+    c = T(coors).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, n, B, dims)
+    nbr = ops.rulebook_subm(c, n_rows, n, vm)
+    res = torch.randn(n, cout, generator=torch.Generator().manual_seed(1))
+    if dtype == torch.bfloat16:
+        res = res.bfloat16().float()
+    for residual, relu in [(None, True), (res, True), (None, False)]:
+        ref = oracle_conv(x, nbr_ref, w, n, scale, shift, residual, relu)
+        for impl in (1, 0):
+            y = ops.spconv_fwd(x.to(DEV, dtype), nbr, n_rows, n, w.reshape(27, cin, cout).to(DEV, dtype).contiguous(),
+                               scale.to(DEV), shift.to(DEV),
+                               residual=None if residual is None else residual.to(DEV, dtype), relu=relu, impl=impl)
+            assert relerr(y, ref) < tol, (impl, residual is not None, relu, relerr(y, ref))
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 32), (32, 64), (64, 128)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
+def test_spconv_down(cin, cout, dtype, tol):
+    from uni3detr_b200 import ops
+    dims, B, n = (9, 24, 26), 2, 2500
+    coors, x, w, scale, shift = conv_case(n, dims, B, cin, cout, 7 + cin)
+    if dtype == torch.bfloat16:
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    c = T(coors).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, n, B, dims)
+    oc, n_out, ovm, nbr, ocap = ops.rulebook_down(c, n_rows, n, vm, (2, 2, 2), (0, 1, 1))
+    roc, rnbr, rod = G.down_rulebook(coors, dims, (2, 2, 2), (0, 1, 1))
+    m = len(roc)
+    ref = oracle_conv(x, rnbr, w, m, scale, shift, None, True)
+    for impl in (1, 0):
+        y = ops.spconv_fwd(x.to(DEV, dtype), nbr, n_out, ocap, w.reshape(27, cin, cout).to(DEV, dtype).contiguous(),
+                           scale.to(DEV), shift.to(DEV), relu=True, impl=impl)
+        assert relerr(y[:m], ref) < tol, (impl, relerr(y[:m], ref))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
+def test_spconv_pointwise_and_dense(dtype, tol):
+    """conv_out (1x1x1, 128->256) + SparseConvTensor.dense() in both layouts."""
+    from uni3detr_b200 import ops
+    dims, B, n, cin, cout = (5, 12, 10), 2, 700, 128, 256
+    coors, x, w, scale, shift = conv_case(n, dims, B, cin, cout, 3, K=1)
+    if dtype == torch.bfloat16:
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    ref = F.relu((x @ w.reshape(cin, cout)) * scale + shift)
+    y = ops.spconv_fwd(x.to(DEV, dtype), None, n_rows, n, w.reshape(1, cin, cout).to(DEV, dtype).contiguous(),
+                       scale.to(DEV), shift.to(DEV), relu=True)
+    assert relerr(y, ref) < tol
+    c = T(coors).to(DEV)
+    dref = torch.zeros(B, *dims, cout)
+    cl = T(coors.astype(np.int64))
+    dref[cl[:, 0], cl[:, 1], cl[:, 2], cl[:, 3]] = y.float().cpu()
+    d1 = ops.sparse_to_dense(y, c, n_rows, n, B, dims, channels_last=True)
+    d2 = ops.sparse_to_dense(y, c, n_rows, n, B, dims, channels_last=False)
+    torch.testing.assert_close(d1.float().cpu(), dref, rtol=0, atol=0)
+    torch.testing.assert_close(d2.float().cpu(), dref.permute(0, 4, 1, 2, 3), rtol=0, atol=0)
+
+
+def test_spconv_live_count_smaller_than_capacity():
+    """Rows beyond the device-side live count must not be touched (fixed-capacity buffers)."""
+    from uni3detr_b200 import ops
+    dims, B, n, cap = (6, 10, 10), 1, 200, 333
+    coors, x, w, scale, shift = conv_case(n, dims, B, 16, 16, 5)
+    c = torch.cat([T(coors), torch.zeros(cap - n, 4, dtype=torch.int32)]).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, cap, B, dims)
+    nbr = ops.rulebook_subm(c, n_rows, cap, vm)
+    xin = torch.cat([x, torch.full((cap - n, 16), float("nan"))]).to(DEV)
+    out = torch.full((cap, 16), -5.0, device=DEV)
+    ops.spconv_fwd(xin, nbr, n_rows, cap, w.reshape(27, 16, 16).to(DEV).contiguous(), scale.to(DEV), shift.to(DEV),
+                   relu=True, out=out)
+    ref = oracle_conv(x, G.subm_rulebook(coors, dims), w, n, scale, shift, None, True)
+    assert relerr(out[:n], ref) < 1e-4
+    assert bool((out[n:] == -5.0).all())
+
+
+def test_sine_embed_golden(golden):
+    from uni3detr_b200 import ops
+    pos = T(golden["sine_in"]).double()
+    ref_logit = torch.log(pos / (1 - pos)).float().to(DEV)
+    out = ops.sine_embed(ref_logit.reshape(-1, 3).contiguous())
+    np.testing.assert_allclose(out.cpu().numpy().reshape(golden["sine_out"].shape), golden["sine_out"], atol=2e-5)
+
+
+@pytest.mark.parametrize("seq_len,n_seq", [(300, 8), (900, 2), (5, 4), (64, 3), (129, 1)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
+def test_mha_core(seq_len, n_seq, dtype, tol):
+    from uni3detr_b200 import ops
+    g = torch.Generator().manual_seed(seq_len)
+    heads, E = 8, 256
+    qk = torch.randn(n_seq * seq_len, 2 * E, generator=g).to(dtype)
+    v = torch.randn(n_seq * seq_len, E, generator=g).to(dtype)
+    out = ops.mha_core(qk.to(DEV)[:, :E], qk.to(DEV)[:, E:], v.to(DEV), n_seq, seq_len, heads)
+
+    def split(t):
+        return t.float().view(n_seq, seq_len, heads, 32).permute(0, 2, 1, 3)
+    ref = F.scaled_dot_product_attention(split(qk[:, :E]), split(qk[:, E:]), split(v))
+    ref = ref.permute(0, 2, 1, 3).reshape(n_seq * seq_len, E)
+    assert relerr(out, ref) < tol
+
+
+def ca_state_dict():
+    from test_oracle_golden import ca_state_dict as f
+    return f()
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1.5e-2)])
+def test_uni_cross_atten_golden(golden, dtype, tol):
+    """Product UniCrossAtten (cross_sample kernel + proj) vs the output of the reference's own class."""
+    from uni3detr_b200.plugin.transformer import UniCrossAtten
+    m = UniCrossAtten(embed_dims=256, num_heads=8, num_points=1, dropout=0.1).eval()
+    m.load_state_dict(ca_state_dict())
+    m = m.to(DEV)
+    out = m(T(golden["ca_query"]).to(DEV, dtype), None, T(golden["ca_value"]).to(DEV, dtype),
+            query_pos=T(golden["ca_qpos"]).to(DEV, dtype), reference_points=T(golden["ca_ref"]).to(DEV))
+    assert relerr(out, golden["ca_out"]) < tol
+
+
+def test_cross_sample_out_of_bounds_corners():
+    """grid_sample zeros padding at the volume border (align_corners=False)."""
+    from uni3detr_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    B, D, H, W, C, Q = 2, 3, 4, 5, 256, 64
+    vol = torch.randn(B, D, H, W, C, generator=g)
+    ref = torch.randn(B * Q, 3, generator=g) * 6          # many saturate to the borders
+    q = torch.randn(B * Q, C, generator=g)
+    gw, gb = torch.randn(C, generator=g) * 0.05, 0.1
+    out = ops.cross_sample(vol.to(DEV), ref.to(DEV), q.to(DEV), None, gw.to(DEV), gb, Q)
+    grid = ((ref.sigmoid() - 0.5) * 2).view(B, 1, 1, Q, 3)
+    samp = F.grid_sample(vol.permute(0, 4, 1, 2, 3), grid, align_corners=False)[:, :, 0, 0].permute(0, 2, 1)
+    gate = (q @ gw + gb).sigmoid().view(B, Q, 1)
+    assert relerr(out.view(B, Q, C), samp * gate) < 1e-4
+
+
+def head_fixture(golden):
+    from test_oracle_golden import golden_head_cfg
+    from uni3detr_b200 import compat, register_all
+    register_all()
+    cfg0, sd, (nq, ncls, code, L) = golden_head_cfg(golden)
+    layer = dict(type="BaseTransformerLayer",
+                 attn_cfgs=[dict(type="MultiheadAttention", embed_dims=256, num_heads=8, dropout=0.1),
+                            dict(type="UniCrossAtten", num_points=1, embed_dims=256, num_sweeps=1)],
+                 ffn_cfgs=dict(type="FFN", embed_dims=256, feedforward_channels=64, num_fcs=2, ffn_drop=0.1,
+                               act_cfg=dict(type="ReLU", inplace=True)),
+                 norm_cfg=dict(type="LN"),
+                 operation_order=("self_attn", "norm", "cross_attn", "norm", "ffn", "norm"))
+    pc = [-3.2, -0.2, -2., 3.2, 6.2, 0.56]
+    hcfg = dict(type="Uni3DETRHead", num_query=nq, num_classes=ncls, in_channels=256, code_size=code,
+                with_box_refine=True, as_two_stage=False, sync_cls_avg_factor=True,
+                transformer=dict(type="Uni3DETRTransformer", fp16_enabled=False,
+                                 decoder=dict(type="Uni3DETRTransformerDecoder", num_layers=L,
+                                              return_intermediate=True, transformerlayers=layer)),
+                bbox_coder=dict(type="NMSFreeCoder", pc_range=pc, post_center_range=pc, max_num=12, alpha=0.2,
+                                num_classes=ncls),
+                loss_cls=dict(type="SoftFocalLoss", use_sigmoid=True))
+    head = compat.build_from_cfg(hcfg, compat.HEADS).eval()
+    sd = dict(sd)
+    sd["code_weights"] = head.code_weights.data
+    head.load_state_dict(sd, strict=True)
+    return head.to(DEV)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 3e-2)])
+def test_head_forward_golden(golden, dtype, tol):
+    """Product Uni3DETRHead/Transformer/Decoder vs outputs of the reference's own classes."""
+    head = head_fixture(golden)
+    head.set_compute_dtype(dtype)
+    feats = T(golden["head_feats"]).to(DEV, dtype).contiguous(memory_format=torch.channels_last_3d)
+    outs = head(feats, None, T(golden["head_fps"]).to(DEV), random_point=T(golden["head_rand"]).to(DEV))
+    for k in ("all_cls_scores", "all_bbox_preds", "all_iou_preds"):
+        assert outs[k].shape == golden["head_" + k].shape
+        assert relerr(outs[k], golden["head_" + k]) < tol, (k, relerr(outs[k], golden["head_" + k]))
+
+
+def test_nms_free_coder_golden(golden):
+    head = head_fixture(golden)
+    outs = {k: T(golden["head_" + k]).to(DEV) for k in ("all_cls_scores", "all_bbox_preds", "all_iou_preds")}
+    res = head.bbox_coder.decode(outs)
+    for i, r in enumerate(res):
+        np.testing.assert_array_equal(r["labels"].cpu().numpy(), golden[f"coder_{i}_labels"])
+        for k in ("bboxes", "scores", "ious"):
+            np.testing.assert_allclose(r[k].cpu().numpy(), golden[f"coder_{i}_{k}"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 2e-2)])
+def test_dense_cnn_golden(golden, dtype, tol):
+    """Product SECOND3D/SECOND3DFPN (folded BN, NDHWC, 2-D conv trick) vs the reference's classes."""
+    from test_oracle_golden import DENSE_BCFG, DENSE_NCFG, dense_state_dicts
+    from uni3detr_b200 import compat, register_all
+    register_all()
+    bsd, nsd = dense_state_dicts()
+    bb = compat.build_from_cfg(dict(type="SECOND3D", **DENSE_BCFG), compat.BACKBONES).eval()
+    nk = compat.build_from_cfg(dict(type="SECOND3DFPN", **DENSE_NCFG), compat.NECKS).eval()
+    bb.load_state_dict(bsd, strict=True)
+    nk.load_state_dict(nsd, strict=True)
+    bb, nk = bb.to(DEV), nk.to(DEV)
+    bb.compute_dtype = nk.compute_dtype = dtype
+    xs = bb(T(golden["dense_in"]).to(DEV))
+    for i, x in enumerate(xs):
+        assert relerr(x, golden[f"dense_bb{i}"]) < tol
+    y = nk(xs)
+    assert relerr(y, golden["dense_out"]) < tol
+
+
+def test_decode_fixed_equals_decode(golden):
+    head = head_fixture(golden)
+    outs = {k: T(golden["head_" + k]).to(DEV) for k in ("all_cls_scores", "all_bbox_preds", "all_iou_preds")}
+    boxes, scores, labels, mask = head.bbox_coder.decode_fixed(outs)
+    for i, r in enumerate(head.bbox_coder.decode(outs)):
+        torch.testing.assert_close(boxes[i][mask[i]], r["bboxes"])
+        torch.testing.assert_close(scores[i][mask[i]], r["scores"])
+        assert bool((labels[i][mask[i]] == r["labels"]).all())

@@ -55,6 +55,7 @@ _vp, _i32, _f32, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_s
 SIGNATURES = {
     "u3d_last_error": (ctypes.c_char_p, []),
     "u3d_version": (_i32, []),
+    "u3d_launch_count": (ctypes.c_ulonglong, []),
     "u3d_voxmap_words": (_sz, [_i32] * 4),
     "u3d_scan_scratch_ints": (_sz, [_sz]),
     "u3d_voxelize_hard": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32,

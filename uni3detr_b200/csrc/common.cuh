@@ -32,7 +32,14 @@ void set_error(const char* fmt, ...);
     }                                                                          \
   } while (0)
 
-#define U3D_LAUNCH_CHECK() U3D_CUDA(cudaGetLastError())
+// every kernel launch of this library goes through U3D_LAUNCH_CHECK: it also feeds the
+// launch counter behind u3d_launch_count() (bench.py reports it as `gpu_launches`).
+void count_launch();
+#define U3D_LAUNCH_CHECK()           \
+  do {                               \
+    ::u3d::count_launch();           \
+    U3D_CUDA(cudaGetLastError());    \
+  } while (0)
 
 constexpr int kNumSMs = 148;  // B200
 constexpr int kSlotEmpty = 0x7f7f7f7f;  // memset(0x7f) pattern; > any point index

@@ -208,6 +208,7 @@ static int launch_fps(const float* dist_src, int dist_stride, int dist_seg_strid
     U3D_CUDA(cudaFuncSetAttribute(k_fps<PPT, CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   U3D_CUDA(cudaLaunchKernelEx(&cfg, k_fps<PPT, CS>, dist_src, dist_stride, dist_seg_stride,
                               gather_src, gather_stride, seg, nq, reverse, idx, out));
+  count_launch();
   return U3D_OK;
 }
 

@@ -17,7 +17,8 @@ namespace u3d {
 struct VoxGeom {
   float lo[3];   // x,y,z
   float vs[3];   // x,y,z
-  int grid[3];   // x,y,z  (W,H,D)
+  int grid[3];   // x,y,z voxelization grid = round((hi-lo)/vs) like mmcv
+  int dims[3];   // x,y,z index space of the VoxelMap (W,H,D) = sparse_shape, >= grid
 };
 
 __device__ __forceinline__ int scene_of(const int32_t* __restrict__ s_off, int B, int p) {
@@ -53,7 +54,7 @@ k_vox_mark(const float* __restrict__ pts, const int32_t* __restrict__ pt_off, in
   extern __shared__ int32_t s_off[];
   for (int i = threadIdx.x; i <= B; i += blockDim.x) s_off[i] = pt_off[i];
   __syncthreads();
-  const int D = g.grid[2], H = g.grid[1], W = g.grid[0];
+  const int D = g.dims[2], H = g.dims[1], W = g.dims[0];
   // whole warps stay converged for the aggregated atomic
   const int per_round = gridDim.x * blockDim.x;
   int nrounds = (Ntot + per_round - 1) / per_round;
@@ -242,13 +243,26 @@ __global__ void k_scene_rows_from_map(const uint2* __restrict__ map, int B, uint
   if (b <= B) scene_rows[b] = map_rank_at(map, (uint32_t)b * cells_per_scene);
 }
 
+// mmcv Voxelization.__init__: grid = round((range[3:] - range[:3]) / voxel_size) in fp32.
+// (D,H,W) is the index space of the map (the encoder's sparse_shape): SECOND-style configs
+// declare it one cell deeper than the voxel grid (KITTI/nuScenes: grid z = 40, sparse z = 41).
 static int fill_geom(VoxGeom& g, const float* pc_range, const float* voxel_size, int D, int H, int W) {
+  const int dims[3] = {W, H, D};
   for (int i = 0; i < 3; ++i) {
     g.lo[i] = pc_range[i];
     g.vs[i] = voxel_size[i];
+    if (!(voxel_size[i] > 0.f)) {
+      set_error("voxel_size[%d] must be positive", i);
+      return U3D_EINVAL;
+    }
+    g.grid[i] = (int)nearbyintf((pc_range[3 + i] - pc_range[i]) / voxel_size[i]);
+    g.dims[i] = dims[i];
+    if (g.grid[i] < 1 || g.grid[i] > dims[i]) {
+      set_error("voxel grid axis %d = %d does not fit the index space %d", i, g.grid[i], dims[i]);
+      return U3D_EINVAL;
+    }
   }
-  g.grid[0] = W; g.grid[1] = H; g.grid[2] = D;
-  return 0;
+  return U3D_OK;
 }
 
 static inline int grid_for(long long n, int threads, int max_ctas = kNumSMs * 8) {
@@ -285,7 +299,7 @@ extern "C" int u3d_voxelize_hard(const float* points, const int32_t* pt_off, int
   U3D_CHECK_ARG(cap >= need, "u3d_voxelize_hard: cap=%d < %lld", cap, need);
   uint2* map = (uint2*)map_;
   VoxGeom g;
-  fill_geom(g, pc_range, voxel_size, D, H, W);
+  if (int grc = fill_geom(g, pc_range, voxel_size, D, H, W)) return grc;
   U3D_CUDA(cudaMemsetAsync(map, 0, words * sizeof(uint2), st));
   U3D_CUDA(cudaMemsetAsync(slots, 0x7f, (size_t)max(Ntot, 1) * max_pts * sizeof(int32_t), st));
   if (voxels == nullptr && feats == nullptr) {
@@ -335,7 +349,7 @@ extern "C" int u3d_voxelize_dynamic(const float* points, const int32_t* pt_off, 
   }
   uint2* map = (uint2*)map_;
   VoxGeom g;
-  fill_geom(g, pc_range, voxel_size, D, H, W);
+  if (int grc = fill_geom(g, pc_range, voxel_size, D, H, W)) return grc;
   U3D_CUDA(cudaMemsetAsync(map, 0, words * sizeof(uint2), st));
   U3D_CUDA(cudaMemsetAsync(cnt, 0, (size_t)max(cap, 1) * sizeof(int32_t), st));
   U3D_CUDA(cudaMemsetAsync(feats, 0, (size_t)max(cap, 1) * C * sizeof(float), st));

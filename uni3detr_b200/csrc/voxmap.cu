@@ -6,6 +6,7 @@
 // The scan is HBM/L2 streaming work: 8 B read + 4 B written per word, three launches
 // (chunk partial sums, one-CTA scan of the partials, apply).
 #include <stdarg.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace u3d {
@@ -18,6 +19,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
@@ -113,6 +117,7 @@ extern "C" {
 
 const char* u3d_last_error(void) { return u3d::g_err; }
 int u3d_version(void) { return 100; }
+unsigned long long u3d_launch_count(void) { return u3d::g_launches.load(std::memory_order_relaxed); }
 
 size_t u3d_voxmap_words(int B, int D, int H, int W) {
   if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;

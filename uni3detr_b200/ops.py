@@ -6,12 +6,45 @@ sizes stay on the device (int32 counters), buffers are sized by capacity.
 There is no CPU path: tensors must live on a CUDA device.
 """
 import ctypes
+import functools
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
 import torch
 
 from . import _lib
+
+# -- optional per-op device timing (bench.py's roofline pass): CUDA events on the launching stream
+_PROF = None
+
+
+def profile_begin():
+    global _PROF
+    _PROF = []
+
+
+def profile_end():
+    """Returns [(op name, info dict, milliseconds)] for every op since profile_begin()."""
+    global _PROF
+    rec, _PROF = _PROF or [], None
+    torch.cuda.synchronize()
+    return [(n, i, s.elapsed_time(e)) for n, i, s, e in rec]
+
+
+def _timed(info=None):
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*a, **k):
+            if _PROF is None:
+                return fn(*a, **k)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **k)
+            e.record()
+            _PROF.append((fn.__name__, info(r, *a, **k) if info else {}, s, e))
+            return r
+        return wrapper
+    return deco
 
 U3D_F32, U3D_BF16 = 0, 1
 ORDER_FIRST_APPEARANCE, ORDER_LINEAR = 0, 1
@@ -85,6 +118,7 @@ class Voxels:
         return self.scene_rows[-1:]
 
 
+@_timed(lambda r, points, *a, **k: dict(n_points=points.shape[0], C=points.shape[1], out=r))
 def voxelize_hard(points, pt_off, B, pc_range, voxel_size, grid_zyx, max_pts, max_voxels,
                   deterministic=True, want_voxels=False) -> Voxels:
     lib = _lib.load()
@@ -117,6 +151,7 @@ def voxelize_hard(points, pt_off, B, pc_range, voxel_size, grid_zyx, max_pts, ma
                   VoxelMap(vm, row_of_rank, B, (D, H, W)), cap)
 
 
+@_timed(lambda r, points, *a, **k: dict(n_points=points.shape[0], C=points.shape[1], out=r))
 def voxelize_dynamic(points, pt_off, B, pc_range, voxel_size, grid_zyx) -> Voxels:
     lib = _lib.load()
     _req(points, torch.float32, "points")
@@ -157,6 +192,7 @@ def voxmap_build(coors, n_rows, cap, B, dims) -> VoxelMap:
     return VoxelMap(vm, perm, B, (D, H, W))
 
 
+@_timed(lambda r, coors, n_rows, *a, **k: dict(n_rows=n_rows, nbr=r))
 def rulebook_subm(coors, n_rows, cap, vmap: VoxelMap, nbr=None):
     lib = _lib.load()
     _req(coors, torch.int32, "coors")
@@ -172,6 +208,7 @@ def conv_out_dims(in_dims, stride, pad, k=3):
     return tuple((int(d) + 2 * int(p) - k) // int(s) + 1 for d, s, p in zip(in_dims, stride, pad))
 
 
+@_timed(lambda r, coors, n_rows, *a, **k: dict(n_rows=n_rows, n_out=r[1], nbr=r[3]))
 def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=None):
     lib = _lib.load()
     _req(coors, torch.int32, "coors")
@@ -208,6 +245,9 @@ def rulebook_pairs(nbr, n_out):
     return pairs, num
 
 
+@_timed(lambda r, x, nbr, n_out, out_cap, w, *a, **k: dict(
+    n_in=x.shape[0], n_out=n_out, nbr=nbr, K=w.shape[0], Cin=w.shape[1], Cout=w.shape[2],
+    esize=x.element_size()))
 def spconv_fwd(x, nbr, n_out, out_cap, w, scale=None, shift=None, residual=None, relu=False,
                out=None, impl=0):
     """out = act((sum_k x[nbr[k]] @ w[k]) * scale + shift (+ residual)); w is (K,Cin,Cout)."""
@@ -225,6 +265,7 @@ def spconv_fwd(x, nbr, n_out, out_cap, w, scale=None, shift=None, residual=None,
     return out
 
 
+@_timed(lambda r, feats, *a, **k: dict(bytes=r.numel() * r.element_size()))
 def sparse_to_dense(feats, coors, n_rows, cap, B, dims, channels_last=True, out=None):
     lib = _lib.load()
     D, H, W = [int(v) for v in dims]
@@ -238,6 +279,7 @@ def sparse_to_dense(feats, coors, n_rows, cap, B, dims, channels_last=True, out=
     return out
 
 
+@_timed(lambda r, dist_src, ds, dss, gs, gst, seg, B, max_n, nq, **k: dict(B=B, max_n=max_n, nq=nq))
 def fps(dist_src, dist_stride, dist_seg_stride, gather_src, gather_stride, seg, B, max_n, nq,
         reverse=False):
     """Batched D-FPS + gather + min-max normalise. Returns (idx (B,nq) int32, pts (B,nq,3) f32)."""
@@ -261,6 +303,7 @@ def coors_to_float(coors, rows=None):
     return out
 
 
+@_timed(lambda r, ref, *a, **k: dict(rows=ref.numel() // 3, bytes=r.numel() * r.element_size()))
 def sine_embed(ref, dtype=torch.float32):
     lib = _lib.load()
     _req(ref, torch.float32, "ref")
@@ -270,6 +313,8 @@ def sine_embed(ref, dtype=torch.float32):
     return out
 
 
+@_timed(lambda r, q, k_, v, n_seq, seq_len, heads: dict(n_seq=n_seq, seq_len=seq_len, heads=heads,
+                                                       esize=q.element_size()))
 def mha_core(q, k, v, n_seq, seq_len, heads):
     """q,k,v: 2-D views (n_seq*seq_len, heads*32), unit stride in dim 1 (row strides may differ,
     e.g. column slices of a packed QK projection). Returns (n_seq*seq_len, heads*32)."""
@@ -283,6 +328,8 @@ def mha_core(q, k, v, n_seq, seq_len, heads):
     return out
 
 
+@_timed(lambda r, value, ref, query, *a, **k: dict(rows=query.shape[0], C=query.shape[1],
+                                                   esize=query.element_size()))
 def cross_sample(value_ndhwc, ref, query, query_pos, gate_w, gate_b, Q):
     lib = _lib.load()
     B, D, H, W, C = value_ndhwc.shape
@@ -294,3 +341,8 @@ def cross_sample(value_ndhwc, ref, query, query_pos, gate_w, gate_b, Q):
                                     _p(query_pos), _p(gate_w), float(gate_b), Q, _p(out),
                                     _DT[value_ndhwc.dtype], _stream()))
     return out
+
+
+def launch_count():
+    """Kernels launched by libu3d_b200 in this process so far."""
+    return int(_lib.load().u3d_launch_count())

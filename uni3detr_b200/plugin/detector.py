@@ -42,6 +42,7 @@ class Uni3DETR(nn.Module):
         self.fps_stride_quirk = True
         self._fps_stream = None
         self.compute_dtype = torch.float32
+        self.capture = None   # set to a dict to keep intermediates (parity tests)
 
     # ------------------------------------------------------------------ config ---
     @property
@@ -73,7 +74,8 @@ class Uni3DETR(nn.Module):
         """list[B] of (N_i,C) f32 -> x (B,256,D,H,W), fpsbpts (B,2nq,3) in [0,1]."""
         B = len(pts)
         nq = self.num_query
-        points, pt_off, lens, vox = self.pts_voxel_layer.batched(pts)
+        points, pt_off, lens, vox = self.pts_voxel_layer.batched(
+            pts, index_dims=self.pts_middle_encoder.sparse_shape)
         C = points.shape[1]
         cur = torch.cuda.current_stream()
         if self._fps_stream is None:
@@ -98,10 +100,14 @@ class Uni3DETR(nn.Module):
             fpsbpts = torch.cat([fps1, fps2], 1)
         x = self.pts_middle_encoder.forward_voxels(vox.feats, vox.coors, vox.n_rows, vox.cap,
                                                    vox.vmap, B)
+        if self.capture is not None:
+            self.capture.update(voxels=vox, encoder=x)
         if self.with_pts_backbone:
             x = self.pts_backbone(x)
         if self.with_pts_neck:
             x = self.pts_neck(x)
+        if self.capture is not None:
+            self.capture.update(neck=x)
         cur.wait_stream(side)
         for t in (points, pt_off, vox.coors, vox.scene_rows, vox.pt_coors):
             if t is not None:

@@ -68,6 +68,30 @@ class NMSFreeCoder:
                 "scores": s ** self.alpha * ious ** (1 - self.alpha),
                 "labels": labels[mask], "ious": ious}
 
+    @torch.no_grad()
+    def decode_fixed(self, preds_dicts):
+        """Device-resident form of :meth:`decode` for the batched hot path: same arithmetic
+        (nms_free_coder.py:57-97,121-123) over the whole batch at once, but fixed-size outputs and
+        no host synchronisation - rows the reference would drop (centre outside
+        post_center_range, score <= score_threshold) are flagged in ``mask`` instead of removed.
+        Returns bboxes (B,max_num,7|9), scores (B,max_num), labels (B,max_num) int64, mask bool."""
+        cls = torch.mean(preds_dicts["all_cls_scores"][1:].float(), 0)
+        box = torch.mean(preds_dicts["all_bbox_preds"][1:].float(), 0)
+        iou = torch.mean(preds_dicts["all_iou_preds"][1:].float(), 0)
+        B, Q, C = cls.shape
+        scores, idx = cls.sigmoid().view(B, Q * C).topk(self.max_num, dim=1)
+        labels = idx % self.num_classes
+        qi = torch.div(idx, self.num_classes, rounding_mode="floor")
+        boxes = denormalize_bbox(torch.gather(box, 1, qi.unsqueeze(-1).expand(-1, -1, box.shape[-1])),
+                                 self.pc_range)
+        ious = torch.gather(iou.sigmoid().squeeze(-1), 1, qi)
+        pcr = scores.new_tensor(self.post_center_range)
+        mask = (boxes[..., :3] >= pcr[:3]).all(-1) & (boxes[..., :3] <= pcr[3:]).all(-1)
+        if self.score_threshold:
+            mask &= scores > self.score_threshold
+        final = scores ** self.alpha * ious ** (1 - self.alpha)
+        return boxes, final, labels, mask
+
     def decode(self, preds_dicts):
         cls = torch.mean(preds_dicts["all_cls_scores"][1:].float(), 0)
         box = torch.mean(preds_dicts["all_bbox_preds"][1:].float(), 0)

@@ -16,7 +16,7 @@ CONFIG_FILES = {
     "nuscenes": "uni3detr_nuscenes.py",
 }
 
-# model-relevant facts of the four BASELINE configs, so nothing has to read /root/reference at
+# model-relevant facts of the four BASELINE configs, so nothing has to read the reference tree at
 # run time on the GPU box (tests/golden/configs.json holds the full model dicts)
 WORKLOADS = {
     "sunrgbd": dict(config_id=2, n_points=20000, C=4, generator="room",
