@@ -155,13 +155,32 @@ int u3d_rulebook_pairs(const int32_t* nbr, int nbr_stride, const int32_t* n_out,
  *   in (n_in,Cin), out (n_out,Cout), residual (n_out,Cout) or NULL: dtype `dtype`
  *   w: (K,Cin,Cout) same dtype; scale/shift: (Cout) f32 or NULL (identity)
  *   nbr NULL means K==1 pointwise conv with identity mapping (conv_out 1x1x1).
- *   impl: 0 = auto, 1 = SIMT fp32-accumulate kernel, 2 = tcgen05 tensor-core kernel
- *         (bf16 only, Cin%16==0, 16<=Cout<=256 and Cout%16==0)
+ *   This entry point is the SIMT fp32-accumulate kernel (fp32 parity path and the K-starved
+ *   Cin in {4,5} stem); `impl` must be 0 or 1. bf16 layers with Cin >= 16 go through
+ *   u3d_spconv_fwd_packed below.
  */
 int u3d_spconv_fwd(const void* in, const int32_t* nbr, int nbr_stride, const int32_t* n_out,
                    int out_cap, int K, const void* w, const float* scale, const float* shift,
                    const void* residual, int relu, void* out, int Cin, int Cout, int dtype,
                    int impl, void* stream);
+
+/*
+ * Tensor-core flavour of u3d_spconv_fwd (bf16 activations/weights, fp32 accumulation in TMEM,
+ * tcgen05.mma): same arithmetic and epilogue, weights pre-packed ONCE per layer into the
+ * shared-memory image the tensor core reads (K-major (Cout x Cin-block) tiles, hardware swizzle),
+ * so a stage's weight tile is a single bulk (TMA) copy.
+ *   u3d_spconv_packed_bytes: size of the packed buffer, 0 if the shape is unsupported
+ *     (supported: Cin in {16, 32, 64, 128, ... multiples of 64 up to 512}; Cout a power of two in
+ *      [16, 512]; K <= 27)
+ *   u3d_spconv_pack_weights: w (K,Cin,Cout) bf16 row-major -> packed
+ *   u3d_spconv_fwd_packed: in/out/residual bf16, 16-byte aligned; other arguments as u3d_spconv_fwd
+ */
+size_t u3d_spconv_packed_bytes(int K, int Cin, int Cout);
+int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, void* packed, void* stream);
+int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr_stride, const int32_t* n_out,
+                          int out_cap, int K, const void* w_packed, const float* scale,
+                          const float* shift, const void* residual, int relu, void* out, int Cin,
+                          int Cout, void* stream);
 
 /*
  * SparseConvTensor.dense(): scatter rows into a zero-filled volume.

@@ -73,6 +73,12 @@ def test_spconv_subm(cin, cout, dtype, tol):
                                scale.to(DEV), shift.to(DEV),
                                residual=None if residual is None else residual.to(DEV, dtype), relu=relu, impl=impl)
             assert relerr(y, ref) < tol, (impl, residual is not None, relu, relerr(y, ref))
+        if dtype == torch.bfloat16 and ops.spconv_tc_supported(27, cin, cout):     # tcgen05 kernel
+            wp = ops.spconv_pack_weights(w.reshape(27, cin, cout).to(DEV, dtype).contiguous())
+            y = ops.spconv_fwd_packed(x.to(DEV, dtype), nbr, n_rows, n, wp, 27, cin, cout, scale.to(DEV),
+                                      shift.to(DEV), residual=None if residual is None else residual.to(DEV, dtype),
+                                      relu=relu)
+            assert relerr(y, ref) < tol, ("tc", residual is not None, relu, relerr(y, ref))
 
 
 @pytest.mark.parametrize("cin,cout", [(16, 32), (32, 64), (64, 128)])
@@ -94,6 +100,11 @@ def test_spconv_down(cin, cout, dtype, tol):
         y = ops.spconv_fwd(x.to(DEV, dtype), nbr, n_out, ocap, w.reshape(27, cin, cout).to(DEV, dtype).contiguous(),
                            scale.to(DEV), shift.to(DEV), relu=True, impl=impl)
         assert relerr(y[:m], ref) < tol, (impl, relerr(y[:m], ref))
+    if dtype == torch.bfloat16:
+        wp = ops.spconv_pack_weights(w.reshape(27, cin, cout).to(DEV, dtype).contiguous())
+        y = ops.spconv_fwd_packed(x.to(DEV, dtype), nbr, n_out, ocap, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV),
+                                  relu=True)
+        assert relerr(y[:m], ref) < tol, ("tc", relerr(y[:m], ref))
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
@@ -109,6 +120,11 @@ def test_spconv_pointwise_and_dense(dtype, tol):
     y = ops.spconv_fwd(x.to(DEV, dtype), None, n_rows, n, w.reshape(1, cin, cout).to(DEV, dtype).contiguous(),
                        scale.to(DEV), shift.to(DEV), relu=True)
     assert relerr(y, ref) < tol
+    if dtype == torch.bfloat16:
+        wp = ops.spconv_pack_weights(w.reshape(1, cin, cout).to(DEV, dtype).contiguous())
+        y2 = ops.spconv_fwd_packed(x.to(DEV, dtype), None, n_rows, n, wp, 1, cin, cout, scale.to(DEV), shift.to(DEV),
+                                   relu=True)
+        assert relerr(y2, ref) < tol
     c = T(coors).to(DEV)
     dref = torch.zeros(B, *dims, cout)
     cl = T(coors.astype(np.int64))
@@ -273,3 +289,23 @@ def test_decode_fixed_equals_decode(golden):
         torch.testing.assert_close(boxes[i][mask[i]], r["bboxes"])
         torch.testing.assert_close(scores[i][mask[i]], r["scores"])
         assert bool((labels[i][mask[i]] == r["labels"]).all())
+
+
+@pytest.mark.parametrize("cin,cout,n", [(256, 256, 700), (256, 512, 300), (128, 256, 129), (64, 64, 1), (16, 16, 128)])
+def test_spconv_tc_wide_and_ragged(cin, cout, n):
+    """tcgen05 kernel: Cin blocks > 1, Cout = 512 (two UMMA N halves), partial last tile, live count < capacity."""
+    from uni3detr_b200 import ops
+    dims, B, cap = (6, 12, 12), 1, n + 77
+    coors, x, w, scale, shift = conv_case(n, dims, B, cin, cout, n)
+    x, w = x.bfloat16().float(), w.bfloat16().float()
+    c = torch.cat([T(coors), torch.zeros(cap - n, 4, dtype=torch.int32)]).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, cap, B, dims)
+    nbr = ops.rulebook_subm(c, n_rows, cap, vm)
+    wp = ops.spconv_pack_weights(w.reshape(27, cin, cout).to(DEV, torch.bfloat16).contiguous())
+    xin = torch.cat([x, torch.full((cap - n, cin), float("nan"))]).to(DEV, torch.bfloat16)
+    out = torch.full((cap, cout), -5.0, device=DEV, dtype=torch.bfloat16)
+    ops.spconv_fwd_packed(xin, nbr, n_rows, cap, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV), relu=False, out=out)
+    ref = oracle_conv(x, G.subm_rulebook(coors, dims), w, n, scale, shift, None, False)
+    assert relerr(out[:n], ref) < 1e-2, relerr(out[:n], ref)
+    assert bool((out[n:] == -5.0).all())

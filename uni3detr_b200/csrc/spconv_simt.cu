@@ -165,13 +165,8 @@ extern "C" int u3d_spconv_fwd(const void* in, const int32_t* nbr, int nbr_stride
   U3D_CHECK_ARG(K >= 1 && Cin >= 1 && Cout >= 1 && out_cap >= 0, "u3d_spconv_fwd: bad shape");
   U3D_CHECK_ARG(nbr != nullptr || K == 1, "u3d_spconv_fwd: nbr==NULL requires K==1");
   U3D_CHECK_ARG(dtype == U3D_F32 || dtype == U3D_BF16, "u3d_spconv_fwd: bad dtype %d", dtype);
-  U3D_CHECK_ARG(impl >= 0 && impl <= 2, "u3d_spconv_fwd: bad impl %d", impl);
-  bool tc_ok = spconv_tc_supported(Cin, Cout, dtype);
-  if (impl == 2) U3D_CHECK_ARG(tc_ok, "u3d_spconv_fwd: tcgen05 path needs bf16, Cin%%16==0, Cout%%16==0, Cout<=256 (Cin=%d Cout=%d)", Cin, Cout);
-  bool use_tc = (impl == 2) || (impl == 0 && tc_ok && Cin >= 32);
-  if (use_tc)
-    return spconv_fwd_tc(in, nbr, nbr_stride, n_out, out_cap, K, w, scale, shift, residual, relu,
-                         out, Cin, Cout, st);
+  U3D_CHECK_ARG(impl == 0 || impl == 1, "u3d_spconv_fwd: impl %d (the tensor-core kernel takes packed "
+                "weights: u3d_spconv_fwd_packed)", impl);
   if (dtype == U3D_F32)
     return launch_simt<float>(in, nbr, nbr_stride, n_out, out_cap, K, w, scale, shift, residual,
                               relu, out, Cin, Cout, st);

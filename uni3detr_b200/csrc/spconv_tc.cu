@@ -1,10 +1,446 @@
-// placeholder replaced below by the tcgen05 implementation
+// K3 (tensor-core flavour) — sparse conv forward as an output-stationary gather-GEMM on the
+// 5th-generation tensor cores: tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) with the accumulator
+// tile in TMEM, operands staged in shared memory through an mbarrier ring.
+//
+// Reference semantics: SURVEY.md A.3/A.4 (spconv indice_conv: out[o] += in[i] @ W[k] over the
+// rulebook pairs, then BatchNorm1d(eval) + ReLU, SparseBasicBlock identity add) for the layers of
+// projects/mmdet3d_plugin/models/pts_encoder/sparse_encoder_hd.py:106-132.
+//
+// One CTA owns 128 consecutive output rows (UMMA M = 128 = the 128 TMEM lanes) and all Cout
+// columns (UMMA N = Cout <= 256 per instruction, two instructions for Cout = 512). The reduction
+// runs over the active kernel offsets k of the tile (offsets whose 128 rulebook entries are all
+// empty are skipped) and over Cin in blocks of CIN_BLK in {16,32,64} elements:
+//   A stage  = 128 gathered input rows x CIN_BLK bf16, K-major, hardware swizzle of 2*CIN_BLK bytes;
+//              written by 128 producer threads with 16-byte cp.async (zero-fill for missing
+//              neighbours), made visible to the tensor core with fence.proxy.async + mbarrier;
+//   B stage  = W[k][:, block] as a pre-swizzled (Cout x CIN_BLK) K-major image that
+//              u3d_spconv_pack_weights laid out in HBM, fetched with ONE cp.async.bulk (TMA) per
+//              stage that completes on the same mbarrier;
+//   MMA      = one elected thread issues CIN_BLK/16 tcgen05.mma per stage and releases the stage
+//              with tcgen05.commit; a final commit signals the epilogue;
+//   epilogue = the 4 producer warps read their TMEM lane quarter with tcgen05.ld (32x32b.x16),
+//              apply scale/shift (+residual) (+ReLU) and store bf16 rows with 16-byte stores.
+// Several CTAs are co-resident per SM (smem <= ~100 KB, TMEM columns = Cout), so one CTA's
+// epilogue overlaps the gathers and MMAs of its neighbours.
+#include <stdlib.h>
 #include "common.cuh"
+
 namespace u3d {
-bool spconv_tc_supported(int, int, int) { return false; }
-int spconv_fwd_tc(const void*, const int32_t*, int, const int32_t*, int, int, const void*,
-                  const float*, const float*, const void*, int, void*, int, int, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return U3D_EINVAL;
+
+namespace tc {
+
+constexpr int kRows = 128;            // UMMA M
+constexpr int kProducerThreads = 128; // warps 0-3: gather + epilogue
+constexpr int kThreads = 160;         // + warp 4: MMA issue
+constexpr int kMaxK = 27;
+constexpr int kLag = 2;               // cp.async groups a producer keeps in flight
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+        "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in the canonical swizzled layout: rows of P = 2*CIN_BLK bytes, 16-byte
+// chunk index XORed with address bits [7, 7+log2(P/16)); 8-row groups are SBO = 8*P bytes apart.
+template <int CIN_BLK> struct Swz {
+  static constexpr int P = 2 * CIN_BLK;                 // row pitch in bytes = swizzle span
+  static constexpr uint32_t kMask = P / 16 - 1;         // 7 (128B), 3 (64B), 1 (32B)
+  static constexpr uint64_t kLayout = P == 128 ? 2 : (P == 64 ? 4 : 6);
+  static constexpr int kSBO = 8 * P;
+  __host__ __device__ static inline uint32_t offset(int row, int chunk) {
+    uint32_t o = (uint32_t)row * P + (uint32_t)chunk * 16;
+    return o ^ (((o >> 7) & kMask) << 4);
+  }
+  __device__ static inline uint64_t desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46) |
+           (kLayout << 61);
+  }
+};
+
+struct Smem {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+  int n_active;
+  int active[kMaxK];
+  float scale[512];
+  float shift[512];
+  int nbr[kMaxK][kRows];
+};
+
+template <int CIN_BLK>
+__global__ void __launch_bounds__(kThreads)
+k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
+            const int32_t* __restrict__ n_out_p, int K, const __nv_bfloat16* __restrict__ wpk,
+            const float* __restrict__ scale, const float* __restrict__ shift,
+            const __nv_bfloat16* __restrict__ residual, int relu, __nv_bfloat16* __restrict__ out,
+            int Cin, int Cout, int stages, uint32_t tmem_cols) {
+  using SW = Swz<CIN_BLK>;
+  constexpr int kChunks = CIN_BLK / 8;                    // 16-byte chunks per A row
+  constexpr int kABytes = kRows * SW::P;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int n_out = *n_out_p;
+  const int m0 = blockIdx.x * kRows;
+  if (m0 >= n_out) return;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = Cin / CIN_BLK;
+  const uint32_t b_bytes = (uint32_t)Cout * SW::P;
+  const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  Smem& S = *reinterpret_cast<Smem*>(tiles + (size_t)stages * stage_bytes);
+
+  // ---- prologue: barriers, TMEM, rulebook slice, epilogue constants
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&S.full[s], kProducerThreads + 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    mbar_init(&S.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&S.tmem_base)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < kProducerThreads) {
+    const int o = m0 + tid;
+    for (int k = 0; k < K; ++k) {
+      int r = -1;
+      if (o < n_out) r = nbr ? __ldg(&nbr[(size_t)k * nbr_stride + o]) : o;
+      S.nbr[k][tid] = r;
+    }
+    for (int c = tid; c < Cout; c += kProducerThreads) {
+      S.scale[c] = scale ? __ldg(&scale[c]) : 1.f;
+      S.shift[c] = shift ? __ldg(&shift[c]) : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 0) {  // active-offset list of this tile (warp-uniform ballots)
+    int n = 0;
+    for (int k = 0; k < K; ++k) {
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < kRows / 32; ++j) any |= S.nbr[k][lane + 32 * j] >= 0;
+      if (__any_sync(0xffffffffu, any)) {
+        if (lane == 0) S.active[n] = k;
+        ++n;
+      }
+    }
+    if (lane == 0) S.n_active = n;
+  }
+  __syncthreads();
+  const int n_stage_total = S.n_active * nkb;
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp < 4) {
+    // ================= producers: gather A (cp.async) + fetch B (TMA bulk) =================
+    const int chunk = tid % kChunks;
+    const int row0 = tid / kChunks;
+    constexpr int kRowStep = kProducerThreads / kChunks;
+    const int lag = stages > kLag ? kLag : 1;
+    for (int st = 0; st < n_stage_total; ++st) {
+      const int slot = st % stages;
+      const uint32_t ph = (uint32_t)(st / stages) & 1u;
+      mbar_wait(&S.empty[slot], ph ^ 1u);
+      const int k = S.active[st / nkb], kb = st % nkb;
+      uint8_t* a_tile = tiles + (size_t)slot * stage_bytes;
+      if (tid == 0) {
+        mbar_expect_tx(&S.full[slot], b_bytes);
+        bulk_g2s(a_tile + kABytes, (const uint8_t*)wpk + ((size_t)k * nkb + kb) * b_bytes, b_bytes,
+                 &S.full[slot]);
+      }
+      const uint32_t a_s = smem_u32(a_tile);
+      const __nv_bfloat16* src_col = in + (size_t)kb * CIN_BLK + chunk * 8;
+#pragma unroll
+      for (int i = 0; i < kRows / kRowStep; ++i) {
+        const int r = row0 + i * kRowStep;
+        const int src_row = S.nbr[k][r];
+        const void* src = src_row >= 0 ? (const void*)(src_col + (size_t)src_row * Cin) : (const void*)in;
+        cp_async16(a_s + SW::offset(r, chunk), src, src_row >= 0 ? 16u : 0u);
+      }
+      cp_async_commit();
+      // deferred arrive: keep `lag` gather groups in flight (lag < stages, or the ring deadlocks)
+      if (st >= lag) {
+        if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(&S.full[(st - lag) % stages]);
+      }
+    }
+    // drain the last `lag` groups in order
+    for (int st = n_stage_total > lag ? n_stage_total - lag : 0; st < n_stage_total; ++st) {
+      if (n_stage_total - 1 - st >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&S.full[st % stages]);
+    }
+
+    // ================= epilogue: TMEM -> registers -> global =================
+    if (n_stage_total > 0) {
+      mbar_wait(&S.acc_full, 0);
+      tc_fence_after();
+    }
+    const int o = m0 + tid;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < Cout; c0 += 16) {
+      uint32_t v[16];
+      if (n_stage_total > 0) {
+        tmem_ld16(lane_base + (uint32_t)c0, v);   // warp-collective: every lane participates
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (o < n_out) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * S.scale[c0 + j] + S.shift[c0 + j];
+        if (residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(residual + (size_t)o * Cout + c0);
+          uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 a = __bfloat1622float2(h0[j]), b = __bfloat1622float2(h1[j]);
+            f[2 * j] += a.x; f[2 * j + 1] += a.y;
+            f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint4 w0, w1;
+        __nv_bfloat162* p0 = reinterpret_cast<__nv_bfloat162*>(&w0);
+        __nv_bfloat162* p1 = reinterpret_cast<__nv_bfloat162*>(&w1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          p0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          p1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+        }
+        uint4* op = reinterpret_cast<uint4*>(out + (size_t)o * Cout + c0);
+        op[0] = w0;
+        op[1] = w1;
+      }
+    }
+    tc_fence_before();
+  } else if (lane == 0) {
+    // ================= MMA issuer (one thread) =================
+    const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 4) << 24);
+    for (int st = 0; st < n_stage_total; ++st) {
+      const int slot = st % stages;
+      const uint32_t ph = (uint32_t)(st / stages) & 1u;
+      mbar_wait(&S.full[slot], ph);
+      tc_fence_after();
+      const uint32_t a_s = smem_u32(tiles + (size_t)slot * stage_bytes);
+      const uint32_t b_s = a_s + kABytes;
+      for (int n0 = 0; n0 < Cout; n0 += 256) {
+        const int n = Cout - n0 < 256 ? Cout - n0 : 256;
+        const uint32_t idesc = idesc_base | ((uint32_t)(n >> 3) << 17);
+        const uint64_t a_desc = SW::desc(a_s);
+        const uint64_t b_desc = SW::desc(b_s + (uint32_t)n0 * SW::P);
+#pragma unroll
+        for (int kk = 0; kk < CIN_BLK / 16; ++kk)
+          umma_bf16(tmem + (uint32_t)n0, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                    (st > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(&S.empty[slot]);   // frees the stage once these MMAs have read it
+    }
+    if (n_stage_total > 0) umma_commit(&S.acc_full);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols)
+                 : "memory");
+  }
+}
+
+// (K,Cin,Cout) row-major bf16 -> [K][Cin/CIN_BLK] images of (Cout x CIN_BLK), K-major, swizzled
+template <int CIN_BLK>
+__global__ void __launch_bounds__(256)
+k_pack_w(const __nv_bfloat16* __restrict__ w, int K, int Cin, int Cout, __nv_bfloat16* __restrict__ out) {
+  using SW = Swz<CIN_BLK>;
+  const int nkb = Cin / CIN_BLK;
+  const size_t total = (size_t)K * Cin * Cout;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
+       e += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(e % Cout);
+    const int c = (int)((e / Cout) % Cin);
+    const int k = (int)(e / ((size_t)Cout * Cin));
+    const int kb = c / CIN_BLK, cc = c % CIN_BLK;
+    const size_t img = ((size_t)k * nkb + kb) * ((size_t)Cout * SW::P);
+    const uint32_t off = SW::offset(n, cc / 8) + (uint32_t)(cc % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + img + off) = w[e];
+  }
+}
+
+static inline int cin_blk_for(int Cin) { return Cin % 64 == 0 ? 64 : (Cin == 32 ? 32 : (Cin == 16 ? 16 : 0)); }
+
+}  // namespace tc
+
+bool spconv_tc_supported(int Cin, int Cout, int dtype) {
+  if (dtype != U3D_BF16) return false;
+  if (tc::cin_blk_for(Cin) == 0 || Cin > 512) return false;
+  if (Cout < 16 || Cout > 512 || (Cout & (Cout - 1)) != 0) return false;  // power of two: TMEM columns
+  return true;
+}
+
+int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride, const int32_t* n_out,
+                  int out_cap, int K, const void* wpk, const float* scale, const float* shift,
+                  const void* residual, int relu, void* out, int Cin, int Cout, cudaStream_t st) {
+  using namespace tc;
+  U3D_CHECK_ARG(K >= 1 && K <= kMaxK, "spconv tc: K=%d unsupported", K);
+  U3D_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)wpk | (uintptr_t)residual) & 15) == 0,
+                "spconv tc: buffers must be 16-byte aligned");
+  const int blk = cin_blk_for(Cin);
+  const uint32_t P = 2 * blk;
+  const uint32_t b_bytes = (uint32_t)Cout * P;
+  const uint32_t stage_bytes = kRows * P + ((b_bytes + 1023u) & ~1023u);
+  // two co-resident CTAs per SM when >= 3 stages fit in ~92 KB (one CTA's epilogue then overlaps
+  // its neighbour's gathers); otherwise one CTA per SM with as deep a ring as fits. 2..8 stages.
+  const size_t fixed = sizeof(Smem) + 1024;
+  int stages = (int)((110u * 1024u - fixed) / stage_bytes);
+  if (stages < 3) stages = (int)((220u * 1024u - fixed) / stage_bytes);
+  if (const char* e = getenv("U3D_TC_STAGES")) stages = atoi(e);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  U3D_CHECK_ARG(smem <= 227 * 1024, "spconv tc: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
+  uint32_t tmem_cols = Cout < 32 ? 32 : (uint32_t)Cout;
+  int tiles = cdiv(out_cap, kRows);
+  if (tiles < 1) return U3D_OK;
+#define U3D_TC_LAUNCH(BLK)                                                                          \
+  do {                                                                                              \
+    U3D_CUDA(cudaFuncSetAttribute(k_spconv_tc<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                  (int)smem));                                                      \
+    k_spconv_tc<BLK><<<tiles, kThreads, smem, st>>>(                                                \
+        (const __nv_bfloat16*)in, nbr, nbr_stride, n_out, K, (const __nv_bfloat16*)wpk, scale, shift, \
+        (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, tmem_cols);   \
+  } while (0)
+  if (blk == 64) U3D_TC_LAUNCH(64);
+  else if (blk == 32) U3D_TC_LAUNCH(32);
+  else U3D_TC_LAUNCH(16);
+#undef U3D_TC_LAUNCH
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
 }  // namespace u3d
+
+using namespace u3d;
+
+extern "C" size_t u3d_spconv_packed_bytes(int K, int Cin, int Cout) {
+  if (!spconv_tc_supported(Cin, Cout, U3D_BF16) || K < 1) return 0;
+  return (size_t)K * Cin * Cout * sizeof(__nv_bfloat16);
+}
+
+extern "C" int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, void* packed,
+                                       void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  U3D_CHECK_ARG(w && packed, "u3d_spconv_pack_weights: null buffer");
+  U3D_CHECK_ARG(spconv_tc_supported(Cin, Cout, U3D_BF16) && K >= 1 && K <= tc::kMaxK,
+                "u3d_spconv_pack_weights: unsupported shape K=%d Cin=%d Cout=%d", K, Cin, Cout);
+  const size_t total = (size_t)K * Cin * Cout;
+  int grid = (int)((total + 255) / 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  const int blk = tc::cin_blk_for(Cin);
+  if (blk == 64) tc::k_pack_w<64><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, K, Cin, Cout, (__nv_bfloat16*)packed);
+  else if (blk == 32) tc::k_pack_w<32><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, K, Cin, Cout, (__nv_bfloat16*)packed);
+  else tc::k_pack_w<16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, K, Cin, Cout, (__nv_bfloat16*)packed);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+extern "C" int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr_stride,
+                                     const int32_t* n_out, int out_cap, int K, const void* w_packed,
+                                     const float* scale, const float* shift, const void* residual,
+                                     int relu, void* out, int Cin, int Cout, void* stream) {
+  U3D_CHECK_ARG(in && n_out && w_packed && out, "u3d_spconv_fwd_packed: null buffer");
+  U3D_CHECK_ARG(nbr != nullptr || K == 1, "u3d_spconv_fwd_packed: nbr==NULL requires K==1");
+  U3D_CHECK_ARG(spconv_tc_supported(Cin, Cout, U3D_BF16),
+                "u3d_spconv_fwd_packed: needs Cin in {16,32,64k<=512}, Cout a power of two in [16,512] "
+                "(Cin=%d Cout=%d)", Cin, Cout);
+  return spconv_fwd_tc(in, nbr, nbr_stride, n_out, out_cap, K, w_packed, scale, shift, residual, relu, out,
+                       Cin, Cout, (cudaStream_t)stream);
+}

@@ -265,6 +265,41 @@ def spconv_fwd(x, nbr, n_out, out_cap, w, scale=None, shift=None, residual=None,
     return out
 
 
+def spconv_tc_supported(K, Cin, Cout):
+    return _lib.load().u3d_spconv_packed_bytes(K, Cin, Cout) != 0
+
+
+def spconv_pack_weights(w):
+    """(K,Cin,Cout) bf16 -> packed tensor-core weight image (see include/u3d.h)."""
+    lib = _lib.load()
+    _req(w, torch.bfloat16, "w")
+    K, Cin, Cout = w.shape
+    nbytes = lib.u3d_spconv_packed_bytes(K, Cin, Cout)
+    if nbytes == 0:
+        raise _lib.U3DError(f"tensor-core sparse conv does not support K={K} Cin={Cin} Cout={Cout}")
+    packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.u3d_spconv_pack_weights(_p(w), K, Cin, Cout, _p(packed), _stream()))
+    return packed
+
+
+@_timed(lambda r, x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, *a, **k: dict(
+    n_in=x.shape[0], n_out=n_out, nbr=nbr, K=K, Cin=Cin, Cout=Cout, esize=2, tc=True))
+def spconv_fwd_packed(x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, scale=None, shift=None,
+                      residual=None, relu=False, out=None):
+    """tcgen05 sparse conv: bf16 in/out, weights from spconv_pack_weights."""
+    lib = _lib.load()
+    _req(x, torch.bfloat16, "x")
+    if residual is not None:
+        _req(residual, torch.bfloat16, "residual")
+    if out is None:
+        out = torch.empty((out_cap, Cout), dtype=torch.bfloat16, device=x.device)
+    stride = nbr.stride(0) if nbr is not None else 0
+    _lib.check(lib.u3d_spconv_fwd_packed(_p(x), _p(nbr), stride, _p(n_out), out_cap, K, _p(w_packed),
+                                         _p(scale), _p(shift), _p(residual), int(bool(relu)), _p(out),
+                                         Cin, Cout, _stream()))
+    return out
+
+
 @_timed(lambda r, feats, *a, **k: dict(bytes=r.numel() * r.element_size()))
 def sparse_to_dense(feats, coors, n_rows, cap, B, dims, channels_last=True, out=None):
     lib = _lib.load()

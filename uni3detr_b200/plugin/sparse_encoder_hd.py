@@ -134,7 +134,7 @@ class SparseEncoderHD(nn.Module):
         if fp16_enabled:
             self.fp16_enabled = fp16_enabled
         self.compute_dtype = torch.float32
-        self.conv_impl = 0  # 0 auto, 1 SIMT, 2 tcgen05 (see u3d_spconv_fwd)
+        self.use_tensor_cores = True  # bf16 layers with Cin >= 16 run on tcgen05 (u3d_spconv_fwd_packed)
 
         self.conv_input = make_sparse_convmodule(in_channels, base_channels, 3, norm_cfg=norm_cfg,
                                                  padding=1, indice_key="subm1",
@@ -211,10 +211,16 @@ class SparseEncoderHD(nn.Module):
             k = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
             w = conv.weight.detach().reshape(k, conv.in_channels, conv.out_channels)
             scale, shift = _fold_bn(s["bn"], conv.bias)
-            steps.append(dict(w=w.to(dtype).contiguous(), scale=scale, shift=shift, relu=s["relu"],
+            w = w.to(dtype).contiguous()
+            packed = None
+            if (self.use_tensor_cores and dtype == torch.bfloat16 and w.is_cuda
+                    and ops.spconv_tc_supported(k, conv.in_channels, conv.out_channels)):
+                packed = ops.spconv_pack_weights(w)
+            steps.append(dict(w=w, packed=packed, scale=scale, shift=shift, relu=s["relu"],
                               save=s["save"], add=s["add"], subm=conv.subm, k=k,
+                              cin=conv.in_channels, cout=conv.out_channels,
                               stride=conv.stride, pad=conv.padding))
-        self._plan = dict(dtype=dtype, steps=steps)
+        self._plan = dict(dtype=dtype, steps=steps, tc=self.use_tensor_cores)
         return self._plan
 
     # --------------------------------------------------------------- forward ----
@@ -226,7 +232,7 @@ class SparseEncoderHD(nn.Module):
             raise NotImplementedError("SparseEncoderHD: training-mode BN is a 'next' row "
                                       "(SURVEY.md 8f); call .eval()")
         plan = self._plan
-        if plan is None or plan["dtype"] != self.compute_dtype:
+        if plan is None or plan["dtype"] != self.compute_dtype or plan["tc"] != self.use_tensor_cores:
             plan = self.prepare()
         dtype = plan["dtype"]
         x = feats.to(dtype).contiguous()
@@ -248,9 +254,14 @@ class SparseEncoderHD(nn.Module):
                 out_level = dict(coors=oc, n=on, cap=ocap, vmap=ovm, nbr=None, dims=ovm.dims)
             if st["save"]:
                 saved = x
-            x = ops.spconv_fwd(x, nbr, out_level["n"], out_level["cap"], st["w"], st["scale"],
-                               st["shift"], residual=saved if st["add"] else None, relu=st["relu"],
-                               impl=self.conv_impl)
+            res = saved if st["add"] else None
+            if st["packed"] is not None:
+                x = ops.spconv_fwd_packed(x, nbr, out_level["n"], out_level["cap"], st["packed"],
+                                          st["k"], st["cin"], st["cout"], st["scale"], st["shift"],
+                                          residual=res, relu=st["relu"])
+            else:
+                x = ops.spconv_fwd(x, nbr, out_level["n"], out_level["cap"], st["w"], st["scale"],
+                                   st["shift"], residual=res, relu=st["relu"])
             if st["add"]:
                 saved = None
             level = out_level
