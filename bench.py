@@ -154,8 +154,9 @@ def roofline_pass(step_fn, peaks, reps=3):
         ops.profile_begin()
         step_fn()
         for name, info, ms in ops.profile_end():
-            if name == "spconv_fwd":
-                key = f"spconv_fwd[{info['K']}x{info['Cin']}->{info['Cout']}]"
+            if name in ("spconv_fwd", "spconv_fwd_packed"):
+                key = f"{'spconv_tc' if name.endswith('packed') else 'spconv_simt'}[{info['K']}x{info['Cin']}->{info['Cout']}]"
+                name = "spconv_fwd"
             elif name == "fps":
                 key = f"fps[n<={info['max_n']},nq={info['nq']}]"
             else:
