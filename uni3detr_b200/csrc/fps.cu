@@ -7,8 +7,12 @@
 //
 // Here one thread-block CLUSTER owns one scene: every thread keeps PPT points and their
 // running min-distances in registers for the whole kernel (points are read from HBM
-// exactly once: N*12 B), the per-iteration arg-max is a warp-shuffle reduction, a
-// shared-memory stage and - for clusters - one DSMEM exchange + cluster barrier.
+// exactly once: N*12 B). Per iteration: thread-local arg-max, warp arg-max with two REDUX
+// instructions on a packed (distance bits, ~index) key, one __syncthreads, CTA arg-max in
+// warp 0, then each CTA pushes one 32-byte candidate into every peer's shared memory
+// (st.shared::cluster) and arrives on the peer's mbarrier (release.cluster); waiting on the
+// local mbarrier (acquire.cluster) replaces the much slower barrier.cluster round trip.
+// Candidate slots and barriers are double-buffered by iteration parity.
 // All scenes of the batch run concurrently (grid = B clusters).
 //
 // Defined arithmetic (mirrored by oracle/): d = ((dx*dx + dy*dy) + dz*dz) with no FMA
@@ -21,45 +25,67 @@ namespace cg = cooperative_groups;
 
 namespace u3d {
 
-constexpr int kFpsThreads = 1024;
 constexpr int kFpsMaxNq = 4096;
 
-struct Cand {
-  float d;
-  int idx;
+// One candidate travelling between CTAs: 32 bytes = two 16-byte DSMEM stores.
+// (hi, lo) is the arg-max key: hi = bits of the (non-negative) distance, lo = ~index, so an
+// unsigned 64-bit max picks the largest distance and, on exact ties, the LOWEST index.
+struct __align__(16) FpsMsg {
+  uint32_t hi, lo;
   float x, y, z;
+  uint32_t pad[3];
 };
 
-__device__ __forceinline__ bool better(float d, int i, float d2, int i2) {
-  return d > d2 || (d == d2 && i < i2);
+__device__ __forceinline__ uint32_t fps_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-template <int PPT, int CS>
-__global__ void __launch_bounds__(kFpsThreads, 1)
+// warp arg-max of a (hi, lo) key with two REDUX instructions; returns true on the winning lane
+__device__ __forceinline__ bool warp_argmax(uint32_t hi, uint32_t lo, uint32_t& whi, uint32_t& wlo) {
+  whi = __reduce_max_sync(0xffffffffu, hi);
+  wlo = __reduce_max_sync(0xffffffffu, hi == whi ? lo : 0u);
+  return hi == whi && lo == wlo;
+}
+
+template <int THREADS, int PPT, int CS, bool SMEM_XYZ>
+__global__ void __launch_bounds__(THREADS, 1)
 k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
       const float* __restrict__ gather_src, int gather_stride, const int32_t* __restrict__ seg,
       int nq, int reverse, int32_t* __restrict__ idx_out, float* __restrict__ out) {
-  __shared__ Cand s_warp[32];
-  __shared__ Cand s_slot[2][CS];
+  constexpr int NW = THREADS / 32;
+  extern __shared__ float s_dyn[];              // SMEM_XYZ: x[PPT*THREADS], y[..], z[..]
+  __shared__ FpsMsg s_warp[NW];
+  __shared__ FpsMsg s_slot[2][CS];              // written by every CTA of the cluster (DSMEM)
+  __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ int s_sel[kFpsMaxNq];
   __shared__ float s_mm[6];
+  __shared__ float s_red[NW][6];
 
   const int scene = blockIdx.x / CS;
   const int crank = blockIdx.x % CS;  // == cluster block rank (1-D cluster)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s0 = seg[scene];
   const int n = seg[scene + 1] - s0;
   const float* base = dist_src + (size_t)s0 * dist_seg_stride;
 
-  float px[PPT], py[PPT], pz[PPT], td[PPT];
+  float px[SMEM_XYZ ? 1 : PPT], py[SMEM_XYZ ? 1 : PPT], pz[SMEM_XYZ ? 1 : PPT], td[PPT];
+  float* sx = s_dyn;
+  float* sy = s_dyn + PPT * THREADS;
+  float* sz = s_dyn + 2 * PPT * THREADS;
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
-    int i = (j * CS + crank) * kFpsThreads + threadIdx.x;
-    bool ok = i < n;
-    px[j] = ok ? __ldg(base + (size_t)i * dist_stride + 0) : 0.f;
-    py[j] = ok ? __ldg(base + (size_t)i * dist_stride + 1) : 0.f;
-    pz[j] = ok ? __ldg(base + (size_t)i * dist_stride + 2) : 0.f;
-    td[j] = ok ? 1e10f : -1.f;  // padding can never win (real distances are >= 0)
+    const int i = (j * CS + crank) * THREADS + tid;
+    const bool ok = i < n;
+    const float x = ok ? __ldg(base + (size_t)i * dist_stride + 0) : 0.f;
+    const float y = ok ? __ldg(base + (size_t)i * dist_stride + 1) : 0.f;
+    const float z = ok ? __ldg(base + (size_t)i * dist_stride + 2) : 0.f;
+    if (SMEM_XYZ) {
+      sx[j * THREADS + tid] = x; sy[j * THREADS + tid] = y; sz[j * THREADS + tid] = z;
+    } else {
+      px[j] = x; py[j] = y; pz[j] = z;
+    }
+    // padding keeps distance 0 and an index >= n: it loses against every real point
+    td[j] = ok ? 1e10f : 0.f;
   }
 
   float lx = 0.f, ly = 0.f, lz = 0.f;
@@ -68,81 +94,94 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
     ly = __ldg(base + 1);
     lz = __ldg(base + 2);
   }
-  if (threadIdx.x == 0) s_sel[0] = 0;
-  if (CS > 1) cg::this_cluster().sync();  // all CTAs of the cluster are resident before DSMEM use
+  if (tid == 0) {
+    s_sel[0] = 0;
+    if (CS > 1) {
+      for (int b = 0; b < 2; ++b)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&s_bar[b])), "r"(CS));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  if (CS > 1) cg::this_cluster().sync();  // barriers initialised + every CTA resident before DSMEM use
+  else __syncthreads();
 
   for (int it = 1; it < nq; ++it) {
-    // 1. update running distances, local arg-max (ascending index => strict '>' keeps lowest)
-    Cand best;
-    best.d = -2.f; best.idx = 0x7fffffff; best.x = 0.f; best.y = 0.f; best.z = 0.f;
+    // 1. update running distances, thread-local arg-max (ascending index: strict '>' keeps the lowest)
+    float bt = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+    int bj = 0;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
-      float dx = __fsub_rn(px[j], lx), dy = __fsub_rn(py[j], ly), dz = __fsub_rn(pz[j], lz);
-      float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      float t = fminf(td[j], d);
+      const float x = SMEM_XYZ ? sx[j * THREADS + tid] : px[j];
+      const float y = SMEM_XYZ ? sy[j * THREADS + tid] : py[j];
+      const float z = SMEM_XYZ ? sz[j * THREADS + tid] : pz[j];
+      const float dx = __fsub_rn(x, lx), dy = __fsub_rn(y, ly), dz = __fsub_rn(z, lz);
+      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const float t = fminf(td[j], d);
       td[j] = t;
-      if (t > best.d) {
-        best.d = t;
-        best.idx = (j * CS + crank) * kFpsThreads + threadIdx.x;
-        best.x = px[j]; best.y = py[j]; best.z = pz[j];
-      }
+      if (t > bt) { bt = t; bj = j; bx = x; by = y; bz = z; }
     }
-    // 2. warp arg-max on (d, idx); the winning lane publishes its coordinates
-    float wd = best.d;
-    int wi = best.idx;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float od = __shfl_xor_sync(0xffffffffu, wd, o);
-      int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-      if (better(od, oi, wd, wi)) { wd = od; wi = oi; }
+    const uint32_t hi = __float_as_uint(bt);
+    const uint32_t lo = 0xffffffffu - (uint32_t)((bj * CS + crank) * THREADS + tid);
+    // 2. warp arg-max (2 REDUX); the winning lane publishes key + coordinates
+    uint32_t whi, wlo;
+    if (warp_argmax(hi, lo, whi, wlo)) {
+      FpsMsg m;
+      m.hi = hi; m.lo = lo; m.x = bx; m.y = by; m.z = bz;
+      s_warp[warp] = m;
     }
-    if (best.idx == wi && best.d == wd) s_warp[warp] = best;  // unique: idx is unique
     __syncthreads();
-    // 3. CTA arg-max by warp 0
+    // 3. CTA arg-max by warp 0, then one 32-byte message to every CTA of the cluster
+    const int par = it & 1;
     if (warp == 0) {
-      Cand c = s_warp[lane];
-      float cd = c.d;
-      int ci = c.idx;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        float od = __shfl_xor_sync(0xffffffffu, cd, o);
-        int oi = __shfl_xor_sync(0xffffffffu, ci, o);
-        if (better(od, oi, cd, ci)) { cd = od; ci = oi; }
-      }
-      if (c.idx == ci && c.d == cd) {
-        if (CS == 1) {
-          s_slot[it & 1][0] = c;
-        } else {
-          cg::cluster_group cluster = cg::this_cluster();
-#pragma unroll
-          for (int r = 0; r < CS; ++r) {
-            Cand* remote = cluster.map_shared_rank(&s_slot[it & 1][crank], r);
-            *remote = c;
-          }
-        }
+      const bool have = lane < NW;
+      const uint32_t chi = have ? s_warp[lane].hi : 0u, clo = have ? s_warp[lane].lo : 0u;
+      uint32_t bhi, blo;
+      const bool win = warp_argmax(chi, clo, bhi, blo) && have;
+      const int src = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
+      if (CS == 1) {
+        if (lane == src) s_slot[par][0] = s_warp[lane];
+      } else if (lane < CS) {
+        const uint4* m = reinterpret_cast<const uint4*>(&s_warp[src]);
+        const uint4 m0 = m[0], m1 = m[1];
+        __syncwarp(__activemask());   // every sender has read the winner before anyone arrives
+        uint32_t rdst, rbar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(fps_smem_u32(&s_slot[par][crank])), "r"(lane));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(fps_smem_u32(&s_bar[par])), "r"(lane));
+        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rdst), "r"(m0.x), "r"(m0.y), "r"(m0.z), "r"(m0.w) : "memory");
+        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rdst + 16), "r"(m1.x), "r"(m1.y), "r"(m1.z), "r"(m1.w) : "memory");
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
       }
     }
+    // 4. wait for the CS candidates of this iteration, resolve the winner (identical in every CTA)
     if (CS == 1) {
       __syncthreads();
     } else {
-      cg::this_cluster().sync();
+      const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "FPS_WAIT:\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+          "@p bra FPS_DONE;\n\t"
+          "bra FPS_WAIT;\n\t"
+          "FPS_DONE:\n\t"
+          "}" ::"r"(fps_smem_u32(&s_bar[par])), "r"(parity) : "memory");
     }
-    // 4. every thread resolves the winner among the CS CTA candidates
-    Cand w = s_slot[it & 1][0];
+    FpsMsg w = s_slot[par][0];
 #pragma unroll
     for (int r = 1; r < CS; ++r) {
-      Cand c = s_slot[it & 1][r];
-      if (better(c.d, c.idx, w.d, w.idx)) w = c;
+      const FpsMsg c = s_slot[par][r];
+      if (c.hi > w.hi || (c.hi == w.hi && c.lo > w.lo)) w = c;
     }
     lx = w.x; ly = w.y; lz = w.z;
-    if (threadIdx.x == 0) s_sel[it] = w.idx;
+    if (tid == 0) s_sel[it] = (int)(0xffffffffu - w.lo);
   }
   __syncthreads();
   if (crank != 0) return;  // every CTA holds the same selection; rank 0 writes it
 
   // gather + per-scene min/max of the sampled set + normalise to [0,1]
   float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-  for (int q = threadIdx.x; q < nq; q += kFpsThreads) {
+  for (int q = tid; q < nq; q += THREADS) {
     int i = n > 0 ? s_sel[q] : 0;
     const float* g = gather_src + (size_t)(s0 + i) * gather_stride;
 #pragma unroll
@@ -160,20 +199,19 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
       mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
     }
   }
-  __shared__ float s_red[32][6];
   if (lane == 0) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) { s_red[warp][c] = mn[c]; s_red[warp][3 + c] = mx[c]; }
   }
   __syncthreads();
-  if (threadIdx.x < 6) {
-    int c = threadIdx.x;
+  if (tid < 6) {
+    int c = tid;
     float v = s_red[0][c];
-    for (int w = 1; w < 32; ++w) v = c < 3 ? fminf(v, s_red[w][c]) : fmaxf(v, s_red[w][c]);
+    for (int w = 1; w < NW; ++w) v = c < 3 ? fminf(v, s_red[w][c]) : fmaxf(v, s_red[w][c]);
     s_mm[c] = v;
   }
   __syncthreads();
-  for (int q = threadIdx.x; q < nq; q += kFpsThreads) {
+  for (int q = tid; q < nq; q += THREADS) {
     int i = n > 0 ? s_sel[q] : 0;
     idx_out[(size_t)scene * nq + q] = i;
     const float* g = gather_src + (size_t)(s0 + i) * gather_stride;
@@ -188,14 +226,16 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
   }
 }
 
-template <int PPT, int CS>
+template <int THREADS, int PPT, int CS, bool SMEM_XYZ>
 static int launch_fps(const float* dist_src, int dist_stride, int dist_seg_stride,
                       const float* gather_src, int gather_stride, const int32_t* seg, int B, int nq,
                       int reverse, int32_t* idx, float* out, cudaStream_t st) {
+  auto kern = k_fps<THREADS, PPT, CS, SMEM_XYZ>;
+  const size_t dyn = SMEM_XYZ ? (size_t)3 * PPT * THREADS * sizeof(float) : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(B * CS);
-  cfg.blockDim = dim3(kFpsThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = dyn;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -204,10 +244,11 @@ static int launch_fps(const float* dist_src, int dist_stride, int dist_seg_strid
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (CS > 8)
-    U3D_CUDA(cudaFuncSetAttribute(k_fps<PPT, CS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  U3D_CUDA(cudaLaunchKernelEx(&cfg, k_fps<PPT, CS>, dist_src, dist_stride, dist_seg_stride,
-                              gather_src, gather_stride, seg, nq, reverse, idx, out));
+  if (CS > 8) U3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (dyn > 48 * 1024)
+    U3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  U3D_CUDA(cudaLaunchKernelEx(&cfg, kern, dist_src, dist_stride, dist_seg_stride, gather_src,
+                              gather_stride, seg, nq, reverse, idx, out));
   count_launch();
   return U3D_OK;
 }
@@ -233,22 +274,24 @@ extern "C" int u3d_fps(const float* dist_src, int dist_stride, int dist_seg_stri
   U3D_CHECK_ARG(B >= 1 && nq >= 1 && nq <= kFpsMaxNq && max_n >= 0, "u3d_fps: bad B/nq (nq<=%d)",
                 kFpsMaxNq);
   U3D_CHECK_ARG(dist_stride >= 3 && gather_stride >= 3 && dist_seg_stride >= 3, "u3d_fps: strides");
-#define U3D_FPS_CASE(PPT, CS)                                                                    \
-  if ((long long)max_n <= (long long)PPT * CS * kFpsThreads)                                     \
-    return launch_fps<PPT, CS>(dist_src, dist_stride, dist_seg_stride, gather_src, gather_stride, \
-                               seg, B, nq, reverse, idx, out, st);
-  // smallest register footprint that covers max_n; clusters first (latency), then PPT
-  // (a 1024-thread CTA has 64 registers/thread: at most ~13 points of 4 floats each)
-  U3D_FPS_CASE(4, 1)    //   4 096
-  U3D_FPS_CASE(4, 2)    //   8 192
-  U3D_FPS_CASE(4, 4)    //  16 384
-  U3D_FPS_CASE(4, 8)    //  32 768
-  U3D_FPS_CASE(8, 8)    //  65 536
-  U3D_FPS_CASE(12, 8)   //  98 304
-  U3D_FPS_CASE(8, 16)   // 131 072 (non-portable cluster of 16)
-  U3D_FPS_CASE(13, 16)  // 212 992
+#define U3D_FPS_CASE(THREADS, PPT, CS, SM)                                                         \
+  if ((long long)max_n <= (long long)THREADS * PPT * CS)                                          \
+    return launch_fps<THREADS, PPT, CS, SM>(dist_src, dist_stride, dist_seg_stride, gather_src,   \
+                                           gather_stride, seg, B, nq, reverse, idx, out, st);
+  // smallest configuration that keeps every point of a scene on chip: registers up to 16
+  // points/thread, shared memory for the coordinates beyond that (distances stay in registers)
+  U3D_FPS_CASE(256, 8, 1, false)     //   2 048
+  U3D_FPS_CASE(256, 8, 2, false)     //   4 096
+  U3D_FPS_CASE(256, 8, 4, false)     //   8 192
+  U3D_FPS_CASE(256, 8, 8, false)     //  16 384
+  U3D_FPS_CASE(256, 10, 8, false)    //  20 480
+  U3D_FPS_CASE(256, 16, 8, false)    //  32 768
+  U3D_FPS_CASE(512, 16, 8, false)    //  65 536
+  U3D_FPS_CASE(512, 13, 16, false)   // 106 496 (non-portable cluster of 16)
+  U3D_FPS_CASE(512, 16, 16, false)   // 131 072
+  U3D_FPS_CASE(512, 26, 16, true)    // 212 992
 #undef U3D_FPS_CASE
-  set_error("u3d_fps: max_n=%d exceeds the 212992-point register-resident limit", max_n);
+  set_error("u3d_fps: max_n=%d exceeds the 212992-point on-chip limit", max_n);
   return U3D_EINVAL;
 }
 

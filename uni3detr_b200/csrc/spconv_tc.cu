@@ -6,22 +6,25 @@
 // rulebook pairs, then BatchNorm1d(eval) + ReLU, SparseBasicBlock identity add) for the layers of
 // projects/mmdet3d_plugin/models/pts_encoder/sparse_encoder_hd.py:106-132.
 //
-// One CTA owns 128 consecutive output rows (UMMA M = 128 = the 128 TMEM lanes) and all Cout
-// columns (UMMA N = Cout <= 256 per instruction, two instructions for Cout = 512). The reduction
-// runs over the active kernel offsets k of the tile (offsets whose 128 rulebook entries are all
-// empty are skipped) and over Cin in blocks of CIN_BLK in {16,32,64} elements:
-//   A stage  = 128 gathered input rows x CIN_BLK bf16, K-major, hardware swizzle of 2*CIN_BLK bytes;
-//              written by 128 producer threads with 16-byte cp.async (zero-fill for missing
-//              neighbours), made visible to the tensor core with fence.proxy.async + mbarrier;
-//   B stage  = W[k][:, block] as a pre-swizzled (Cout x CIN_BLK) K-major image that
-//              u3d_spconv_pack_weights laid out in HBM, fetched with ONE cp.async.bulk (TMA) per
-//              stage that completes on the same mbarrier;
-//   MMA      = one elected thread issues CIN_BLK/16 tcgen05.mma per stage and releases the stage
-//              with tcgen05.commit; a final commit signals the epilogue;
-//   epilogue = the 4 producer warps read their TMEM lane quarter with tcgen05.ld (32x32b.x16),
-//              apply scale/shift (+residual) (+ReLU) and store bf16 rows with 16-byte stores.
-// Several CTAs are co-resident per SM (smem <= ~100 KB, TMEM columns = Cout), so one CTA's
-// epilogue overlaps the gathers and MMAs of its neighbours.
+// Persistent, warp-specialised kernel: one CTA per SM loops over 128-row output tiles (UMMA M =
+// 128 = the 128 TMEM lanes; N = Cout <= 256 per instruction, two instructions for Cout = 512).
+// The reduction of a tile runs over its ACTIVE kernel offsets (offsets whose 128 rulebook entries
+// are all empty are skipped) and over Cin in blocks of CIN_BLK in {16,32,64} elements.
+//   warps 5-12  producers: load the tile's rulebook slice (27 x 128 ints) into shared memory,
+//               derive the active-offset mask with warp ballots, then per stage gather
+//               128 input rows x CIN_BLK bf16 with 16-byte cp.async (zero-fill for missing
+//               neighbours) into a K-major stage with the hardware swizzle of 2*CIN_BLK bytes;
+//               a stage is published with fence.proxy.async + mbarrier arrive, `lag` stages
+//               late so several gathers stay in flight per thread. One producer thread fetches
+//               the stage's weight tile W[k][:, block] - a pre-swizzled (Cout x CIN_BLK) image
+//               laid out by u3d_spconv_pack_weights - with ONE cp.async.bulk (TMA) that completes
+//               on the same mbarrier.
+//   warp 4      MMA: one thread issues CIN_BLK/16 tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) per
+//               stage, releases the stage with tcgen05.commit, and commits the tile's accumulator.
+//   warps 0-3   epilogue: tcgen05.ld (32x32b.x16) of their TMEM lane quarter, scale/shift
+//               (+residual) (+ReLU), bf16 rows out with 16-byte stores. The accumulator is
+//               double-buffered in TMEM (2 x Cout columns), so the epilogue of tile i overlaps the
+//               gathers and MMAs of tile i+1.
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -29,11 +32,15 @@ namespace u3d {
 
 namespace tc {
 
-constexpr int kRows = 128;            // UMMA M
-constexpr int kProducerThreads = 128; // warps 0-3: gather + epilogue
-constexpr int kThreads = 160;         // + warp 4: MMA issue
+constexpr int kRows = 128;             // UMMA M
+constexpr int kEpiThreads = 128;       // warps 0-3: epilogue (TMEM lane quarter = warp id)
+constexpr int kMmaWarp = 4;            // warp 4: MMA issue + TMEM allocation
+constexpr int kProdWarp0 = 5;          // warps 5-12: producers
+constexpr int kProdThreads = 256;
+constexpr int kThreads = (kProdWarp0 * 32) + kProdThreads;   // 416
 constexpr int kMaxK = 27;
-constexpr int kLag = 2;               // cp.async groups a producer keeps in flight
+constexpr int kMaxStages = 12;
+constexpr int kMaxLag = 4;             // cp.async groups a producer keeps in flight
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -61,10 +68,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0u;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(dst)),
+          dst),
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
@@ -131,205 +151,263 @@ template <int CIN_BLK> struct Swz {
 };
 
 struct Smem {
-  uint64_t full[8];
-  uint64_t empty[8];
-  uint64_t acc_full;
+  uint64_t full[kMaxStages];    // producers (256 arrives) + weight TMA (1 arrive + tx bytes)
+  uint64_t empty[kMaxStages];   // tcgen05.commit: the MMAs that read the stage have retired
+  uint64_t acc_full[2];         // tcgen05.commit: accumulator of a tile is complete
+  uint64_t acc_empty[2];        // 128 epilogue threads: accumulator drained
+  uint64_t tile_ready[2];       // 256 producers: rulebook slice + active mask of a tile are in smem
+  uint64_t tile_free[2];        // MMA thread: mask consumed, slice buffer reusable
   uint32_t tmem_base;
-  int n_active;
-  int active[kMaxK];
+  uint32_t mask[2];
   float scale[512];
   float shift[512];
-  int nbr[kMaxK][kRows];
+  int nbr[2][kMaxK][kRows];
 };
 
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    default: cp_async_wait<4>(); break;
+  }
+}
+
 template <int CIN_BLK>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
             const int32_t* __restrict__ n_out_p, int K, const __nv_bfloat16* __restrict__ wpk,
             const float* __restrict__ scale, const float* __restrict__ shift,
             const __nv_bfloat16* __restrict__ residual, int relu, __nv_bfloat16* __restrict__ out,
-            int Cin, int Cout, int stages, uint32_t tmem_cols) {
+            int Cin, int Cout, int stages, int lag, int acc_bufs, uint32_t tmem_cols) {
   using SW = Swz<CIN_BLK>;
   constexpr int kChunks = CIN_BLK / 8;                    // 16-byte chunks per A row
   constexpr int kABytes = kRows * SW::P;
+  constexpr int kRowsPerPass = kProdThreads / kChunks;    // rows covered by one cp.async per thread
+  constexpr int kPasses = kRows / kRowsPerPass > 0 ? kRows / kRowsPerPass : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr uint32_t kHeader = (uint32_t)((sizeof(Smem) + 1023) & ~(size_t)1023);
+
   const int n_out = *n_out_p;
-  const int m0 = blockIdx.x * kRows;
-  if (m0 >= n_out) return;
+  const int n_tiles = (n_out + kRows - 1) / kRows;
+  if ((int)blockIdx.x >= n_tiles) return;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkb = Cin / CIN_BLK;
   const uint32_t b_bytes = (uint32_t)Cout * SW::P;
   const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
-  uint8_t* tiles = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  Smem& S = *reinterpret_cast<Smem*>(tiles + (size_t)stages * stage_bytes);
+  const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;  // 1024-aligned (dynamic smem base is)
 
-  // ---- prologue: barriers, TMEM, rulebook slice, epilogue constants
+  // ---- prologue: barriers, TMEM, epilogue constants
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&S.full[s], kProducerThreads + 1);
+      mbar_init(&S.full[s], kProdThreads + 1);
       mbar_init(&S.empty[s], 1);
     }
-    mbar_init(&S.acc_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.acc_full[b], 1);
+      mbar_init(&S.acc_empty[b], kEpiThreads);
+      mbar_init(&S.tile_ready[b], kProdThreads);
+      mbar_init(&S.tile_free[b], 1);
+      S.mask[b] = 0u;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&S.tmem_base)),
                  "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid < kProducerThreads) {
-    const int o = m0 + tid;
-    for (int k = 0; k < K; ++k) {
-      int r = -1;
-      if (o < n_out) r = nbr ? __ldg(&nbr[(size_t)k * nbr_stride + o]) : o;
-      S.nbr[k][tid] = r;
-    }
-    for (int c = tid; c < Cout; c += kProducerThreads) {
-      S.scale[c] = scale ? __ldg(&scale[c]) : 1.f;
-      S.shift[c] = shift ? __ldg(&shift[c]) : 0.f;
-    }
+  for (int c = tid; c < Cout; c += kThreads) {
+    S.scale[c] = scale ? __ldg(&scale[c]) : 1.f;
+    S.shift[c] = shift ? __ldg(&shift[c]) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 0) {  // active-offset list of this tile (warp-uniform ballots)
-    int n = 0;
-    for (int k = 0; k < K; ++k) {
-      bool any = false;
-#pragma unroll
-      for (int j = 0; j < kRows / 32; ++j) any |= S.nbr[k][lane + 32 * j] >= 0;
-      if (__any_sync(0xffffffffu, any)) {
-        if (lane == 0) S.active[n] = k;
-        ++n;
-      }
-    }
-    if (lane == 0) S.n_active = n;
-  }
-  __syncthreads();
-  const int n_stage_total = S.n_active * nkb;
   const uint32_t tmem = S.tmem_base;
 
-  if (warp < 4) {
-    // ================= producers: gather A (cp.async) + fetch B (TMA bulk) =================
-    const int chunk = tid % kChunks;
-    const int row0 = tid / kChunks;
-    constexpr int kRowStep = kProducerThreads / kChunks;
-    const int lag = stages > kLag ? kLag : 1;
-    for (int st = 0; st < n_stage_total; ++st) {
-      const int slot = st % stages;
-      const uint32_t ph = (uint32_t)(st / stages) & 1u;
-      mbar_wait(&S.empty[slot], ph ^ 1u);
-      const int k = S.active[st / nkb], kb = st % nkb;
-      uint8_t* a_tile = tiles + (size_t)slot * stage_bytes;
-      if (tid == 0) {
-        mbar_expect_tx(&S.full[slot], b_bytes);
-        bulk_g2s(a_tile + kABytes, (const uint8_t*)wpk + ((size_t)k * nkb + kb) * b_bytes, b_bytes,
-                 &S.full[slot]);
-      }
-      const uint32_t a_s = smem_u32(a_tile);
-      const __nv_bfloat16* src_col = in + (size_t)kb * CIN_BLK + chunk * 8;
-#pragma unroll
-      for (int i = 0; i < kRows / kRowStep; ++i) {
-        const int r = row0 + i * kRowStep;
-        const int src_row = S.nbr[k][r];
-        const void* src = src_row >= 0 ? (const void*)(src_col + (size_t)src_row * Cin) : (const void*)in;
-        cp_async16(a_s + SW::offset(r, chunk), src, src_row >= 0 ? 16u : 0u);
-      }
-      cp_async_commit();
-      // deferred arrive: keep `lag` gather groups in flight (lag < stages, or the ring deadlocks)
-      if (st >= lag) {
-        if (lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+  if (warp >= kProdWarp0) {
+    // ======================= producers =======================
+    const int ptid = tid - kProdWarp0 * 32;
+    const int chunk = ptid % kChunks;
+    const int row0 = ptid / kChunks;
+    int g = 0;    // stages issued so far (global counter, continues across tiles)
+    int pub = 0;  // stages published so far: [pub, g) have cp.async groups still in flight
+    // publish the oldest pending stages until at most `keep` remain in flight
+    auto publish = [&](int keep) {
+      while (g - pub > keep) {
+        cp_async_wait_dyn(g - pub - 1);
         fence_proxy_async();
-        mbar_arrive(&S.full[(st - lag) % stages]);
+        mbar_arrive(&S.full[pub % stages]);
+        ++pub;
+      }
+    };
+    int t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int buf = t & 1;
+      const int m0 = tile * kRows;
+      {
+        // the slice buffer frees up once the MMA thread has started tile t-2; never block on MMA
+        // progress while holding unpublished stages (tiny tiles could deadlock the ring)
+        const uint32_t par = ((uint32_t)(t >> 1) & 1u) ^ 1u;
+        if (!mbar_try(&S.tile_free[buf], par)) {
+          publish(0);
+          mbar_wait(&S.tile_free[buf], par);
+        }
+      }
+      // rulebook slice of the tile: K x 128 entries, coalesced; per-offset "any" via ballot
+      {
+        const int total = K * kRows;
+        int v[(kMaxK * kRows + kProdThreads - 1) / kProdThreads];
+#pragma unroll
+        for (int j = 0; j < (kMaxK * kRows + kProdThreads - 1) / kProdThreads; ++j) {
+          const int e = ptid + j * kProdThreads;
+          const int k = e >> 7, r = e & (kRows - 1);
+          int x = -1;
+          if (e < total) {
+            const int o = m0 + r;
+            if (o < n_out) x = nbr ? __ldg(&nbr[(size_t)k * nbr_stride + o]) : o;
+          }
+          v[j] = x;
+        }
+#pragma unroll
+        for (int j = 0; j < (kMaxK * kRows + kProdThreads - 1) / kProdThreads; ++j) {
+          const int e = ptid + j * kProdThreads;
+          const int k = e >> 7, r = e & (kRows - 1);
+          if (e < total) S.nbr[buf][k][r] = v[j];
+          const unsigned any = __ballot_sync(0xffffffffu, e < total && v[j] >= 0);
+          if (any != 0u && lane == 0) atomicOr(&S.mask[buf], 1u << k);   // a warp spans one k
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
+      uint32_t mask = S.mask[buf];
+      mbar_arrive(&S.tile_ready[buf]);
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int* nb = S.nbr[buf][k];
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int slot = g % stages;
+          mbar_wait(&S.empty[slot], ((uint32_t)(g / stages) & 1u) ^ 1u);
+          const uint32_t a_s = tiles_s + (uint32_t)slot * stage_bytes;
+          if (ptid == 0) {
+            mbar_expect_tx(&S.full[slot], b_bytes);
+            bulk_g2s(a_s + kABytes, (const uint8_t*)wpk + ((size_t)k * nkb + kb) * b_bytes, b_bytes,
+                     &S.full[slot]);
+          }
+          const __nv_bfloat16* src_col = in + kb * CIN_BLK + chunk * 8;
+#pragma unroll
+          for (int i = 0; i < kPasses; ++i) {
+            const int r = row0 + i * kRowsPerPass;
+            if (kRowsPerPass <= kRows || r < kRows) {
+              const int src_row = nb[r];
+              const void* src = src_row >= 0 ? (const void*)(src_col + (size_t)src_row * Cin) : (const void*)in;
+              cp_async16(a_s + SW::offset(r, chunk), src, src_row >= 0 ? 16u : 0u);
+            }
+          }
+          cp_async_commit();
+          ++g;
+          publish(lag);
+        }
       }
     }
-    // drain the last `lag` groups in order
-    for (int st = n_stage_total > lag ? n_stage_total - lag : 0; st < n_stage_total; ++st) {
-      if (n_stage_total - 1 - st >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(&S.full[st % stages]);
+    publish(0);
+  } else if (warp == kMmaWarp) {
+    // ======================= MMA issuer (one thread) =======================
+    if (lane == 0) {
+      const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 4) << 24);
+      int g = 0, t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const int buf = t & 1;
+        const int ab = t % acc_bufs;
+        mbar_wait(&S.tile_ready[buf], (uint32_t)(t >> 1) & 1u);
+        const uint32_t mask = S.mask[buf];
+        S.mask[buf] = 0u;
+        mbar_arrive(&S.tile_free[buf]);
+        const int n_st = __popc(mask) * nkb;
+        mbar_wait(&S.acc_empty[ab], ((uint32_t)(t / acc_bufs) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)(ab * Cout);
+        for (int st = 0; st < n_st; ++st, ++g) {
+          const int slot = g % stages;
+          mbar_wait(&S.full[slot], (uint32_t)(g / stages) & 1u);
+          tc_fence_after();
+          const uint32_t a_s = tiles_s + (uint32_t)slot * stage_bytes;
+          const uint32_t b_s = a_s + kABytes;
+          for (int n0 = 0; n0 < Cout; n0 += 256) {
+            const int n = Cout - n0 < 256 ? Cout - n0 : 256;
+            const uint32_t idesc = idesc_base | ((uint32_t)(n >> 3) << 17);
+            const uint64_t a_desc = SW::desc(a_s);
+            const uint64_t b_desc = SW::desc(b_s + (uint32_t)n0 * SW::P);
+#pragma unroll
+            for (int kk = 0; kk < CIN_BLK / 16; ++kk)
+              umma_bf16(d_tmem + (uint32_t)n0, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2),
+                        idesc, (st > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&S.empty[slot]);   // frees the stage once these MMAs have read it
+        }
+        umma_commit(&S.acc_full[ab]);
+      }
+      tc_fence_before();
     }
-
-    // ================= epilogue: TMEM -> registers -> global =================
-    if (n_stage_total > 0) {
-      mbar_wait(&S.acc_full, 0);
+  } else {
+    // ======================= epilogue: TMEM -> registers -> global =======================
+    int t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int ab = t % acc_bufs;
+      mbar_wait(&S.acc_full[ab], (uint32_t)(t / acc_bufs) & 1u);
       tc_fence_after();
-    }
-    const int o = m0 + tid;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < Cout; c0 += 16) {
-      uint32_t v[16];
-      if (n_stage_total > 0) {
-        tmem_ld16(lane_base + (uint32_t)c0, v);   // warp-collective: every lane participates
+      const int o = tile * kRows + tid;
+      const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * Cout);
+      for (int c0 = 0; c0 < Cout; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(lane_base + (uint32_t)c0, v);   // warp-collective
         tmem_ld_wait();
-      } else {
+        if (o < n_out) {
+          float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
-      }
-      if (o < n_out) {
-        float f[16];
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * S.scale[c0 + j] + S.shift[c0 + j];
+          if (residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(residual + (size_t)o * Cout + c0);
+            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * S.scale[c0 + j] + S.shift[c0 + j];
-        if (residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(residual + (size_t)o * Cout + c0);
-          uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-          const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-          const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+            for (int j = 0; j < 4; ++j) {
+              float2 a = __bfloat1622float2(h0[j]), b = __bfloat1622float2(h1[j]);
+              f[2 * j] += a.x; f[2 * j + 1] += a.y;
+              f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint4 w0, w1;
+          __nv_bfloat162* p0 = reinterpret_cast<__nv_bfloat162*>(&w0);
+          __nv_bfloat162* p1 = reinterpret_cast<__nv_bfloat162*>(&w1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float2 a = __bfloat1622float2(h0[j]), b = __bfloat1622float2(h1[j]);
-            f[2 * j] += a.x; f[2 * j + 1] += a.y;
-            f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+            p0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            p1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
           }
+          uint4* op = reinterpret_cast<uint4*>(out + (size_t)o * Cout + c0);
+          op[0] = w0;
+          op[1] = w1;
         }
-        if (relu) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        uint4 w0, w1;
-        __nv_bfloat162* p0 = reinterpret_cast<__nv_bfloat162*>(&w0);
-        __nv_bfloat162* p1 = reinterpret_cast<__nv_bfloat162*>(&w1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          p0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          p1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-        }
-        uint4* op = reinterpret_cast<uint4*>(out + (size_t)o * Cout + c0);
-        op[0] = w0;
-        op[1] = w1;
       }
+      tc_fence_before();
+      mbar_arrive(&S.acc_empty[ab]);
     }
-    tc_fence_before();
-  } else if (lane == 0) {
-    // ================= MMA issuer (one thread) =================
-    const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 4) << 24);
-    for (int st = 0; st < n_stage_total; ++st) {
-      const int slot = st % stages;
-      const uint32_t ph = (uint32_t)(st / stages) & 1u;
-      mbar_wait(&S.full[slot], ph);
-      tc_fence_after();
-      const uint32_t a_s = smem_u32(tiles + (size_t)slot * stage_bytes);
-      const uint32_t b_s = a_s + kABytes;
-      for (int n0 = 0; n0 < Cout; n0 += 256) {
-        const int n = Cout - n0 < 256 ? Cout - n0 : 256;
-        const uint32_t idesc = idesc_base | ((uint32_t)(n >> 3) << 17);
-        const uint64_t a_desc = SW::desc(a_s);
-        const uint64_t b_desc = SW::desc(b_s + (uint32_t)n0 * SW::P);
-#pragma unroll
-        for (int kk = 0; kk < CIN_BLK / 16; ++kk)
-          umma_bf16(tmem + (uint32_t)n0, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                    (st > 0 || kk > 0) ? 1u : 0u);
-      }
-      umma_commit(&S.empty[slot]);   // frees the stage once these MMAs have read it
-    }
-    if (n_stage_total > 0) umma_commit(&S.acc_full);
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols)
                  : "memory");
@@ -377,26 +455,32 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride, const int3
   const uint32_t P = 2 * blk;
   const uint32_t b_bytes = (uint32_t)Cout * P;
   const uint32_t stage_bytes = kRows * P + ((b_bytes + 1023u) & ~1023u);
-  // two co-resident CTAs per SM when >= 3 stages fit in ~92 KB (one CTA's epilogue then overlaps
-  // its neighbour's gathers); otherwise one CTA per SM with as deep a ring as fits. 2..8 stages.
-  const size_t fixed = sizeof(Smem) + 1024;
-  int stages = (int)((110u * 1024u - fixed) / stage_bytes);
-  if (stages < 3) stages = (int)((220u * 1024u - fixed) / stage_bytes);
+  // one persistent CTA per SM: as deep an operand ring as ~200 KB allows (2..12 stages)
+  const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
+  int stages = (int)((200u * 1024u - header) / stage_bytes);
   if (const char* e = getenv("U3D_TC_STAGES")) stages = atoi(e);
-  if (stages > 8) stages = 8;
+  if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
-  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  int lag = stages - 1 < kMaxLag ? stages - 1 : kMaxLag;
+  if (const char* e = getenv("U3D_TC_LAG")) lag = atoi(e);
+  if (lag < 1) lag = 1;
+  if (lag > stages - 1) lag = stages - 1;
+  const size_t smem = header + (size_t)stages * stage_bytes;
   U3D_CHECK_ARG(smem <= 227 * 1024, "spconv tc: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
-  uint32_t tmem_cols = Cout < 32 ? 32 : (uint32_t)Cout;
+  const int acc_bufs = 2 * Cout <= 512 ? 2 : 1;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < acc_bufs * Cout) tmem_cols <<= 1;
   int tiles = cdiv(out_cap, kRows);
   if (tiles < 1) return U3D_OK;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
 #define U3D_TC_LAUNCH(BLK)                                                                          \
   do {                                                                                              \
     U3D_CUDA(cudaFuncSetAttribute(k_spconv_tc<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                   (int)smem));                                                      \
-    k_spconv_tc<BLK><<<tiles, kThreads, smem, st>>>(                                                \
+    k_spconv_tc<BLK><<<grid, kThreads, smem, st>>>(                                                 \
         (const __nv_bfloat16*)in, nbr, nbr_stride, n_out, K, (const __nv_bfloat16*)wpk, scale, shift, \
-        (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, tmem_cols);   \
+        (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, lag, acc_bufs, \
+        tmem_cols);                                                                                 \
   } while (0)
   if (blk == 64) U3D_TC_LAUNCH(64);
   else if (blk == 32) U3D_TC_LAUNCH(32);

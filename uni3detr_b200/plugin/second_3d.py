@@ -17,6 +17,9 @@ from torch import nn
 from ..compat import BACKBONES, NECKS
 
 
+FUSE_CONV_BIAS_RELU = True
+
+
 def _norm(norm_cfg, ch):
     t = norm_cfg.get("type", "BN3d")
     if t not in ("BN3d", "BN", "naiveSyncBN3d"):
@@ -56,20 +59,24 @@ class _FoldedConv:
         return self._run(x)
 
     def _run(self, x):
+        # conv + bias + ReLU as ONE cuDNN fused op (torch.cudnn_convolution_relu) where it exists
+        # (forward convs on CUDA); transposed convs keep the bias/ReLU as two elementwise launches.
+        fused = FUSE_CONV_BIAS_RELU and x.is_cuda and not self.transposed
         if self.as2d:
             B, C, D, H, W = x.shape
             x2 = x.permute(0, 2, 1, 3, 4).reshape(B * D, C, H, W)  # view on NDHWC memory
             if self.transposed:
-                y = F.conv_transpose2d(x2, self.w, self.b, stride=self.stride[1:])
+                y = torch.relu_(F.conv_transpose2d(x2, self.w, self.b, stride=self.stride[1:]))
+            elif fused:
+                y = torch.cudnn_convolution_relu(x2, self.w, self.b, self.stride[1:], self.padding[1:], (1, 1), 1)
             else:
-                y = F.conv2d(x2, self.w, self.b, stride=self.stride[1:], padding=self.padding[1:])
-            y = torch.relu_(y)
+                y = torch.relu_(F.conv2d(x2, self.w, self.b, stride=self.stride[1:], padding=self.padding[1:]))
             return y.reshape(B, D, y.shape[1], y.shape[2], y.shape[3]).permute(0, 2, 1, 3, 4)
         if self.transposed:
-            y = F.conv_transpose3d(x, self.w, self.b, stride=self.stride)
-        else:
-            y = F.conv3d(x, self.w, self.b, stride=self.stride, padding=self.padding)
-        return torch.relu_(y)
+            return torch.relu_(F.conv_transpose3d(x, self.w, self.b, stride=self.stride))
+        if fused:
+            return torch.cudnn_convolution_relu(x, self.w, self.b, self.stride, self.padding, (1, 1, 1), 1)
+        return torch.relu_(F.conv3d(x, self.w, self.b, stride=self.stride, padding=self.padding))
 
 
 def _fold_sequential(seq, dtype, as2d):
