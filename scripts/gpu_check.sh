@@ -4,13 +4,13 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
-timeout 1800 python -m pytest tests -m gpu -q --timeout 900 -x --no-header -rA 2>&1 | tail -150 > gpurun_out/pytest_gpu.log
+timeout 1200 python -m pytest tests -m gpu -q --timeout 400 -x --no-header -rA 2>&1 | tail -150 > gpurun_out/pytest_gpu.log
 echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 echo "smoke exit: $?" >> gpurun_out/smoke.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit: $?" >> gpurun_out/bench.err
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
   --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
 echo "ncu exit: $?" >> gpurun_out/bench_ncu.log
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/bench.json | cut -c1-600

@@ -156,7 +156,7 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
     if (CS == 1) {
       __syncthreads();
     } else {
-      const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+      const uint32_t parity = (uint32_t)((it - 1) >> 1) & 1u;   // each barrier is used every 2nd iteration
       asm volatile(
           "{\n\t"
           ".reg .pred p;\n\t"
