@@ -129,17 +129,13 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ GPU arm ----
-def spconv_cost(info):
+def spconv_cost(info, n_in):
     """Algorithmic bytes / FLOPs of one sparse-conv launch:
-    (N_in*Cin + N_out*Cout)*sizeof(act) + K*Cin*Cout*sizeof(w) + pairs*8 B; 2*pairs*Cin*Cout FLOP."""
-    n_out = int(info["n_out"])
-    if info["nbr"] is None:
-        pairs = n_out
-    else:
-        pairs = int((info["nbr"][:, :n_out] >= 0).sum())
-    es = info["esize"]
-    by = (info["n_in"] * info["Cin"] + n_out * info["Cout"]) * es + info["K"] * info["Cin"] * info["Cout"] * es + pairs * 8
-    return by, 2.0 * pairs * info["Cin"] * info["Cout"], pairs
+    (N_in*Cin + N_out*Cout)*sizeof(act) + K*Cin*Cout*sizeof(w) + pairs*8 B; 2*pairs*Cin*Cout FLOP.
+    N_in / N_out are the LIVE row counts (not buffer capacities)."""
+    es, pairs, n_out = info["esize"], info["pairs"], info["n_out"]
+    by = (n_in * info["Cin"] + n_out * info["Cout"]) * es + info["K"] * info["Cin"] * info["Cout"] * es + pairs * 8
+    return by, 2.0 * pairs * info["Cin"] * info["Cout"]
 
 
 def roofline_pass(step_fn, peaks, reps=3):
@@ -153,6 +149,7 @@ def roofline_pass(step_fn, peaks, reps=3):
     for _ in range(reps):
         ops.profile_begin()
         step_fn()
+        live_rows = 0   # live rows of the current sparse level = input rows of the next conv
         for name, info, ms in ops.profile_end():
             if name in ("spconv_fwd", "spconv_fwd_packed"):
                 key = f"{'spconv_tc' if name.endswith('packed') else 'spconv_simt'}[{info['K']}x{info['Cin']}->{info['Cout']}]"
@@ -165,17 +162,15 @@ def roofline_pass(step_fn, peaks, reps=3):
             a["ms"] += ms
             a["calls"] += 1
             if name == "spconv_fwd":
-                by, fl, _ = spconv_cost(info)
+                by, fl = spconv_cost(info, live_rows)
+                live_rows = info["n_out"]
                 a["bytes"] += by
                 a["flops"] += fl
             elif name in ("voxelize_hard", "voxelize_dynamic"):
-                m = int(info["out"].scene_rows[-1])
-                a["bytes"] += info["n_points"] * info["C"] * 4 + m * (info["C"] * 4 + 16)
+                live_rows = info["n_voxels"]
+                a["bytes"] += info["n_points"] * info["C"] * 4 + live_rows * (info["C"] * 4 + 16)
             elif name in ("rulebook_subm", "rulebook_down"):
-                n = int(info.get("n_out", info["n_rows"]))
-                nin = int(info["n_rows"])
-                pairs = int((info["nbr"][:, :n] >= 0).sum())
-                a["bytes"] += nin * 16 + pairs * 8 + 2 * nin * 8
+                a["bytes"] += info["n_in"] * 16 + info["pairs"] * 8 + 2 * info["n_in"] * 8
             elif name == "sparse_to_dense":
                 a["bytes"] += info["bytes"]
             elif name == "fps":

@@ -14,8 +14,9 @@
 //               derive the active-offset mask with warp ballots, then per stage gather
 //               128 input rows x CIN_BLK bf16 with 16-byte cp.async (zero-fill for missing
 //               neighbours) into a K-major stage with the hardware swizzle of 2*CIN_BLK bytes;
-//               a stage is published with fence.proxy.async + mbarrier arrive, `lag` stages
-//               late so several gathers stay in flight per thread. One producer thread fetches
+//               a stage is published with cp.async.mbarrier.arrive.noinc - the hardware arrives
+//               on the stage's mbarrier when the thread's copies have landed, so producers never
+//               wait on their own loads and the whole ring stays in flight. One producer thread fetches
 //               the stage's weight tile W[k][:, block] - a pre-swizzled (Cout x CIN_BLK) image
 //               laid out by u3d_spconv_pack_weights - with ONE cp.async.bulk (TMA) that completes
 //               on the same mbarrier.
@@ -40,7 +41,6 @@ constexpr int kProdThreads = 256;
 constexpr int kThreads = (kProdWarp0 * 32) + kProdThreads;   // 416
 constexpr int kMaxK = 27;
 constexpr int kMaxStages = 12;
-constexpr int kMaxLag = 4;             // cp.async groups a producer keeps in flight
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -91,6 +91,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (counts as one of
+// the barrier's expected arrivals; no wait, no fence in the issuing thread)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
@@ -164,23 +169,13 @@ struct Smem {
   int nbr[2][kMaxK][kRows];
 };
 
-__device__ __forceinline__ void cp_async_wait_dyn(int n) {
-  switch (n) {
-    case 0: cp_async_wait<0>(); break;
-    case 1: cp_async_wait<1>(); break;
-    case 2: cp_async_wait<2>(); break;
-    case 3: cp_async_wait<3>(); break;
-    default: cp_async_wait<4>(); break;
-  }
-}
-
 template <int CIN_BLK>
 __global__ void __launch_bounds__(kThreads, 1)
 k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
             const int32_t* __restrict__ n_out_p, int K, const __nv_bfloat16* __restrict__ wpk,
             const float* __restrict__ scale, const float* __restrict__ shift,
             const __nv_bfloat16* __restrict__ residual, int relu, __nv_bfloat16* __restrict__ out,
-            int Cin, int Cout, int stages, int lag, int acc_bufs, uint32_t tmem_cols) {
+            int Cin, int Cout, int stages, int acc_bufs, uint32_t tmem_cols) {
   using SW = Swz<CIN_BLK>;
   constexpr int kChunks = CIN_BLK / 8;                    // 16-byte chunks per A row
   constexpr int kABytes = kRows * SW::P;
@@ -236,36 +231,21 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     const int ptid = tid - kProdWarp0 * 32;
     const int chunk = ptid % kChunks;
     const int row0 = ptid / kChunks;
-    int g = 0;    // stages issued so far (global counter, continues across tiles)
-    int pub = 0;  // stages published so far: [pub, g) have cp.async groups still in flight
-    // publish the oldest pending stages until at most `keep` remain in flight
-    auto publish = [&](int keep) {
-      while (g - pub > keep) {
-        cp_async_wait_dyn(g - pub - 1);
-        fence_proxy_async();
-        mbar_arrive(&S.full[pub % stages]);
-        ++pub;
-      }
-    };
+    int slot = 0;          // ring position of the next stage (continues across tiles)
+    uint32_t eph = 1u;     // parity to wait for on empty[slot] (fresh barriers pass parity 1)
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int buf = t & 1;
       const int m0 = tile * kRows;
-      {
-        // the slice buffer frees up once the MMA thread has started tile t-2; never block on MMA
-        // progress while holding unpublished stages (tiny tiles could deadlock the ring)
-        const uint32_t par = ((uint32_t)(t >> 1) & 1u) ^ 1u;
-        if (!mbar_try(&S.tile_free[buf], par)) {
-          publish(0);
-          mbar_wait(&S.tile_free[buf], par);
-        }
-      }
+      // the slice buffer frees up once the MMA thread has started tile t-2
+      mbar_wait(&S.tile_free[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);
       // rulebook slice of the tile: K x 128 entries, coalesced; per-offset "any" via ballot
       {
         const int total = K * kRows;
-        int v[(kMaxK * kRows + kProdThreads - 1) / kProdThreads];
+        constexpr int kPer = (kMaxK * kRows + kProdThreads - 1) / kProdThreads;
+        int v[kPer];
 #pragma unroll
-        for (int j = 0; j < (kMaxK * kRows + kProdThreads - 1) / kProdThreads; ++j) {
+        for (int j = 0; j < kPer; ++j) {
           const int e = ptid + j * kProdThreads;
           const int k = e >> 7, r = e & (kRows - 1);
           int x = -1;
@@ -276,7 +256,7 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
           v[j] = x;
         }
 #pragma unroll
-        for (int j = 0; j < (kMaxK * kRows + kProdThreads - 1) / kProdThreads; ++j) {
+        for (int j = 0; j < kPer; ++j) {
           const int e = ptid + j * kProdThreads;
           const int k = e >> 7, r = e & (kRows - 1);
           if (e < total) S.nbr[buf][k][r] = v[j];
@@ -292,8 +272,7 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         mask &= mask - 1;
         const int* nb = S.nbr[buf][k];
         for (int kb = 0; kb < nkb; ++kb) {
-          const int slot = g % stages;
-          mbar_wait(&S.empty[slot], ((uint32_t)(g / stages) & 1u) ^ 1u);
+          mbar_wait(&S.empty[slot], eph);
           const uint32_t a_s = tiles_s + (uint32_t)slot * stage_bytes;
           if (ptid == 0) {
             mbar_expect_tx(&S.full[slot], b_bytes);
@@ -304,24 +283,22 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
 #pragma unroll
           for (int i = 0; i < kPasses; ++i) {
             const int r = row0 + i * kRowsPerPass;
-            if (kRowsPerPass <= kRows || r < kRows) {
-              const int src_row = nb[r];
-              const void* src = src_row >= 0 ? (const void*)(src_col + (size_t)src_row * Cin) : (const void*)in;
-              cp_async16(a_s + SW::offset(r, chunk), src, src_row >= 0 ? 16u : 0u);
-            }
+            const int src_row = nb[r];
+            const void* src = src_row >= 0 ? (const void*)(src_col + (size_t)src_row * Cin) : (const void*)in;
+            cp_async16(a_s + SW::offset(r, chunk), src, src_row >= 0 ? 16u : 0u);
           }
-          cp_async_commit();
-          ++g;
-          publish(lag);
+          // asynchronous publish: the hardware arrives on full[slot] when this thread's copies land
+          cp_async_arrive(&S.full[slot]);
+          if (++slot == stages) { slot = 0; eph ^= 1u; }
         }
       }
     }
-    publish(0);
   } else if (warp == kMmaWarp) {
     // ======================= MMA issuer (one thread) =======================
     if (lane == 0) {
       const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kRows >> 4) << 24);
-      int g = 0, t = 0;
+      int slot = 0, t = 0;
+      uint32_t fph = 0u;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
         const int buf = t & 1;
         const int ab = t % acc_bufs;
@@ -333,9 +310,8 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         mbar_wait(&S.acc_empty[ab], ((uint32_t)(t / acc_bufs) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem + (uint32_t)(ab * Cout);
-        for (int st = 0; st < n_st; ++st, ++g) {
-          const int slot = g % stages;
-          mbar_wait(&S.full[slot], (uint32_t)(g / stages) & 1u);
+        for (int st = 0; st < n_st; ++st) {
+          mbar_wait(&S.full[slot], fph);
           tc_fence_after();
           const uint32_t a_s = tiles_s + (uint32_t)slot * stage_bytes;
           const uint32_t b_s = a_s + kABytes;
@@ -350,6 +326,7 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
                         idesc, (st > 0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&S.empty[slot]);   // frees the stage once these MMAs have read it
+          if (++slot == stages) { slot = 0; fph ^= 1u; }
         }
         umma_commit(&S.acc_full[ab]);
       }
@@ -461,10 +438,6 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride, const int3
   if (const char* e = getenv("U3D_TC_STAGES")) stages = atoi(e);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
-  int lag = stages - 1 < kMaxLag ? stages - 1 : kMaxLag;
-  if (const char* e = getenv("U3D_TC_LAG")) lag = atoi(e);
-  if (lag < 1) lag = 1;
-  if (lag > stages - 1) lag = stages - 1;
   const size_t smem = header + (size_t)stages * stage_bytes;
   U3D_CHECK_ARG(smem <= 227 * 1024, "spconv tc: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
   const int acc_bufs = 2 * Cout <= 512 ? 2 : 1;
@@ -479,7 +452,7 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride, const int3
                                   (int)smem));                                                      \
     k_spconv_tc<BLK><<<grid, kThreads, smem, st>>>(                                                 \
         (const __nv_bfloat16*)in, nbr, nbr_stride, n_out, K, (const __nv_bfloat16*)wpk, scale, shift, \
-        (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, lag, acc_bufs, \
+        (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, acc_bufs,      \
         tmem_cols);                                                                                 \
   } while (0)
   if (blk == 64) U3D_TC_LAUNCH(64);

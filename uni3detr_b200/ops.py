@@ -31,6 +31,11 @@ def profile_end():
     return [(n, i, s.elapsed_time(e)) for n, i, s, e in rec]
 
 
+def _live_pairs(nbr, n_out):
+    n = int(n_out)
+    return n if nbr is None else int((nbr[:, :n] >= 0).sum())
+
+
 def _timed(info=None):
     def deco(fn):
         @functools.wraps(fn)
@@ -38,9 +43,12 @@ def _timed(info=None):
             if _PROF is None:
                 return fn(*a, **k)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.current_stream().synchronize()   # each op is timed alone (profile mode only)
             s.record()
             r = fn(*a, **k)
             e.record()
+            # info() returns plain python numbers (it may synchronise); no tensor is kept alive, so
+            # the profile pass does not perturb the caching allocator
             _PROF.append((fn.__name__, info(r, *a, **k) if info else {}, s, e))
             return r
         return wrapper
@@ -118,7 +126,8 @@ class Voxels:
         return self.scene_rows[-1:]
 
 
-@_timed(lambda r, points, *a, **k: dict(n_points=points.shape[0], C=points.shape[1], out=r))
+@_timed(lambda r, points, *a, **k: dict(n_points=points.shape[0], C=points.shape[1],
+                                        n_voxels=int(r.scene_rows[-1])))
 def voxelize_hard(points, pt_off, B, pc_range, voxel_size, grid_zyx, max_pts, max_voxels,
                   deterministic=True, want_voxels=False) -> Voxels:
     lib = _lib.load()
@@ -151,7 +160,8 @@ def voxelize_hard(points, pt_off, B, pc_range, voxel_size, grid_zyx, max_pts, ma
                   VoxelMap(vm, row_of_rank, B, (D, H, W)), cap)
 
 
-@_timed(lambda r, points, *a, **k: dict(n_points=points.shape[0], C=points.shape[1], out=r))
+@_timed(lambda r, points, *a, **k: dict(n_points=points.shape[0], C=points.shape[1],
+                                        n_voxels=int(r.scene_rows[-1])))
 def voxelize_dynamic(points, pt_off, B, pc_range, voxel_size, grid_zyx) -> Voxels:
     lib = _lib.load()
     _req(points, torch.float32, "points")
@@ -192,7 +202,8 @@ def voxmap_build(coors, n_rows, cap, B, dims) -> VoxelMap:
     return VoxelMap(vm, perm, B, (D, H, W))
 
 
-@_timed(lambda r, coors, n_rows, *a, **k: dict(n_rows=n_rows, nbr=r))
+@_timed(lambda r, coors, n_rows, *a, **k: dict(n_in=int(n_rows), n_out=int(n_rows),
+                                               pairs=_live_pairs(r, n_rows)))
 def rulebook_subm(coors, n_rows, cap, vmap: VoxelMap, nbr=None):
     lib = _lib.load()
     _req(coors, torch.int32, "coors")
@@ -208,7 +219,8 @@ def conv_out_dims(in_dims, stride, pad, k=3):
     return tuple((int(d) + 2 * int(p) - k) // int(s) + 1 for d, s, p in zip(in_dims, stride, pad))
 
 
-@_timed(lambda r, coors, n_rows, *a, **k: dict(n_rows=n_rows, n_out=r[1], nbr=r[3]))
+@_timed(lambda r, coors, n_rows, *a, **k: dict(n_in=int(n_rows), n_out=int(r[1]),
+                                               pairs=_live_pairs(r[3], r[1])))
 def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=None):
     lib = _lib.load()
     _req(coors, torch.int32, "coors")
@@ -246,7 +258,7 @@ def rulebook_pairs(nbr, n_out):
 
 
 @_timed(lambda r, x, nbr, n_out, out_cap, w, *a, **k: dict(
-    n_in=x.shape[0], n_out=n_out, nbr=nbr, K=w.shape[0], Cin=w.shape[1], Cout=w.shape[2],
+    n_out=int(n_out), pairs=_live_pairs(nbr, n_out), K=w.shape[0], Cin=w.shape[1], Cout=w.shape[2],
     esize=x.element_size()))
 def spconv_fwd(x, nbr, n_out, out_cap, w, scale=None, shift=None, residual=None, relu=False,
                out=None, impl=0):
@@ -283,7 +295,7 @@ def spconv_pack_weights(w):
 
 
 @_timed(lambda r, x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, *a, **k: dict(
-    n_in=x.shape[0], n_out=n_out, nbr=nbr, K=K, Cin=Cin, Cout=Cout, esize=2, tc=True))
+    n_out=int(n_out), pairs=_live_pairs(nbr, n_out), K=K, Cin=Cin, Cout=Cout, esize=2, tc=True))
 def spconv_fwd_packed(x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, scale=None, shift=None,
                       residual=None, relu=False, out=None):
     """tcgen05 sparse conv: bf16 in/out, weights from spconv_pack_weights."""
