@@ -115,10 +115,12 @@ int u3d_voxmap_build(const int32_t* coors, const int32_t* n_rows, int cap, int B
  * Replaces: spconv get_indice_pairs (subm=True) behind every SubMConv3d built at
  * projects/mmdet3d_plugin/models/pts_encoder/sparse_encoder_hd.py:71-88,193-199.
  *   n_rows: DEVICE int32 live row count; cap: host capacity of coors/nbr columns
+ *   tile_mask (may be NULL): ceil(cap/128) uint32 (out); bit k of word t = kernel offset k feeds
+ *     at least one of output rows [128t, 128t+128) - lets the tensor-core conv skip empty offsets
  */
 int u3d_rulebook_subm(const int32_t* coors, const int32_t* n_rows, int cap,
                       const void* map, const int32_t* perm, int B, int D, int H, int W,
-                      int32_t* nbr, int nbr_stride, void* stream);
+                      int32_t* nbr, int nbr_stride, uint32_t* tile_mask, void* stream);
 
 /*
  * Rulebook for a strided SparseConv3d(k=3): builds the output VoxelMap, the output
@@ -135,7 +137,7 @@ int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, int in_cap,
                       const int32_t* stride, const int32_t* pad,
                       void* out_map, int32_t* scan_scratch, int32_t* out_coors,
                       int32_t* n_out, int out_cap, int32_t* nbr, int nbr_stride,
-                      void* stream);
+                      uint32_t* tile_mask /* ceil(out_cap/128) words or NULL */, void* stream);
 
 /*
  * Convert a neighbour table to the (in,out) pair lists of spconv 1.x
@@ -173,11 +175,15 @@ int u3d_spconv_fwd(const void* in, const int32_t* nbr, int nbr_stride, const int
  *     (supported: Cin in {16, 32, 64, 128, ... multiples of 64 up to 512}; Cout a power of two in
  *      [16, 512]; K <= 27)
  *   u3d_spconv_pack_weights: w (K,Cin,Cout) bf16 row-major -> packed
- *   u3d_spconv_fwd_packed: in/out/residual bf16, 16-byte aligned; other arguments as u3d_spconv_fwd
+ *   u3d_spconv_fwd_packed: in/out/residual bf16, 16-byte aligned; other arguments as u3d_spconv_fwd.
+ *     nbr must be 16-byte aligned with nbr_stride a multiple of 4 and >= 128*ceil(out_cap/128)
+ *     (whole 512-byte rulebook rows are bulk-copied into shared memory);
+ *     tile_mask from u3d_rulebook_* (NULL = treat every offset as active).
  */
 size_t u3d_spconv_packed_bytes(int K, int Cin, int Cout);
 int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, void* packed, void* stream);
-int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr_stride, const int32_t* n_out,
+int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr_stride,
+                          const uint32_t* tile_mask, const int32_t* n_out,
                           int out_cap, int K, const void* w_packed, const float* scale,
                           const float* shift, const void* residual, int relu, void* out, int Cin,
                           int Cout, void* stream);

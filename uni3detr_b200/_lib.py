@@ -63,16 +63,16 @@ SIGNATURES = {
     "u3d_voxelize_dynamic": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "u3d_voxmap_build": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
-    "u3d_rulebook_subm": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "u3d_rulebook_subm": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp]),
     "u3d_rulebook_down": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _i32, _vp, _i32, _vp]),
+                                 _vp, _i32, _vp, _i32, _vp, _vp]),
     "u3d_rulebook_pairs": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "u3d_spconv_fwd": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32,
                               _i32, _i32, _i32, _vp]),
     "u3d_spconv_packed_bytes": (_sz, [_i32, _i32, _i32]),
     "u3d_spconv_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
-    "u3d_spconv_fwd_packed": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp,
-                                     _i32, _i32, _vp]),
+    "u3d_spconv_fwd_packed": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
+                                     _i32, _vp, _i32, _i32, _vp]),
     "u3d_sparse_to_dense": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                    _vp, _vp]),
     "u3d_fps": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

@@ -129,10 +129,10 @@ static inline size_t dtype_size(int dtype) { return dtype == U3D_BF16 ? 2 : 4; }
 // internal launchers shared between translation units
 int voxmap_scan(uint2* map, size_t words, int32_t* scratch, int32_t* total_out, cudaStream_t st);
 
-int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride, const int32_t* n_out,
-                  int out_cap, int K, const void* w, const float* scale, const float* shift,
-                  const void* residual, int relu, void* out, int Cin, int Cout,
-                  cudaStream_t st);
+int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
+                  const uint32_t* tile_mask, const int32_t* n_out, int out_cap, int K, const void* w,
+                  const float* scale, const float* shift, const void* residual, int relu, void* out,
+                  int Cin, int Cout, cudaStream_t st);
 bool spconv_tc_supported(int Cin, int Cout, int dtype);
 
 }  // namespace u3d

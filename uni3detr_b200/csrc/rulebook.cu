@@ -19,22 +19,33 @@ struct Dims3 { int d[3]; };  // z,y,x
 __global__ void __launch_bounds__(256)
 k_nbr_build(const int32_t* __restrict__ out_coors, const int32_t* __restrict__ n_out_p,
             const uint2* __restrict__ in_map, const int32_t* __restrict__ in_perm, Dims3 in_dims,
-            Dims3 stride, Dims3 pad, int32_t* __restrict__ nbr, int nbr_stride) {
+            Dims3 stride, Dims3 pad, int32_t* __restrict__ nbr, int nbr_stride,
+            uint32_t* __restrict__ tile_mask) {
   const int n_out = *n_out_p;
   const int k = blockIdx.y;
   const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
   const int D = in_dims.d[0], H = in_dims.d[1], W = in_dims.d[2];
-  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += gridDim.x * blockDim.x) {
-    int4 c = __ldg(reinterpret_cast<const int4*>(out_coors) + o);  // b,z,y,x
-    int z = c.y * stride.d[0] - pad.d[0] + kz;
-    int y = c.z * stride.d[1] - pad.d[1] + ky;
-    int x = c.w * stride.d[2] - pad.d[2] + kx;
+  // uniform trip count: whole warps stay converged for the ballot behind the tile masks
+  const int per_round = gridDim.x * blockDim.x;
+  const int nrounds = (n_out + per_round - 1) / per_round;
+  for (int r = 0; r < nrounds; ++r) {
+    const int o = r * per_round + blockIdx.x * blockDim.x + threadIdx.x;
     int row = -1;
-    if (z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W) {
-      uint32_t lin = (uint32_t)((((size_t)c.x * D + z) * H + y) * W + x);
-      row = map_lookup(in_map, in_perm, lin);
+    if (o < n_out) {
+      int4 c = __ldg(reinterpret_cast<const int4*>(out_coors) + o);  // b,z,y,x
+      int z = c.y * stride.d[0] - pad.d[0] + kz;
+      int y = c.z * stride.d[1] - pad.d[1] + ky;
+      int x = c.w * stride.d[2] - pad.d[2] + kx;
+      if (z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W) {
+        uint32_t lin = (uint32_t)((((size_t)c.x * D + z) * H + y) * W + x);
+        row = map_lookup(in_map, in_perm, lin);
+      }
+      nbr[(size_t)k * nbr_stride + o] = row;
     }
-    nbr[(size_t)k * nbr_stride + o] = row;
+    // bit k of tile_mask[t] = "offset k feeds at least one of output rows [128t, 128t+128)";
+    // a warp covers 32 consecutive rows of one tile, so one atomicOr per warp at most
+    const unsigned any = __ballot_sync(0xffffffffu, row >= 0);
+    if (tile_mask && any && (threadIdx.x & 31) == 0) atomicOr(&tile_mask[o >> 7], 1u << k);
   }
 }
 
@@ -192,15 +203,16 @@ extern "C" int u3d_voxmap_build(const int32_t* coors, const int32_t* n_rows, int
 
 extern "C" int u3d_rulebook_subm(const int32_t* coors, const int32_t* n_rows, int cap,
                                  const void* map, const int32_t* perm, int B, int D, int H, int W,
-                                 int32_t* nbr, int nbr_stride, void* stream) {
+                                 int32_t* nbr, int nbr_stride, uint32_t* tile_mask, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   U3D_CHECK_ARG(coors && n_rows && map && nbr, "u3d_rulebook_subm: null buffer");
   U3D_CHECK_ARG(nbr_stride >= cap && cap >= 0, "u3d_rulebook_subm: nbr_stride < cap");
   U3D_CHECK_ARG(u3d_voxmap_words(B, D, H, W) != 0, "u3d_rulebook_subm: bad grid");
   Dims3 dims{{D, H, W}}, one{{1, 1, 1}};
+  if (tile_mask) U3D_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)cdiv(cap > 0 ? cap : 1, 128) * 4, st));
   dim3 grid(grid_x_for(cap, 256, kNumSMs * 2), 27);
   k_nbr_build<<<grid, 256, 0, st>>>(coors, n_rows, (const uint2*)map, perm, dims, one, one, nbr,
-                                    nbr_stride);
+                                    nbr_stride, tile_mask);
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }
@@ -210,7 +222,8 @@ extern "C" int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, i
                                  const int32_t* in_dims, const int32_t* out_dims,
                                  const int32_t* stride, const int32_t* pad, void* out_map_,
                                  int32_t* scan_scratch, int32_t* out_coors, int32_t* n_out,
-                                 int out_cap, int32_t* nbr, int nbr_stride, void* stream) {
+                                 int out_cap, int32_t* nbr, int nbr_stride, uint32_t* tile_mask,
+                                 void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   U3D_CHECK_ARG(in_coors && n_in && in_map && out_map_ && scan_scratch && out_coors && n_out && nbr,
                 "u3d_rulebook_down: null buffer");
@@ -235,9 +248,10 @@ extern "C" int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, i
   k_map_emit_coors<<<grid_x_for((long long)words, 256, kNumSMs * 8), 256, 0, st>>>(
       out_map, words, od.d[0], od.d[1], od.d[2], out_coors, out_cap);
   U3D_LAUNCH_CHECK();
+  if (tile_mask) U3D_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)cdiv(out_cap > 0 ? out_cap : 1, 128) * 4, st));
   dim3 gn(grid_x_for(out_cap, 256, kNumSMs * 2), 27);
   k_nbr_build<<<gn, 256, 0, st>>>(out_coors, n_out, (const uint2*)in_map, in_perm, id, s, p, nbr,
-                                  nbr_stride);
+                                  nbr_stride, tile_mask);
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }

@@ -8,18 +8,22 @@
 //
 // Persistent, warp-specialised kernel: one CTA per SM loops over 128-row output tiles (UMMA M =
 // 128 = the 128 TMEM lanes; N = Cout <= 256 per instruction, two instructions for Cout = 512).
-// The reduction of a tile runs over its ACTIVE kernel offsets (offsets whose 128 rulebook entries
-// are all empty are skipped) and over Cin in blocks of CIN_BLK in {16,32,64} elements.
-//   warps 5-12  producers: load the tile's rulebook slice (27 x 128 ints) into shared memory,
-//               derive the active-offset mask with warp ballots, then per stage gather
-//               128 input rows x CIN_BLK bf16 with 16-byte cp.async (zero-fill for missing
-//               neighbours) into a K-major stage with the hardware swizzle of 2*CIN_BLK bytes;
-//               a stage is published with cp.async.mbarrier.arrive.noinc - the hardware arrives
-//               on the stage's mbarrier when the thread's copies have landed, so producers never
-//               wait on their own loads and the whole ring stays in flight. One producer thread fetches
-//               the stage's weight tile W[k][:, block] - a pre-swizzled (Cout x CIN_BLK) image
-//               laid out by u3d_spconv_pack_weights - with ONE cp.async.bulk (TMA) that completes
-//               on the same mbarrier.
+// The reduction of a tile runs over its ACTIVE kernel offsets (per-tile bit masks written by the
+// rulebook build: offsets whose 128 entries are all empty are skipped) and over Cin in blocks of
+// CIN_BLK in {16,32,64} elements.
+//   warp 5      slice loader: bulk-copies (cp.async.bulk) the active 512-byte rows of the next
+//               tiles' rulebook slices into a 3-deep shared-memory ring.
+//   warps 6-13  producers, one STAGE per warp at a time (warp w owns ring slot w, ring <= 8): the
+//               warp gathers the stage's 128 input rows x CIN_BLK bf16 with 16-byte cp.async
+//               (zero-fill for missing neighbours) into the K-major stage with the hardware
+//               swizzle of 2*CIN_BLK bytes - 32 copies per lane in an unrolled loop, so barrier and
+//               loop overhead is paid once per stage per warp - and publishes it with
+//               cp.async.mbarrier.arrive.noinc (the hardware arrives when the copies land; no
+//               producer-side wait or fence). Lane 0 adds the stage's weight tile W[k][:, block] -
+//               a pre-swizzled (Cout x CIN_BLK) image from u3d_spconv_pack_weights - with ONE
+//               cp.async.bulk (TMA) completing on the same mbarrier.
+//               (A cp.async.bulk.tensor tile::gather4 producer was measured 2-3x slower than this
+//               LSU gather for 32..128-byte rows: 0.47 vs 0.21 ms on the 64->64 layers.)
 //   warp 4      MMA: one thread issues CIN_BLK/16 tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) per
 //               stage, releases the stage with tcgen05.commit, and commits the tile's accumulator.
 //   warps 0-3   epilogue: tcgen05.ld (32x32b.x16) of their TMEM lane quarter, scale/shift
@@ -36,11 +40,13 @@ namespace tc {
 constexpr int kRows = 128;             // UMMA M
 constexpr int kEpiThreads = 128;       // warps 0-3: epilogue (TMEM lane quarter = warp id)
 constexpr int kMmaWarp = 4;            // warp 4: MMA issue + TMEM allocation
-constexpr int kProdWarp0 = 5;          // warps 5-12: producers
-constexpr int kProdThreads = 256;
-constexpr int kThreads = (kProdWarp0 * 32) + kProdThreads;   // 416
+constexpr int kSliceWarp = 5;          // warp 5: rulebook-slice loader
+constexpr int kProdWarp0 = 6;          // warps 6-13: producers
+constexpr int kNumProd = 8;
+constexpr int kThreads = (kProdWarp0 + kNumProd) * 32;   // 448
+constexpr int kSliceBufs = 3;
 constexpr int kMaxK = 27;
-constexpr int kMaxStages = 12;
+constexpr int kMaxStages = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -156,31 +162,31 @@ template <int CIN_BLK> struct Swz {
 };
 
 struct Smem {
-  uint64_t full[kMaxStages];    // producers (256 arrives) + weight TMA (1 arrive + tx bytes)
+  uint64_t full[kMaxStages];    // 32 cp.async arrives (owning warp) + 1 arrive.expect_tx (weight TMA)
   uint64_t empty[kMaxStages];   // tcgen05.commit: the MMAs that read the stage have retired
   uint64_t acc_full[2];         // tcgen05.commit: accumulator of a tile is complete
   uint64_t acc_empty[2];        // 128 epilogue threads: accumulator drained
-  uint64_t tile_ready[2];       // 256 producers: rulebook slice + active mask of a tile are in smem
-  uint64_t tile_free[2];        // MMA thread: mask consumed, slice buffer reusable
+  uint64_t slice_full[kSliceBufs];   // tx bytes: rulebook slice of a tile has landed
+  uint64_t slice_empty[kSliceBufs];  // the active producer warps are done with the slice
   uint32_t tmem_base;
-  uint32_t mask[2];
   float scale[512];
   float shift[512];
-  int nbr[2][kMaxK][kRows];
+  alignas(128) int nbr[kSliceBufs][kMaxK][kRows];
 };
 
 template <int CIN_BLK>
 __global__ void __launch_bounds__(kThreads, 1)
 k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
-            const int32_t* __restrict__ n_out_p, int K, const __nv_bfloat16* __restrict__ wpk,
-            const float* __restrict__ scale, const float* __restrict__ shift,
-            const __nv_bfloat16* __restrict__ residual, int relu, __nv_bfloat16* __restrict__ out,
-            int Cin, int Cout, int stages, int acc_bufs, uint32_t tmem_cols) {
+            const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ n_out_p, int K,
+            const __nv_bfloat16* __restrict__ wpk, const float* __restrict__ scale,
+            const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
+            __nv_bfloat16* __restrict__ out, int Cin, int Cout, int stages, int acc_bufs,
+            uint32_t tmem_cols) {
   using SW = Swz<CIN_BLK>;
-  constexpr int kChunks = CIN_BLK / 8;                    // 16-byte chunks per A row
+  constexpr int kChunks = CIN_BLK / 8;            // 16-byte chunks per A row
+  constexpr int kRowsPerPass = 32 / kChunks;      // rows one warp-wide cp.async covers
+  constexpr int kPasses = kRows / kRowsPerPass;   // 32 / 16 / 8 copies per lane per stage
   constexpr int kABytes = kRows * SW::P;
-  constexpr int kRowsPerPass = kProdThreads / kChunks;    // rows covered by one cp.async per thread
-  constexpr int kPasses = kRows / kRowsPerPass > 0 ? kRows / kRowsPerPass : 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr uint32_t kHeader = (uint32_t)((sizeof(Smem) + 1023) & ~(size_t)1023);
@@ -194,19 +200,21 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   const uint32_t b_bytes = (uint32_t)Cout * SW::P;
   const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
   const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;  // 1024-aligned (dynamic smem base is)
+  const uint32_t all_mask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
 
   // ---- prologue: barriers, TMEM, epilogue constants
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&S.full[s], kProdThreads + 1);
+      mbar_init(&S.full[s], 32 + 1);
       mbar_init(&S.empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&S.acc_full[b], 1);
       mbar_init(&S.acc_empty[b], kEpiThreads);
-      mbar_init(&S.tile_ready[b], kProdThreads);
-      mbar_init(&S.tile_free[b], 1);
-      S.mask[b] = 0u;
+    }
+    for (int b = 0; b < kSliceBufs; ++b) {
+      mbar_init(&S.slice_full[b], 1);
+      mbar_init(&S.slice_empty[b], stages < kNumProd ? stages : kNumProd);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -227,69 +235,78 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   const uint32_t tmem = S.tmem_base;
 
   if (warp >= kProdWarp0) {
-    // ======================= producers =======================
-    const int ptid = tid - kProdWarp0 * 32;
-    const int chunk = ptid % kChunks;
-    const int row0 = ptid / kChunks;
-    int slot = 0;          // ring position of the next stage (continues across tiles)
-    uint32_t eph = 1u;     // parity to wait for on empty[slot] (fresh barriers pass parity 1)
+    // ======================= producers: one stage per warp at a time =======================
+    const int w = warp - kProdWarp0;
+    const int chunk = lane % kChunks;
+    const int rsub = lane / kChunks;
+    // per-lane constants: swizzled destination offset of passes 0 and 1; the XOR term of the swizzle
+    // has a period of 8 rows (128-byte rows) or less, i.e. at most 2 passes
+    const uint32_t off_even = SW::offset(rsub, chunk);
+    const uint32_t off_odd = SW::offset(rsub + kRowsPerPass, chunk) - (uint32_t)(kRowsPerPass * SW::P);
+    const uint64_t row_bytes = (uint64_t)Cin * 2;
+    // Each active producer warp OWNS ring slot w (host guarantees stages <= 8): it fills stages
+    // g = w, w + stages, w + 2*stages, ... so it meets the generations of its slot in order and the
+    // 1-bit mbarrier parity is never ambiguous.
+    const bool active = w < stages;
+    const int slot = w;
+    int ng = w;          // my next stage (global index)
+    uint32_t eph = 1u;   // parity to wait for on empty[slot]; flips on every visit
+    int g0 = 0;          // global index of the first stage of the current tile
     int t = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-      const int buf = t & 1;
+    for (int tile = blockIdx.x; active && tile < n_tiles; tile += gridDim.x, ++t) {
+      const int buf = t % kSliceBufs;
       const int m0 = tile * kRows;
-      // the slice buffer frees up once the MMA thread has started tile t-2
-      mbar_wait(&S.tile_free[buf], ((uint32_t)(t >> 1) & 1u) ^ 1u);
-      // rulebook slice of the tile: K x 128 entries, coalesced; per-offset "any" via ballot
-      {
-        const int total = K * kRows;
-        constexpr int kPer = (kMaxK * kRows + kProdThreads - 1) / kProdThreads;
-        int v[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          const int e = ptid + j * kProdThreads;
-          const int k = e >> 7, r = e & (kRows - 1);
-          int x = -1;
-          if (e < total) {
-            const int o = m0 + r;
-            if (o < n_out) x = nbr ? __ldg(&nbr[(size_t)k * nbr_stride + o]) : o;
-          }
-          v[j] = x;
+      const uint32_t mask = tile_mask ? __ldg(&tile_mask[tile]) : all_mask;
+      const int n_units = __popc(mask) * nkb;
+      const int rows_live = n_out - m0;   // rulebook entries of rows >= n_out are uninitialised memory
+      // every active warp passes through every slice (even one it owns no stage of): a warp can
+      // then never arrive twice on slice_empty[buf] within one phase
+      if (nbr) mbar_wait(&S.slice_full[buf], (uint32_t)(t / kSliceBufs) & 1u);
+      // my stages of this tile
+      for (; ng < g0 + n_units; ng += stages, eph ^= 1u) {
+        const int u = ng - g0;
+        const int ki = u / nkb, kb = u - ki * nkb;
+        const int k = __fns(mask, 0, ki + 1);            // position of the ki-th set bit
+        mbar_wait(&S.empty[slot], eph);
+        const uint32_t a_s = tiles_s + (uint32_t)slot * stage_bytes;
+        if (lane == 0) {
+          mbar_expect_tx(&S.full[slot], b_bytes);
+          bulk_g2s(a_s + kABytes, (const uint8_t*)wpk + ((size_t)k * nkb + kb) * b_bytes, b_bytes,
+                   &S.full[slot]);
         }
+        const uint8_t* src_base = reinterpret_cast<const uint8_t*>(in) + (size_t)(kb * CIN_BLK + chunk * 8) * 2;
+        const int* nb = nbr ? &S.nbr[buf][k][rsub] : nullptr;
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-          const int e = ptid + j * kProdThreads;
-          const int k = e >> 7, r = e & (kRows - 1);
-          if (e < total) S.nbr[buf][k][r] = v[j];
-          const unsigned any = __ballot_sync(0xffffffffu, e < total && v[j] >= 0);
-          if (any != 0u && lane == 0) atomicOr(&S.mask[buf], 1u << k);   // a warp spans one k
+        for (int i = 0; i < kPasses; ++i) {
+          const int src_row = nb ? nb[i * kRowsPerPass] : m0 + i * kRowsPerPass + rsub;
+          const bool ok = src_row >= 0 && i * kRowsPerPass + rsub < rows_live;
+          const uint8_t* src = src_base + (ok ? (uint64_t)(uint32_t)src_row * row_bytes : 0ull);
+          cp_async16(a_s + ((i & 1) ? off_odd : off_even) + (uint32_t)(i * kRowsPerPass * SW::P), src,
+                     ok ? 16u : 0u);
         }
+        // asynchronous publish: the hardware arrives on full[slot] when this lane's copies land
+        cp_async_arrive(&S.full[slot]);
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
-      uint32_t mask = S.mask[buf];
-      mbar_arrive(&S.tile_ready[buf]);
-      while (mask) {
-        const int k = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int* nb = S.nbr[buf][k];
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&S.empty[slot], eph);
-          const uint32_t a_s = tiles_s + (uint32_t)slot * stage_bytes;
-          if (ptid == 0) {
-            mbar_expect_tx(&S.full[slot], b_bytes);
-            bulk_g2s(a_s + kABytes, (const uint8_t*)wpk + ((size_t)k * nkb + kb) * b_bytes, b_bytes,
-                     &S.full[slot]);
-          }
-          const __nv_bfloat16* src_col = in + kb * CIN_BLK + chunk * 8;
-#pragma unroll
-          for (int i = 0; i < kPasses; ++i) {
-            const int r = row0 + i * kRowsPerPass;
-            const int src_row = nb[r];
-            const void* src = src_row >= 0 ? (const void*)(src_col + (size_t)src_row * Cin) : (const void*)in;
-            cp_async16(a_s + SW::offset(r, chunk), src, src_row >= 0 ? 16u : 0u);
-          }
-          // asynchronous publish: the hardware arrives on full[slot] when this thread's copies land
-          cp_async_arrive(&S.full[slot]);
-          if (++slot == stages) { slot = 0; eph ^= 1u; }
+      g0 += n_units;
+      if (nbr) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.slice_empty[buf]);
+      }
+    }
+  } else if (warp == kSliceWarp) {
+    // ======================= rulebook-slice loader (one thread) =======================
+    if (lane == 0 && nbr != nullptr) {
+      int t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const int buf = t % kSliceBufs;
+        mbar_wait(&S.slice_empty[buf], (((uint32_t)(t / kSliceBufs)) & 1u) ^ 1u);
+        uint32_t m = tile_mask ? __ldg(&tile_mask[tile]) : all_mask;
+        mbar_expect_tx(&S.slice_full[buf], (uint32_t)__popc(m) * (uint32_t)(kRows * 4));
+        while (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1;
+          bulk_g2s(smem_u32(&S.nbr[buf][k][0]), nbr + (size_t)k * nbr_stride + (size_t)tile * kRows,
+                   kRows * 4, &S.slice_full[buf]);
         }
       }
     }
@@ -300,12 +317,8 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       int slot = 0, t = 0;
       uint32_t fph = 0u;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
-        const int buf = t & 1;
         const int ab = t % acc_bufs;
-        mbar_wait(&S.tile_ready[buf], (uint32_t)(t >> 1) & 1u);
-        const uint32_t mask = S.mask[buf];
-        S.mask[buf] = 0u;
-        mbar_arrive(&S.tile_free[buf]);
+        const uint32_t mask = tile_mask ? __ldg(&tile_mask[tile]) : all_mask;
         const int n_st = __popc(mask) * nkb;
         mbar_wait(&S.acc_empty[ab], ((uint32_t)(t / acc_bufs) & 1u) ^ 1u);
         tc_fence_after();
@@ -421,13 +434,21 @@ bool spconv_tc_supported(int Cin, int Cout, int dtype) {
   return true;
 }
 
-int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride, const int32_t* n_out,
-                  int out_cap, int K, const void* wpk, const float* scale, const float* shift,
-                  const void* residual, int relu, void* out, int Cin, int Cout, cudaStream_t st) {
+int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
+                  const uint32_t* tile_mask, const int32_t* n_out, int out_cap, int K, const void* wpk,
+                  const float* scale, const float* shift, const void* residual, int relu, void* out,
+                  int Cin, int Cout, cudaStream_t st) {
   using namespace tc;
   U3D_CHECK_ARG(K >= 1 && K <= kMaxK, "spconv tc: K=%d unsupported", K);
   U3D_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)wpk | (uintptr_t)residual) & 15) == 0,
                 "spconv tc: buffers must be 16-byte aligned");
+  int tiles = cdiv(out_cap, kRows);
+  if (tiles < 1) return U3D_OK;
+  if (nbr) {
+    U3D_CHECK_ARG((((uintptr_t)nbr) & 15) == 0 && nbr_stride % 4 == 0 && nbr_stride >= tiles * kRows,
+                  "spconv tc: the rulebook must be 16-byte aligned with a row stride that is a multiple of 4 "
+                  "and >= 128*ceil(out_cap/128) (stride=%d, out_cap=%d)", nbr_stride, out_cap);
+  }
   const int blk = cin_blk_for(Cin);
   const uint32_t P = 2 * blk;
   const uint32_t b_bytes = (uint32_t)Cout * P;
@@ -436,23 +457,23 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride, const int3
   const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
   int stages = (int)((200u * 1024u - header) / stage_bytes);
   if (const char* e = getenv("U3D_TC_STAGES")) stages = atoi(e);
-  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > kNumProd) stages = kNumProd;   // one ring slot per producer warp
   if (stages < 2) stages = 2;
   const size_t smem = header + (size_t)stages * stage_bytes;
   U3D_CHECK_ARG(smem <= 227 * 1024, "spconv tc: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
   const int acc_bufs = 2 * Cout <= 512 ? 2 : 1;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < acc_bufs * Cout) tmem_cols <<= 1;
-  int tiles = cdiv(out_cap, kRows);
-  if (tiles < 1) return U3D_OK;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+
 #define U3D_TC_LAUNCH(BLK)                                                                          \
   do {                                                                                              \
     U3D_CUDA(cudaFuncSetAttribute(k_spconv_tc<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                   (int)smem));                                                      \
     k_spconv_tc<BLK><<<grid, kThreads, smem, st>>>(                                                 \
-        (const __nv_bfloat16*)in, nbr, nbr_stride, n_out, K, (const __nv_bfloat16*)wpk, scale, shift, \
-        (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, acc_bufs,      \
+        (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, n_out, K, (const __nv_bfloat16*)wpk,  \
+        scale, shift,                                                                               \
+        (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, acc_bufs,     \
         tmem_cols);                                                                                 \
   } while (0)
   if (blk == 64) U3D_TC_LAUNCH(64);
@@ -490,7 +511,8 @@ extern "C" int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, 
 }
 
 extern "C" int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr_stride,
-                                     const int32_t* n_out, int out_cap, int K, const void* w_packed,
+                                     const uint32_t* tile_mask, const int32_t* n_out, int out_cap,
+                                     int K, const void* w_packed,
                                      const float* scale, const float* shift, const void* residual,
                                      int relu, void* out, int Cin, int Cout, void* stream) {
   U3D_CHECK_ARG(in && n_out && w_packed && out, "u3d_spconv_fwd_packed: null buffer");
@@ -498,6 +520,6 @@ extern "C" int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr
   U3D_CHECK_ARG(spconv_tc_supported(Cin, Cout, U3D_BF16),
                 "u3d_spconv_fwd_packed: needs Cin in {16,32,64k<=512}, Cout a power of two in [16,512] "
                 "(Cin=%d Cout=%d)", Cin, Cout);
-  return spconv_fwd_tc(in, nbr, nbr_stride, n_out, out_cap, K, w_packed, scale, shift, residual, relu, out,
-                       Cin, Cout, (cudaStream_t)stream);
+  return spconv_fwd_tc(in, nbr, nbr_stride, tile_mask, n_out, out_cap, K, w_packed, scale, shift,
+                       residual, relu, out, Cin, Cout, (cudaStream_t)stream);
 }

@@ -202,16 +202,32 @@ def voxmap_build(coors, n_rows, cap, B, dims) -> VoxelMap:
     return VoxelMap(vm, perm, B, (D, H, W))
 
 
+class Rulebook(torch.Tensor):
+    """Neighbour table (27, cap) int32 that also carries the per-128-row tile masks
+    (`.tile_mask`, uint32 as int32) the tensor-core conv uses to skip empty kernel offsets."""
+    tile_mask = None
+    __torch_function__ = torch._C._disabled_torch_function_impl   # ops on it yield plain tensors
+
+    @staticmethod
+    def alloc(cap, device):
+        # row stride padded to whole 128-row tiles: the conv bulk-copies 512-byte rulebook rows
+        pad = max((cap + 127) // 128, 1) * 128
+        nbr = torch.empty((27, pad), dtype=torch.int32, device=device)[:, :max(cap, 1)].as_subclass(Rulebook)
+        nbr.tile_mask = torch.empty(pad // 128, dtype=torch.int32, device=device)
+        return nbr
+
+
 @_timed(lambda r, coors, n_rows, *a, **k: dict(n_in=int(n_rows), n_out=int(n_rows),
                                                pairs=_live_pairs(r, n_rows)))
 def rulebook_subm(coors, n_rows, cap, vmap: VoxelMap, nbr=None):
     lib = _lib.load()
     _req(coors, torch.int32, "coors")
     if nbr is None:
-        nbr = torch.empty((27, cap), dtype=torch.int32, device=coors.device)
+        nbr = Rulebook.alloc(cap, coors.device)
     D, H, W = vmap.dims
     _lib.check(lib.u3d_rulebook_subm(_p(coors), _p(n_rows), cap, _p(vmap.words), _p(vmap.perm),
-                                     vmap.B, D, H, W, _p(nbr), nbr.stride(0), _stream()))
+                                     vmap.B, D, H, W, _p(nbr), nbr.stride(0),
+                                     _p(getattr(nbr, "tile_mask", None)), _stream()))
     return nbr
 
 
@@ -235,14 +251,15 @@ def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=No
     scratch = _scan_scratch(words, dev)
     out_coors = torch.empty((out_cap, 4), dtype=torch.int32, device=dev)
     n_out = torch.empty(1, dtype=torch.int32, device=dev)
-    nbr = torch.empty((27, out_cap), dtype=torch.int32, device=dev)
+    nbr = Rulebook.alloc(out_cap, dev)
     a1, p1 = _iarr(in_dims)
     a2, p2 = _iarr(out_dims)
     a3, p3 = _iarr(stride)
     a4, p4 = _iarr(pad)
     _lib.check(lib.u3d_rulebook_down(_p(coors), _p(n_rows), in_cap, _p(vmap.words), _p(vmap.perm),
                                      vmap.B, p1, p2, p3, p4, _p(out_vm), _p(scratch), _p(out_coors),
-                                     _p(n_out), out_cap, _p(nbr), nbr.stride(0), _stream()))
+                                     _p(n_out), out_cap, _p(nbr), nbr.stride(0), _p(nbr.tile_mask),
+                                     _stream()))
     return out_coors, n_out, VoxelMap(out_vm, None, vmap.B, out_dims), nbr, out_cap
 
 
@@ -306,7 +323,9 @@ def spconv_fwd_packed(x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, scale=None
     if out is None:
         out = torch.empty((out_cap, Cout), dtype=torch.bfloat16, device=x.device)
     stride = nbr.stride(0) if nbr is not None else 0
-    _lib.check(lib.u3d_spconv_fwd_packed(_p(x), _p(nbr), stride, _p(n_out), out_cap, K, _p(w_packed),
+    tile_mask = getattr(nbr, "tile_mask", None) if nbr is not None else None
+    _lib.check(lib.u3d_spconv_fwd_packed(_p(x), _p(nbr), stride, _p(tile_mask), _p(n_out),
+                                         out_cap, K, _p(w_packed),
                                          _p(scale), _p(shift), _p(residual), int(bool(relu)), _p(out),
                                          Cin, Cout, _stream()))
     return out
