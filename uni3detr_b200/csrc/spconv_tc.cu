@@ -10,10 +10,11 @@
 // 128 = the 128 TMEM lanes; N = Cout <= 256 per instruction, two instructions for Cout = 512).
 // The reduction of a tile runs over its ACTIVE kernel offsets (per-tile bit masks written by the
 // rulebook build: offsets whose 128 entries are all empty are skipped) and over Cin in blocks of
-// CIN_BLK in {16,32,64} elements.
+// CIN_BLK in {16,32,64} elements; one pipeline stage always carries K = 64 reduction columns
+// (one 64-column block of one offset, or 2 / 4 whole offsets for Cin = 32 / 16).
 //   warp 5      slice loader: bulk-copies (cp.async.bulk) the active 512-byte rows of the next
 //               tiles' rulebook slices into a 3-deep shared-memory ring.
-//   warps 6-13  producers, one STAGE per warp at a time (warp w owns ring slot w, ring <= 8): the
+//   warps 6-13  producers, one STAGE per warp at a time (warp w owns ring slots w, w+8): the
 //               warp gathers the stage's 128 input rows x CIN_BLK bf16 with 16-byte cp.async
 //               (zero-fill for missing neighbours) into the K-major stage with the hardware
 //               swizzle of 2*CIN_BLK bytes - 32 copies per lane in an unrolled loop, so barrier and
@@ -46,7 +47,7 @@ constexpr int kNumProd = 8;
 constexpr int kThreads = (kProdWarp0 + kNumProd) * 32;   // 448
 constexpr int kSliceBufs = 3;
 constexpr int kMaxK = 27;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -181,12 +182,14 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
             const __nv_bfloat16* __restrict__ wpk, const float* __restrict__ scale,
             const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
             __nv_bfloat16* __restrict__ out, int Cin, int Cout, int stages, int acc_bufs,
-            uint32_t tmem_cols) {
+            uint32_t tmem_cols, int dbg) {
   using SW = Swz<CIN_BLK>;
   constexpr int kChunks = CIN_BLK / 8;            // 16-byte chunks per A row
   constexpr int kRowsPerPass = 32 / kChunks;      // rows one warp-wide cp.async covers
-  constexpr int kPasses = kRows / kRowsPerPass;   // 32 / 16 / 8 copies per lane per stage
-  constexpr int kABytes = kRows * SW::P;
+  constexpr int kPasses = kRows / kRowsPerPass;   // 32 / 16 / 8 copies per lane per unit
+  constexpr int kG = 64 / CIN_BLK;                // (offset, Cin-block) units per stage: K = 64 per stage
+  constexpr int kUnitA = kRows * SW::P;           // one 128-row A sub-tile
+  constexpr int kABytes = kG * kUnitA;            // 16 KB for every CIN_BLK
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr uint32_t kHeader = (uint32_t)((sizeof(Smem) + 1023) & ~(size_t)1023);
@@ -197,8 +200,9 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkb = Cin / CIN_BLK;
-  const uint32_t b_bytes = (uint32_t)Cout * SW::P;
-  const uint32_t stage_bytes = kABytes + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t b_bytes = (uint32_t)Cout * SW::P;                       // one weight sub-tile
+  const uint32_t b_unit = (b_bytes + 1023u) & ~1023u;                     // 1024-aligned sub-tiles
+  const uint32_t stage_bytes = kABytes + kG * b_unit;
   const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;  // 1024-aligned (dynamic smem base is)
   const uint32_t all_mask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
 
@@ -244,13 +248,12 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     const uint32_t off_even = SW::offset(rsub, chunk);
     const uint32_t off_odd = SW::offset(rsub + kRowsPerPass, chunk) - (uint32_t)(kRowsPerPass * SW::P);
     const uint64_t row_bytes = (uint64_t)Cin * 2;
-    // Each active producer warp OWNS ring slot w (host guarantees stages <= 8): it fills stages
-    // g = w, w + stages, w + 2*stages, ... so it meets the generations of its slot in order and the
-    // 1-bit mbarrier parity is never ambiguous.
+    // Each active producer warp OWNS ring slots w and w+8 (ring <= 16): it fills the stages
+    // g = w, w+8 (mod ring) in increasing order, so it meets the generations of each of its slots
+    // in order and the 1-bit mbarrier parity is never ambiguous.
     const bool active = w < stages;
-    const int slot = w;
-    int ng = w;          // my next stage (global index)
-    uint32_t eph = 1u;   // parity to wait for on empty[slot]; flips on every visit
+    int ng_a = w, ng_b = (w + kNumProd < stages) ? w + kNumProd : 0x7fffffff;   // next stage per slot
+    uint32_t eph_a = 1u, eph_b = 1u;   // parity to wait for on empty[slot]; flips on every visit
     int g0 = 0;          // global index of the first stage of the current tile
     int t = 0;
     for (int tile = blockIdx.x; active && tile < n_tiles; tile += gridDim.x, ++t) {
@@ -258,36 +261,52 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       const int m0 = tile * kRows;
       const uint32_t mask = tile_mask ? __ldg(&tile_mask[tile]) : all_mask;
       const int n_units = __popc(mask) * nkb;
+      const int n_st = (n_units + kG - 1) / kG;   // stages of this tile (kG units each, last one partial)
       const int rows_live = n_out - m0;   // rulebook entries of rows >= n_out are uninitialised memory
       // every active warp passes through every slice (even one it owns no stage of): a warp can
       // then never arrive twice on slice_empty[buf] within one phase
       if (nbr) mbar_wait(&S.slice_full[buf], (uint32_t)(t / kSliceBufs) & 1u);
       // my stages of this tile
-      for (; ng < g0 + n_units; ng += stages, eph ^= 1u) {
-        const int u = ng - g0;
-        const int ki = u / nkb, kb = u - ki * nkb;
-        const int k = __fns(mask, 0, ki + 1);            // position of the ki-th set bit
+      for (;;) {
+        const bool second = ng_b < ng_a;
+        const int ng = second ? ng_b : ng_a;
+        if (ng >= g0 + n_st) break;
+        const int slot = second ? w + kNumProd : w;
+        const uint32_t eph = second ? eph_b : eph_a;
+        if (second) { ng_b += stages; eph_b ^= 1u; } else { ng_a += stages; eph_a ^= 1u; }
+        const int u0 = (ng - g0) * kG;
+        const int cnt = n_units - u0 < kG ? n_units - u0 : kG;
         mbar_wait(&S.empty[slot], eph);
         const uint32_t a_s = tiles_s + (uint32_t)slot * stage_bytes;
-        if (lane == 0) {
-          mbar_expect_tx(&S.full[slot], b_bytes);
-          bulk_g2s(a_s + kABytes, (const uint8_t*)wpk + ((size_t)k * nkb + kb) * b_bytes, b_bytes,
-                   &S.full[slot]);
-        }
-        const uint8_t* src_base = reinterpret_cast<const uint8_t*>(in) + (size_t)(kb * CIN_BLK + chunk * 8) * 2;
-        const int* nb = nbr ? &S.nbr[buf][k][rsub] : nullptr;
+        if (lane == 0) mbar_expect_tx(&S.full[slot], (uint32_t)cnt * b_bytes);
 #pragma unroll
-        for (int i = 0; i < kPasses; ++i) {
-          const int src_row = nb ? nb[i * kRowsPerPass] : m0 + i * kRowsPerPass + rsub;
-          const bool ok = src_row >= 0 && i * kRowsPerPass + rsub < rows_live;
-          const uint8_t* src = src_base + (ok ? (uint64_t)(uint32_t)src_row * row_bytes : 0ull);
-          cp_async16(a_s + ((i & 1) ? off_odd : off_even) + (uint32_t)(i * kRowsPerPass * SW::P), src,
-                     ok ? 16u : 0u);
+        for (int j = 0; j < kG; ++j) {
+          if (j < cnt) {
+            const int u = u0 + j;
+            const int ki = u / nkb, kb = u - ki * nkb;
+            const int k = __fns(mask, 0, ki + 1);            // position of the ki-th set bit
+            if (lane == 0)
+              bulk_g2s(a_s + kABytes + (uint32_t)j * b_unit,
+                       (const uint8_t*)wpk + ((size_t)k * nkb + kb) * b_bytes, b_bytes, &S.full[slot]);
+            const uint8_t* src_base =
+                reinterpret_cast<const uint8_t*>(in) + (size_t)(kb * CIN_BLK + chunk * 8) * 2;
+            const int* nb = nbr ? &S.nbr[buf][k][rsub] : nullptr;
+            const uint32_t a_u = a_s + (uint32_t)(j * kUnitA);
+            if (!(dbg & 1))
+#pragma unroll
+            for (int i = 0; i < kPasses; ++i) {
+              const int src_row = nb ? nb[i * kRowsPerPass] : m0 + i * kRowsPerPass + rsub;
+              const bool ok = src_row >= 0 && i * kRowsPerPass + rsub < rows_live;
+              const uint8_t* src = src_base + (ok ? (uint64_t)(uint32_t)src_row * row_bytes : 0ull);
+              cp_async16(a_u + ((i & 1) ? off_odd : off_even) + (uint32_t)(i * kRowsPerPass * SW::P), src,
+                         ok ? 16u : 0u);
+            }
+          }
         }
         // asynchronous publish: the hardware arrives on full[slot] when this lane's copies land
         cp_async_arrive(&S.full[slot]);
       }
-      g0 += n_units;
+      g0 += n_st;
       if (nbr) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.slice_empty[buf]);
@@ -319,24 +338,37 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
         const int ab = t % acc_bufs;
         const uint32_t mask = tile_mask ? __ldg(&tile_mask[tile]) : all_mask;
-        const int n_st = __popc(mask) * nkb;
+        const int n_units = __popc(mask) * nkb;
+        const int n_st = (n_units + kG - 1) / kG;
         mbar_wait(&S.acc_empty[ab], ((uint32_t)(t / acc_bufs) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem + (uint32_t)(ab * Cout);
         for (int st = 0; st < n_st; ++st) {
+          const int cnt = n_units - st * kG < kG ? n_units - st * kG : kG;
           mbar_wait(&S.full[slot], fph);
-          tc_fence_after();
+          if (!(dbg & 8)) tc_fence_after();
           const uint32_t a_s = tiles_s + (uint32_t)slot * stage_bytes;
           const uint32_t b_s = a_s + kABytes;
+          if (dbg & 2) {   // timing experiment: no MMA, release the stage directly
+            mbar_arrive(&S.empty[slot]);
+            if (++slot == stages) { slot = 0; fph ^= 1u; }
+            continue;
+          }
+          for (int rep = 0; rep < ((dbg & 4) ? 2 : 1); ++rep)
           for (int n0 = 0; n0 < Cout; n0 += 256) {
             const int n = Cout - n0 < 256 ? Cout - n0 : 256;
             const uint32_t idesc = idesc_base | ((uint32_t)(n >> 3) << 17);
-            const uint64_t a_desc = SW::desc(a_s);
-            const uint64_t b_desc = SW::desc(b_s + (uint32_t)n0 * SW::P);
 #pragma unroll
-            for (int kk = 0; kk < CIN_BLK / 16; ++kk)
-              umma_bf16(d_tmem + (uint32_t)n0, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2),
-                        idesc, (st > 0 || kk > 0) ? 1u : 0u);
+            for (int j = 0; j < kG; ++j) {
+              if (j < cnt) {
+                const uint64_t a_desc = SW::desc(a_s + (uint32_t)(j * kUnitA));
+                const uint64_t b_desc = SW::desc(b_s + (uint32_t)j * b_unit + (uint32_t)n0 * SW::P);
+#pragma unroll
+                for (int kk = 0; kk < CIN_BLK / 16; ++kk)
+                  umma_bf16(d_tmem + (uint32_t)n0, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2),
+                            idesc, (st > 0 || j > 0 || kk > 0) ? 1u : 0u);
+              }
+            }
           }
           umma_commit(&S.empty[slot]);   // frees the stage once these MMAs have read it
           if (++slot == stages) { slot = 0; fph ^= 1u; }
@@ -452,12 +484,13 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
   const int blk = cin_blk_for(Cin);
   const uint32_t P = 2 * blk;
   const uint32_t b_bytes = (uint32_t)Cout * P;
-  const uint32_t stage_bytes = kRows * P + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t kg = 64 / blk;   // units per stage (see kG in the kernel)
+  const uint32_t stage_bytes = kg * kRows * P + kg * ((b_bytes + 1023u) & ~1023u);
   // one persistent CTA per SM: as deep an operand ring as ~200 KB allows (2..12 stages)
   const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
   int stages = (int)((200u * 1024u - header) / stage_bytes);
   if (const char* e = getenv("U3D_TC_STAGES")) stages = atoi(e);
-  if (stages > kNumProd) stages = kNumProd;   // one ring slot per producer warp
+  if (stages > kMaxStages) stages = kMaxStages;   // at most two ring slots per producer warp
   if (stages < 2) stages = 2;
   const size_t smem = header + (size_t)stages * stage_bytes;
   U3D_CHECK_ARG(smem <= 227 * 1024, "spconv tc: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
@@ -465,6 +498,8 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < acc_bufs * Cout) tmem_cols <<= 1;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  int dbg = 0;   // U3D_TC_DEBUG: timing experiments only (1 = skip the gathers, 2 = skip the MMAs)
+  if (const char* e = getenv("U3D_TC_DEBUG")) dbg = atoi(e);
 
 #define U3D_TC_LAUNCH(BLK)                                                                          \
   do {                                                                                              \
@@ -474,7 +509,7 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
         (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, n_out, K, (const __nv_bfloat16*)wpk,  \
         scale, shift,                                                                               \
         (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, acc_bufs,     \
-        tmem_cols);                                                                                 \
+        tmem_cols, dbg);                                                                            \
   } while (0)
   if (blk == 64) U3D_TC_LAUNCH(64);
   else if (blk == 32) U3D_TC_LAUNCH(32);
