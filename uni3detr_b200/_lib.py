@@ -13,8 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libu3d_b200.so")
 _SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu",
-            "fps.cu", "decoder.cu"]
-_HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_HERE, "..", "include", "u3d.h")]
+            "fps.cu", "decoder.cu", "mha_tc.cu"]
+_HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"),
+            os.path.join(_HERE, "..", "include", "u3d.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -5,6 +5,7 @@
 // Reference: projects/mmdet3d_plugin/models/utils/uni3detr_transformer.py
 //   get_sine_pos_embed :33-65 (called :180), UniCrossAtten.forward :271-360, and the
 //   nn.MultiheadAttention self-attention of mmcv's BaseTransformerLayer.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace u3d {
@@ -280,6 +281,10 @@ extern "C" int u3d_mha_core(const void* q, const void* k, const void* v, int ldq
                 "u3d_mha_core: bad shape");
   U3D_CHECK_ARG(n_seq <= 65535 && heads <= 65535, "u3d_mha_core: grid too large");
   U3D_CHECK_ARG(dtype == U3D_F32 || dtype == U3D_BF16, "u3d_mha_core: bad dtype");
+  // bf16: tcgen05 kernel (mha_tc.cu); fp32 (parity mode) and unsupported shapes: SIMT kernel below
+  if (dtype == U3D_BF16 && getenv("U3D_MHA_SIMT") == nullptr &&
+      mha_tc_supported(seq_len, ldq, ldk, ldv, q, k, v, out))
+    return mha_core_tc(q, k, v, ldq, ldk, ldv, n_seq, seq_len, heads, out, st);
   dim3 grid(cdiv(seq_len, kQBlock), heads, n_seq);
   if (dtype == U3D_F32)
     k_mha_core<float><<<grid, kMhaWarps * 32, 0, st>>>((const float*)q, (const float*)k,

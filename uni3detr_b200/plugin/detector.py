@@ -74,20 +74,27 @@ class Uni3DETR(nn.Module):
         """list[B] of (N_i,C) f32 -> x (B,256,D,H,W), fpsbpts (B,2nq,3) in [0,1]."""
         B = len(pts)
         nq = self.num_query
-        points, pt_off, lens, vox = self.pts_voxel_layer.batched(
-            pts, index_dims=self.pts_middle_encoder.sparse_shape)
-        C = points.shape[1]
         cur = torch.cuda.current_stream()
         if self._fps_stream is None:
-            self._fps_stream = torch.cuda.Stream(device=points.device)
-        side = self._fps_stream
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            # FPS #1 on the raw points (uni3detr.py:178-181)
+            dev = pts[0].device
+            self._fps_stream = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+        s1, s2 = self._fps_stream
+        cat = self.pts_voxel_layer.concat(pts)
+        points, pt_off, lens = cat
+        C = points.shape[1]
+        # FPS #1 on the raw points (uni3detr.py:178-181) needs nothing but the points: it starts
+        # right away on its own stream, next to the voxelization
+        s1.wait_stream(cur)
+        with torch.cuda.stream(s1):
             ds = 3 if self.fps_stride_quirk else C
             _, fps1 = ops.fps(points, ds, C, points, C, pt_off, B, max(lens), nq, reverse=False)
-            # FPS #2 on voxel coordinates (uni3detr.py:183-187): hard -> input voxel coords;
-            # dynamic -> the per-point coords (including -1 rows), as the reference does
+        points, pt_off, lens, vox = self.pts_voxel_layer.batched(
+            pts, index_dims=self.pts_middle_encoder.sparse_shape, concat=cat)
+        # FPS #2 on voxel coordinates (uni3detr.py:183-187): hard -> input voxel coords;
+        # dynamic -> the per-point coords (including -1 rows), as the reference does.
+        # Second side stream: it overlaps the sparse encoder.
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s2):
             if self.dynamic_voxelization:
                 cf = ops.coors_to_float(vox.pt_coors)
                 seg, max_n = pt_off, max(lens)
@@ -97,7 +104,6 @@ class Uni3DETR(nn.Module):
                 mv = self.pts_voxel_layer.current_max_voxels()
                 max_n = max(min(n, mv) if mv > 0 else n for n in lens)
             _, fps2 = ops.fps(cf, 3, 3, cf, 3, seg, B, max_n, nq, reverse=True)
-            fpsbpts = torch.cat([fps1, fps2], 1)
         x = self.pts_middle_encoder.forward_voxels(vox.feats, vox.coors, vox.n_rows, vox.cap,
                                                    vox.vmap, B)
         if self.capture is not None:
@@ -108,11 +114,16 @@ class Uni3DETR(nn.Module):
             x = self.pts_neck(x)
         if self.capture is not None:
             self.capture.update(neck=x)
-        cur.wait_stream(side)
-        for t in (points, pt_off, vox.coors, vox.scene_rows, vox.pt_coors):
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+        for t in (points, pt_off):
+            t.record_stream(s1)         # allocated on `cur`, read on the side streams
+        for t in (vox.coors, vox.scene_rows, vox.pt_coors, pt_off):
             if t is not None:
-                t.record_stream(side)   # allocated on `cur`, read on the side stream
-        fpsbpts.record_stream(cur)      # allocated on the side stream, read on `cur`
+                t.record_stream(s2)
+        for t in (fps1, fps2, cf):
+            t.record_stream(cur)        # allocated on a side stream, consumed/freed on `cur`
+        fpsbpts = torch.cat([fps1, fps2], 1)
         return x, fpsbpts
 
     def forward(self, return_loss=True, **kwargs):

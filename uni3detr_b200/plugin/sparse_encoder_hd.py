@@ -212,13 +212,20 @@ class SparseEncoderHD(nn.Module):
             w = conv.weight.detach().reshape(k, conv.in_channels, conv.out_channels)
             scale, shift = _fold_bn(s["bn"], conv.bias)
             w = w.to(dtype).contiguous()
-            packed = None
-            if (self.use_tensor_cores and dtype == torch.bfloat16 and w.is_cuda
-                    and ops.spconv_tc_supported(k, conv.in_channels, conv.out_channels)):
-                packed = ops.spconv_pack_weights(w)
+            packed, cin = None, conv.in_channels
+            if self.use_tensor_cores and dtype == torch.bfloat16 and w.is_cuda:
+                if cin < 16 and not steps:
+                    # the K-starved stem (Cin = 4/5): zero-pad the reduction dim to 16 so it runs on
+                    # the tensor-core kernel too (the input features are padded in forward_voxels)
+                    cin = 16
+                    w = torch.nn.functional.pad(w, (0, 0, 0, cin - conv.in_channels)).contiguous()
+                if ops.spconv_tc_supported(k, cin, conv.out_channels):
+                    packed = ops.spconv_pack_weights(w)
+                else:
+                    cin, w = conv.in_channels, w[:, :conv.in_channels].contiguous()
             steps.append(dict(w=w, packed=packed, scale=scale, shift=shift, relu=s["relu"],
                               save=s["save"], add=s["add"], subm=conv.subm, k=k,
-                              cin=conv.in_channels, cout=conv.out_channels,
+                              cin=cin, cout=conv.out_channels,
                               stride=conv.stride, pad=conv.padding))
         self._plan = dict(dtype=dtype, steps=steps, tc=self.use_tensor_cores)
         return self._plan
@@ -236,6 +243,8 @@ class SparseEncoderHD(nn.Module):
             plan = self.prepare()
         dtype = plan["dtype"]
         x = feats.to(dtype).contiguous()
+        if plan["steps"][0]["cin"] > x.shape[1]:
+            x = torch.nn.functional.pad(x, (0, plan["steps"][0]["cin"] - x.shape[1]))
         dims = tuple(self.sparse_shape)
         level = dict(coors=coors, n=n_rows, cap=cap, vmap=vmap, nbr=None, dims=dims)
         saved = None

@@ -56,18 +56,23 @@ class Voxelization(nn.Module):
         m = int(v.scene_rows[-1].item())  # the per-sample API returns exact-size tensors
         return v.voxels[:m], v.coors[:m, 1:], v.num_points[:m]
 
-    def batched(self, points_list, index_dims=None):
+    @staticmethod
+    def concat(points_list):
+        """list[B] of (N_i,C) -> (points (Ntot,C) f32, pt_off (B+1) int32 on device, lens)."""
+        lens = [int(p.shape[0]) for p in points_list]
+        pts = torch.cat([p.float() for p in points_list], 0).contiguous()
+        off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0).tolist()), dtype=torch.int32)
+        return pts, off.to(pts.device, non_blocking=True), lens
+
+    def batched(self, points_list, index_dims=None, concat=None):
         """Fused batch path: one launch sequence for the whole batch, VFE mean included.
         index_dims: (D,H,W) index space of the VoxelMap = the encoder's sparse_shape (SECOND-style
         configs declare it one cell deeper in z than the voxel grid); default: the voxel grid."""
         dims = tuple(int(v) for v in index_dims) if index_dims is not None else self.grid_zyx
         if any(g > d for g, d in zip(self.grid_zyx, dims)):
             raise ValueError(f"voxel grid {self.grid_zyx} does not fit sparse_shape {dims}")
-        lens = [int(p.shape[0]) for p in points_list]
-        pts = torch.cat([p.float() for p in points_list], 0).contiguous()
-        off = torch.tensor([0] + list(torch.tensor(lens).cumsum(0).tolist()), dtype=torch.int32)
-        off = off.to(pts.device, non_blocking=True)
-        B = len(points_list)
+        pts, off, lens = concat if concat is not None else self.concat(points_list)
+        B = len(lens)
         if self.dynamic:
             v = ops.voxelize_dynamic(pts, off, B, self.point_cloud_range, self.voxel_size, dims)
         else:
