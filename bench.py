@@ -237,10 +237,23 @@ def run_gpu(args):
     dev_pts = [p.to(dev) for p in host_pts]
     rp = torch.rand(B, nq, 3, generator=torch.Generator().manual_seed(1234 + rank)).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    host_batch = torch.cat(host_pts, 0).pin_memory()                # (B*20000, C) pinned
 
-    def step(points):
+    def eager_step(points):
         outs, _ = model.forward_raw(points, random_point=rp)
         return coder.decode_fixed(outs)
+
+    graphed = None
+    if not args.no_graph:
+        # the public serving call: the whole forward captured once as a CUDA graph, replayed per batch
+        from uni3detr_b200 import GraphedForward
+        graphed = GraphedForward(model, [p.shape[0] for p in host_pts], host_pts[0].shape[1], random_point=rp)
+        graphed.load(host_batch)
+
+    def step(points):
+        if graphed is not None:
+            return graphed.run(points if torch.is_tensor(points) else None)
+        return eager_step(points)
 
     # ---- device-resident throughput ("value")
     for _ in range(W):
@@ -261,6 +274,8 @@ def run_gpu(args):
         e.record()
     torch.cuda.synchronize()
     launches = ops.launch_count() - n0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * K      # kernels of the replayed graph
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -275,8 +290,10 @@ def run_gpu(args):
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        pts = [p.to(dev, non_blocking=True) for p in host_pts]
-        boxes, scores, labels, mask = step(pts)
+        if graphed is not None:
+            boxes, scores, labels, mask = step(host_batch)                # H2D of the batch inside
+        else:
+            boxes, scores, labels, mask = step([p.to(dev, non_blocking=True) for p in host_pts])
         out_host = [t.cpu() for t in (boxes, scores, labels, mask)]      # D2H read of the step's result
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -289,7 +306,7 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     # ---- rank 0 only: roofline of the dominant libu3d kernel + CPU baseline
-    roof, kernels, ours_ms = roofline_pass(lambda: step(dev_pts), peaks)
+    roof, kernels, ours_ms = roofline_pass(lambda: eager_step(dev_pts), peaks)
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -302,7 +319,8 @@ def run_gpu(args):
             "config": {"workload": "uni3detr_sunrgbd.py synthetic 20k-pt scenes, 300 queries x4 groups, 3 decoder "
                                    "layers, full forward (voxelize+sparse encoder+dense CNN+FPS+decoder+top-k)",
                        "scenes_per_step_per_gpu": B, "points_per_scene": 20000, "parallelism": f"scenes sharded x{world}",
-                       "l2": "256 MiB flush write between timed steps (untimed)", "timing": "CUDA events per step, max over ranks"},
+                       "l2": "256 MiB flush write between timed steps (untimed)", "timing": "CUDA events per step, max over ranks",
+                       "launch": "eager" if graphed is None else "CUDA graph replay (uni3detr_b200.GraphedForward)"},
             "e2e": {"value": scenes / e2e_max, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "kernels": kernels, "libu3d_ms_per_step": ours_ms, "checksum": checksum}
@@ -321,6 +339,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-scenes", type=int, default=2, help="bounded CPU-baseline sample (scenes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 20:

@@ -13,6 +13,12 @@ from .compat import Config, build_model  # noqa: F401
 __version__ = "0.1.0"
 
 
+def GraphedForward(*args, **kwargs):
+    """CUDA-graph replay of the forward for fixed batch signatures (see graphed.py)."""
+    from .graphed import GraphedForward as _G
+    return _G(*args, **kwargs)
+
+
 def register_all():
     """Import the plugin modules (registers every drop-in class)."""
     from . import plugin  # noqa: F401

@@ -124,6 +124,16 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
   return __float2bfloat16_rn(v);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the requirement grows: launches (and
+// CUDA-graph captures) after the first one of a kernel/size make no attribute call at all
+template <typename Kern>
+static inline cudaError_t ensure_dynamic_smem(Kern kern, size_t bytes, int* cur) {
+  if ((int)bytes <= *cur) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) *cur = (int)bytes;
+  return e;
+}
+
 static inline size_t dtype_size(int dtype) { return dtype == U3D_BF16 ? 2 : 4; }
 
 // internal launchers shared between translation units

@@ -244,9 +244,13 @@ static int launch_fps(const float* dist_src, int dist_stride, int dist_seg_strid
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (CS > 8) U3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  if (dyn > 48 * 1024)
-    U3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  static bool configured = false;   // per template instantiation
+  if (!configured) {
+    if (CS > 8) U3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (dyn > 48 * 1024)
+      U3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    configured = true;
+  }
   U3D_CUDA(cudaLaunchKernelEx(&cfg, kern, dist_src, dist_stride, dist_seg_stride, gather_src,
                               gather_stride, seg, nq, reverse, idx, out));
   count_launch();

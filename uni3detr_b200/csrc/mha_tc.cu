@@ -227,7 +227,8 @@ int mha_core_tc(const void* q, const void* k, const void* v, int ldq, int ldk, i
                 int seq_len, int heads, void* out, cudaStream_t st) {
   using namespace mha;
   const size_t smem = make_layout((seq_len + 63) & ~63).total + 1024;
-  U3D_CUDA(cudaFuncSetAttribute(k_mha_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static int cur_smem = 0;
+  U3D_CUDA(ensure_dynamic_smem(k_mha_tc, smem, &cur_smem));
   dim3 grid(cdiv(seq_len, kQB), heads, n_seq);
   k_mha_tc<<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
                                           (const __nv_bfloat16*)v, ldq, ldk, ldv, seq_len, heads,

@@ -390,8 +390,8 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
 
 #define U3D_TC_LAUNCH(BLK)                                                                          \
   do {                                                                                              \
-    U3D_CUDA(cudaFuncSetAttribute(k_spconv_tc<BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                  (int)smem));                                                      \
+    static int cur_smem = 0;                                                                        \
+    U3D_CUDA(ensure_dynamic_smem(k_spconv_tc<BLK>, smem, &cur_smem));                               \
     k_spconv_tc<BLK><<<grid, kThreads, smem, st>>>(                                                 \
         (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, n_out, K, (const __nv_bfloat16*)wpk,  \
         scale, shift,                                                                               \

@@ -70,16 +70,18 @@ class Uni3DETR(nn.Module):
 
     # ---------------------------------------------------------------- hot path ---
     @torch.no_grad()
-    def extract_pts_feat(self, pts):
-        """list[B] of (N_i,C) f32 -> x (B,256,D,H,W), fpsbpts (B,2nq,3) in [0,1]."""
-        B = len(pts)
+    def extract_pts_feat(self, pts, concat=None):
+        """list[B] of (N_i,C) f32 -> x (B,256,D,H,W), fpsbpts (B,2nq,3) in [0,1].
+        concat = (points (Ntot,C), pt_off (B+1) int32 device, lens) replaces `pts` with an already
+        concatenated batch (static buffers of a captured CUDA graph)."""
+        B = len(concat[2]) if concat is not None else len(pts)
         nq = self.num_query
         cur = torch.cuda.current_stream()
         if self._fps_stream is None:
             dev = pts[0].device
             self._fps_stream = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         s1, s2 = self._fps_stream
-        cat = self.pts_voxel_layer.concat(pts)
+        cat = concat if concat is not None else self.pts_voxel_layer.concat(pts)
         points, pt_off, lens = cat
         C = points.shape[1]
         # FPS #1 on the raw points (uni3detr.py:178-181) needs nothing but the points: it starts
@@ -116,6 +118,9 @@ class Uni3DETR(nn.Module):
             self.capture.update(neck=x)
         cur.wait_stream(s1)
         cur.wait_stream(s2)
+        fpsbpts = torch.cat([fps1, fps2], 1)
+        if torch.cuda.is_current_stream_capturing():
+            return x, fpsbpts           # graph-private memory pool: no cross-stream bookkeeping
         for t in (points, pt_off):
             t.record_stream(s1)         # allocated on `cur`, read on the side streams
         for t in (vox.coors, vox.scene_rows, vox.pt_coors, pt_off):
@@ -123,7 +128,6 @@ class Uni3DETR(nn.Module):
                 t.record_stream(s2)
         for t in (fps1, fps2, cf):
             t.record_stream(cur)        # allocated on a side stream, consumed/freed on `cur`
-        fpsbpts = torch.cat([fps1, fps2], 1)
         return x, fpsbpts
 
     def forward(self, return_loss=True, **kwargs):
@@ -163,7 +167,7 @@ class Uni3DETR(nn.Module):
         return results
 
     @torch.no_grad()
-    def forward_raw(self, points, random_point=None):
+    def forward_raw(self, points, random_point=None, concat=None):
         """Hot path only (no CPU post-processing): returns the head's prediction dict."""
-        pts_feat, fpsbpts = self.extract_pts_feat(points)
+        pts_feat, fpsbpts = self.extract_pts_feat(points, concat=concat)
         return self.pts_bbox_head(pts_feat, None, fpsbpts, random_point=random_point), fpsbpts

@@ -42,6 +42,15 @@ class NMSFreeCoder:
         self.score_threshold = score_threshold
         self.num_classes = num_classes
         self.alpha = alpha
+        self._pcr = {}
+
+    def _range(self, like):
+        """post_center_range as a tensor on `like`'s device, created once per device (so a captured
+        CUDA graph of the forward contains no host-to-device copy)."""
+        key = (like.device, like.dtype)
+        if key not in self._pcr:
+            self._pcr[key] = like.new_tensor(self.post_center_range)
+        return self._pcr[key]
 
     def encode(self):
         pass
@@ -57,7 +66,7 @@ class NMSFreeCoder:
         if self.post_center_range is None:
             raise NotImplementedError("Need to reorganize output as a batch, only support "
                                       "post_center_range is not None for now!")
-        pcr = scores.new_tensor(self.post_center_range)
+        pcr = self._range(scores)
         mask = (final_box_preds[..., :3] >= pcr[:3]).all(1)
         mask &= (final_box_preds[..., :3] <= pcr[3:]).all(1)
         if self.score_threshold:
@@ -85,7 +94,7 @@ class NMSFreeCoder:
         boxes = denormalize_bbox(torch.gather(box, 1, qi.unsqueeze(-1).expand(-1, -1, box.shape[-1])),
                                  self.pc_range)
         ious = torch.gather(iou.sigmoid().squeeze(-1), 1, qi)
-        pcr = scores.new_tensor(self.post_center_range)
+        pcr = self._range(scores)
         mask = (boxes[..., :3] >= pcr[:3]).all(-1) & (boxes[..., :3] <= pcr[3:]).all(-1)
         if self.score_threshold:
             mask &= scores > self.score_threshold
