@@ -78,7 +78,7 @@ class Uni3DETR(nn.Module):
         nq = self.num_query
         cur = torch.cuda.current_stream()
         if self._fps_stream is None:
-            dev = pts[0].device
+            dev = concat[0].device if concat is not None else pts[0].device
             self._fps_stream = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
         s1, s2 = self._fps_stream
         cat = concat if concat is not None else self.pts_voxel_layer.concat(pts)

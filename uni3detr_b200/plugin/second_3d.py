@@ -232,9 +232,11 @@ class SECOND3DFPN(_PlanMixin, nn.Module):
             p = self.prepare()
         ups = [d(xi.to(self.compute_dtype).contiguous(memory_format=torch.channels_last_3d))
                for d, xi in zip(p["deblocks"], x)]
-        out = ups[0]
+        # sum in the tensors' own memory order (NDHWC): the add is then one vectorised kernel
+        out = ups[0].permute(0, 2, 3, 4, 1)
         for u in ups[1:]:
-            out = out + u
+            out = out + u.permute(0, 2, 3, 4, 1)
+        out = out.permute(0, 4, 1, 2, 3)
         for conv in p["extra"]:
             out = conv(out)
         return out
