@@ -23,6 +23,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# The driver parses ONE JSON line from stdout: keep the real stdout for that line only and send
+# everything else that libraries print on fd 1 (NCCL's version banner, cuDNN notices) to stderr.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 WORKLOAD = "sunrgbd"
 RIDGE_NOTE = "bound = tensor if FLOP/byte of the launch exceeds measured bf16 peak / measured HBM peak, else hbm"
 
@@ -125,7 +137,7 @@ def run_reference(args):
                              "sample": f"{steps} scene(s), one per step, oracle/model.py full forward + decode"},
             "e2e": {"value": rate, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ GPU arm ----
@@ -324,7 +336,7 @@ def run_gpu(args):
             "e2e": {"value": scenes / e2e_max, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "kernels": kernels, "libu3d_ms_per_step": ours_ms, "checksum": checksum}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

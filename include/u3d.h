@@ -229,6 +229,19 @@ int u3d_coors_to_float(const int32_t* coors, int rows, float* out, void* stream)
 int u3d_sine_embed(const float* ref, int rows, void* out, int dtype, void* stream);
 
 /*
+ * Fused residual add + LayerNorm (+ReLU): out = act(LN(a (+b) (+c)) * gamma + beta), rows of C.
+ * Replaces the `identity + x` adds and nn.LayerNorm launches of mmcv's BaseTransformerLayer
+ * (operation_order self_attn/norm/cross_attn/norm/ffn/norm, config uni3detr_sunrgbd.py:76-100), the
+ * LayerNorm+ReLU pairs of UniCrossAtten.position_encoder (uni3detr_transformer.py:253-260) and of the
+ * head's cls branches (uni3detr_head.py:367-374).
+ *   a, b, c, out: (rows, C) `dtype`; b, c may be NULL; gamma, beta: (C) `dtype`
+ *   C a multiple of 256 (bf16) / 128 (f32), at most 1024 / 512
+ */
+int u3d_add_layernorm(const void* a, const void* b, const void* c, const void* gamma,
+                      const void* beta, float eps, int rows, int C, int relu, void* out, int dtype,
+                      void* stream);
+
+/*
  * Multi-head self-attention core: softmax(Q K^T / sqrt(hd)) V per (sequence, head),
  * warp-shuffle online softmax. Replaces the attention core of nn.MultiheadAttention
  * used through mmcv MultiheadAttention (config uni3detr_sunrgbd.py:79-83).

@@ -256,9 +256,100 @@ k_cross_sample(const T* __restrict__ value, int D, int H, int W, int C,
   }
 }
 
+// ------------------------------------------------- fused residual add + LayerNorm ---
+// out[r,:] = act( LN(a[r,:] (+ b[r,:]) (+ c[r,:])) * gamma + beta ); one warp per row, the row stays
+// in registers between the statistics and the normalisation (one HBM read of each input, one write).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_add_layernorm(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c,
+                const T* __restrict__ gamma, const T* __restrict__ beta, float eps, int rows, int C,
+                int relu, T* __restrict__ out) {
+  typedef Vec<T> V;
+  typedef typename V::type vec_t;
+  constexpr int VN = V::N;
+  constexpr int kMaxVec = 4;                       // C <= 32 * VN * 4
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int nvec = C / (32 * VN);
+  float x[kMaxVec][VN];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    if (j < nvec) {
+      const size_t off = (size_t)r * C + (size_t)(j * 32 + lane) * VN;
+      V::unpack(__ldg(reinterpret_cast<const vec_t*>(a + off)), x[j]);
+      if (b) {
+        float t[VN];
+        V::unpack(__ldg(reinterpret_cast<const vec_t*>(b + off)), t);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) x[j][i] += t[i];
+      }
+      if (c) {
+        float t[VN];
+        V::unpack(__ldg(reinterpret_cast<const vec_t*>(c + off)), t);
+#pragma unroll
+        for (int i = 0; i < VN; ++i) x[j][i] += t[i];
+      }
+#pragma unroll
+      for (int i = 0; i < VN; ++i) sum += x[j][i];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j)
+    if (j < nvec)
+#pragma unroll
+      for (int i = 0; i < VN; ++i) { const float d = x[j][i] - mean; var += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / (float)C + eps);
+#pragma unroll
+  for (int j = 0; j < kMaxVec; ++j) {
+    if (j < nvec) {
+      const int col = (j * 32 + lane) * VN;
+      float g[VN], be[VN], y[VN];
+      V::unpack(__ldg(reinterpret_cast<const vec_t*>(gamma + col)), g);
+      V::unpack(__ldg(reinterpret_cast<const vec_t*>(beta + col)), be);
+#pragma unroll
+      for (int i = 0; i < VN; ++i) {
+        y[i] = (x[j][i] - mean) * rstd * g[i] + be[i];
+        if (relu) y[i] = fmaxf(y[i], 0.f);
+      }
+      *reinterpret_cast<vec_t*>(out + (size_t)r * C + col) = V::pack(y);
+    }
+  }
+}
+
 }  // namespace u3d
 
 using namespace u3d;
+
+extern "C" int u3d_add_layernorm(const void* a, const void* b, const void* c, const void* gamma,
+                                 const void* beta, float eps, int rows, int C, int relu, void* out,
+                                 int dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  U3D_CHECK_ARG(a && gamma && beta && out && rows >= 0, "u3d_add_layernorm: bad argument");
+  U3D_CHECK_ARG(dtype == U3D_F32 || dtype == U3D_BF16, "u3d_add_layernorm: bad dtype");
+  const int vn = dtype == U3D_BF16 ? 8 : 4;
+  U3D_CHECK_ARG(C >= 32 * vn && C % (32 * vn) == 0 && C <= 32 * vn * 4,
+                "u3d_add_layernorm: C=%d must be a multiple of %d and <= %d", C, 32 * vn, 32 * vn * 4);
+  if (rows == 0) return U3D_OK;
+  const int grid = cdiv(rows, 8);
+  if (dtype == U3D_F32)
+    k_add_layernorm<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, (const float*)c,
+                                                 (const float*)gamma, (const float*)beta, eps, rows, C, relu,
+                                                 (float*)out);
+  else
+    k_add_layernorm<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)c, (const __nv_bfloat16*)gamma,
+        (const __nv_bfloat16*)beta, eps, rows, C, relu, (__nv_bfloat16*)out);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
 
 extern "C" int u3d_sine_embed(const float* ref, int rows, void* out, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;

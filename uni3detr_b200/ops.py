@@ -379,6 +379,22 @@ def sine_embed(ref, dtype=torch.float32):
     return out
 
 
+@_timed(lambda r, a, *x, **k: dict(rows=a.shape[0], bytes=(2 + len([t for t in x[:2] if t is not None]))
+                                    * a.numel() * a.element_size()))
+def add_layernorm(a, b, c, gamma, beta, eps, relu=False):
+    """act(LN(a (+b) (+c)) * gamma + beta) over the last dim; a,b,c (rows, C) same dtype."""
+    lib = _lib.load()
+    _req(a, None, "a")
+    rows, C = a.shape
+    for t in (b, c):
+        if t is not None:
+            _req(t, a.dtype, "residual")
+    out = torch.empty_like(a)
+    _lib.check(lib.u3d_add_layernorm(_p(a), _p(b), _p(c), _p(gamma), _p(beta), float(eps), rows, C,
+                                     int(bool(relu)), _p(out), _DT[a.dtype], _stream()))
+    return out
+
+
 @_timed(lambda r, q, k_, v, n_seq, seq_len, heads: dict(n_seq=n_seq, seq_len=seq_len, heads=heads,
                                                        esize=q.element_size()))
 def mha_core(q, k, v, n_seq, seq_len, heads):

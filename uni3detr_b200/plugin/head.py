@@ -14,7 +14,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..compat import BBOX_CODERS, HEADS, TRANSFORMER, build_from_cfg
-from .transformer import _run_mlp, _wb, inverse_sigmoid
+from .transformer import _ln, _run_mlp, _wb, inverse_sigmoid
 
 
 def denormalize_bbox(normalized_bboxes, pc_range=None):
@@ -248,8 +248,10 @@ class Uni3DETRHead(nn.Module):
             x = hs[lvl]
             c = x
             cp = p["cls"][lvl]
+            c = c.reshape(-1, E)
             for i, (w, b) in enumerate(cp["lin"][:-1]):
-                c = torch.relu_(F.layer_norm(F.linear(c, w, b), (E,), *cp["ln"][i]))
+                c = _ln(F.linear(c, w, b), cp["ln"][i], relu=True)
+            c = c.reshape(x.shape)
             outputs_class = F.linear(c, *cp["lin"][-1]).float()
             tmp = _run_mlp(x, p["reg"][lvl]).float()
             outputs_iou = _run_mlp(x, p["iou"][lvl]).float()

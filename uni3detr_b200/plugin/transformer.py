@@ -162,12 +162,28 @@ def _mlp_plan(mlp_layers, dtype):
     return [_wb(l, dtype) for l in mlp_layers]
 
 
+def _linear_relu(x, w, b):
+    """relu(x @ w.T + b) with the bias+ReLU in the GEMM epilogue (cuBLASLt) for 2-D CUDA inputs."""
+    if x.is_cuda and x.dim() == 2:
+        return torch._addmm_activation(b, x, w.t())
+    return torch.relu_(F.linear(x, w, b))
+
+
 def _run_mlp(x, plan):
     for i, (w, b) in enumerate(plan):
-        x = F.linear(x, w, b)
-        if i < len(plan) - 1:
-            x = torch.relu_(x)
+        x = _linear_relu(x, w, b) if i < len(plan) - 1 else F.linear(x, w, b)
     return x
+
+
+def _ln(a, ln, b=None, c=None, relu=False):
+    """act(LayerNorm(a (+b) (+c))): one fused libu3d kernel on CUDA, torch ops otherwise."""
+    w, bias, eps = ln
+    if a.is_cuda and a.dim() == 2 and a.shape[1] % (256 if a.dtype == torch.bfloat16 else 128) == 0:
+        return ops.add_layernorm(a.contiguous(), b, c, w, bias, eps, relu)
+    x = a if b is None else a + b
+    x = x if c is None else x + c
+    y = F.layer_norm(x, (a.shape[-1],), w, bias, eps)
+    return torch.relu_(y) if relu else y
 
 
 @TRANSFORMER_LAYER_SEQUENCE.register_module()
@@ -253,18 +269,17 @@ class Uni3DETRTransformerDecoder(nn.Module):
             qk = F.linear(out + qpos, *L["in_qk"])
             v = F.linear(out, *L["in_v"])
             attn = ops.mha_core(qk[:, :E], qk[:, E:], v, n_seq, nq, L["heads"])
-            x = out + F.linear(attn, *L["out"])
-            x = F.layer_norm(x, (E,), *L["ln"][0])
+            x = _ln(out, L["ln"][0], F.linear(attn, *L["out"]))
             # cross attention: sample * gate -> proj, + residual + positional MLP
             s = ops.cross_sample(value, ref, x, qpos, L["gate_w"], L["gate_b"], Q)
             o = F.linear(s, *L["oproj"])
             pf = ref.to(dt)
             for (w, b), ln in zip(L["pe"], L["pe_ln"]):
-                pf = torch.relu_(F.layer_norm(F.linear(pf, w, b), (E,), *ln))
-            x = F.layer_norm(o + x + pf, (E,), *L["ln"][1])
+                pf = _ln(F.linear(pf, w, b), ln, relu=True)
+            x = _ln(o, L["ln"][1], x, pf)
             # FFN
-            h = torch.relu_(F.linear(x, *L["ffn"][0]))
-            x = F.layer_norm(x + F.linear(h, *L["ffn"][1]), (E,), *L["ln"][2])
+            h = _linear_relu(x, *L["ffn"][0])
+            x = _ln(x, L["ln"][2], F.linear(h, *L["ffn"][1]))
             out = x
             if reg_plans is not None:
                 tmp = _run_mlp(out, reg_plans[lid]).float()
