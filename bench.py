@@ -212,7 +212,12 @@ def roofline_pass(step_fn, peaks, reps=3):
     else:
         roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": top["gbs"] / peaks["hbm"]}
-    roof.update({"traffic": None, "kernel": top["kernel"], "avg_launch_ms": top["avg_launch_ms"],
+    traffic = None   # dram__bytes_read+write per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(top["kernel"], {}).get("dram_bytes_per_launch")
+    roof.update({"traffic": traffic, "kernel": top["kernel"], "avg_launch_ms": top["avg_launch_ms"],
                  "algorithmic_bytes_per_launch": top["bytes_per_launch"],
                  "algorithmic_flops_per_launch": top["flops_per_launch"],
                  "peak_source": peaks["source"] + " (sustained bf16 / copy bandwidth)", "rule": RIDGE_NOTE})

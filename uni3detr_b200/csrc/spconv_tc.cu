@@ -43,7 +43,7 @@ constexpr int kEpiThreads = 128;       // warps 0-3: epilogue (TMEM lane quarter
 constexpr int kMmaWarp = 4;            // warp 4: MMA issue + TMEM allocation
 constexpr int kSliceWarp = 5;          // warp 5: rulebook-slice loader
 constexpr int kProdWarp0 = 6;          // warps 6-13: producers
-constexpr int kNumProd = 8;
+constexpr int kNumProd = 8;            // producer warps with one CTA per SM (4 with two)
 constexpr int kThreads = (kProdWarp0 + kNumProd) * 32;   // 448
 constexpr int kSliceBufs = 3;
 constexpr int kMaxK = 27;
@@ -62,8 +62,8 @@ struct Smem {
   alignas(128) int nbr[kSliceBufs][kMaxK][kRows];
 };
 
-template <int CIN_BLK>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CIN_BLK, int CTAS>
+__global__ void __launch_bounds__(CTAS == 1 ? kThreads : (kProdWarp0 + kNumProd / 2) * 32, CTAS)
 k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
             const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ n_out_p, int K,
             const __nv_bfloat16* __restrict__ wpk, const float* __restrict__ scale,
@@ -71,6 +71,8 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
             __nv_bfloat16* __restrict__ out, int Cin, int Cout, int stages, int acc_bufs,
             uint32_t tmem_cols, int dbg) {
   using SW = Swz<CIN_BLK>;
+  constexpr int kNP = kNumProd / CTAS;            // producer warps of this CTA
+  constexpr int kNT = (kProdWarp0 + kNP) * 32;    // threads of this CTA
   constexpr int kChunks = CIN_BLK / 8;            // 16-byte chunks per A row
   constexpr int kRowsPerPass = 32 / kChunks;      // rows one warp-wide cp.async covers
   constexpr int kPasses = kRows / kRowsPerPass;   // 32 / 16 / 8 copies per lane per unit
@@ -105,7 +107,7 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     }
     for (int b = 0; b < kSliceBufs; ++b) {
       mbar_init(&S.slice_full[b], 1);
-      mbar_init(&S.slice_empty[b], stages < kNumProd ? stages : kNumProd);
+      mbar_init(&S.slice_empty[b], stages < kNP ? stages : kNP);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -116,7 +118,7 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int c = tid; c < Cout; c += kThreads) {
+  for (int c = tid; c < Cout; c += kNT) {
     S.scale[c] = scale ? __ldg(&scale[c]) : 1.f;
     S.shift[c] = shift ? __ldg(&shift[c]) : 0.f;
   }
@@ -139,7 +141,7 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     // g = w, w+8 (mod ring) in increasing order, so it meets the generations of each of its slots
     // in order and the 1-bit mbarrier parity is never ambiguous.
     const bool active = w < stages;
-    int ng_a = w, ng_b = (w + kNumProd < stages) ? w + kNumProd : 0x7fffffff;   // next stage per slot
+    int ng_a = w, ng_b = (w + kNP < stages) ? w + kNP : 0x7fffffff;   // next stage per slot
     uint32_t eph_a = 1u, eph_b = 1u;   // parity to wait for on empty[slot]; flips on every visit
     int g0 = 0;          // global index of the first stage of the current tile
     int t = 0;
@@ -158,7 +160,7 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         const bool second = ng_b < ng_a;
         const int ng = second ? ng_b : ng_a;
         if (ng >= g0 + n_st) break;
-        const int slot = second ? w + kNumProd : w;
+        const int slot = second ? w + kNP : w;
         const uint32_t eph = second ? eph_b : eph_a;
         if (second) { ng_b += stages; eph_b ^= 1u; } else { ng_a += stages; eph_a ^= 1u; }
         const int u0 = (ng - g0) * kG;
@@ -373,26 +375,36 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
   const uint32_t b_bytes = (uint32_t)Cout * P;
   const uint32_t kg = 64 / blk;   // units per stage (see kG in the kernel)
   const uint32_t stage_bytes = kg * kRows * P + kg * ((b_bytes + 1023u) & ~1023u);
-  // one persistent CTA per SM: as deep an operand ring as ~200 KB allows (2..12 stages)
+  // persistent CTAs: one per SM with as deep an operand ring as ~200 KB allows, or (U3D_TC_CTAS=2)
+  // two per SM with half the ring, half the producer warps and half of TMEM each
+  int ctas = 1;
+  if (const char* e = getenv("U3D_TC_CTAS")) ctas = atoi(e) == 2 ? 2 : 1;
+  if (Cout > 256) ctas = 1;
   const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
-  int stages = (int)((200u * 1024u - header) / stage_bytes);
+  const size_t budget = ctas == 1 ? 200u * 1024u : 110u * 1024u;
+  int stages = (int)((budget - header) / stage_bytes);
   if (const char* e = getenv("U3D_TC_STAGES")) stages = atoi(e);
-  if (stages > kMaxStages) stages = kMaxStages;   // at most two ring slots per producer warp
+  const int max_stages = 2 * (kNumProd / ctas);   // at most two ring slots per producer warp
+  if (stages > max_stages) stages = max_stages;
   if (stages < 2) stages = 2;
   const size_t smem = header + (size_t)stages * stage_bytes;
   U3D_CHECK_ARG(smem <= 227 * 1024, "spconv tc: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
-  const int acc_bufs = 2 * Cout <= 512 ? 2 : 1;
+  const int acc_bufs = 2 * Cout * ctas <= 512 ? 2 : 1;
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < acc_bufs * Cout) tmem_cols <<= 1;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  const int grid = tiles < kNumSMs * ctas ? tiles : kNumSMs * ctas;
   int dbg = 0;   // U3D_TC_DEBUG: timing experiments only (1 = skip the gathers, 2 = skip the MMAs)
   if (const char* e = getenv("U3D_TC_DEBUG")) dbg = atoi(e);
 
-#define U3D_TC_LAUNCH(BLK)                                                                          \
+#define U3D_TC_LAUNCH(BLK) \
+  do {                     \
+    if (ctas == 1) U3D_TC_LAUNCH2(BLK, 1); else U3D_TC_LAUNCH2(BLK, 2); \
+  } while (0)
+#define U3D_TC_LAUNCH2(BLK, CT)                                                                     \
   do {                                                                                              \
     static int cur_smem = 0;                                                                        \
-    U3D_CUDA(ensure_dynamic_smem(k_spconv_tc<BLK>, smem, &cur_smem));                               \
-    k_spconv_tc<BLK><<<grid, kThreads, smem, st>>>(                                                 \
+    U3D_CUDA(ensure_dynamic_smem(k_spconv_tc<BLK, CT>, smem, &cur_smem));                           \
+    k_spconv_tc<BLK, CT><<<grid, (kProdWarp0 + kNumProd / CT) * 32, smem, st>>>(                    \
         (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, n_out, K, (const __nv_bfloat16*)wpk,  \
         scale, shift,                                                                               \
         (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages, acc_bufs,     \
@@ -402,6 +414,7 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
   else if (blk == 32) U3D_TC_LAUNCH(32);
   else U3D_TC_LAUNCH(16);
 #undef U3D_TC_LAUNCH
+#undef U3D_TC_LAUNCH2
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }
