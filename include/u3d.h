@@ -264,6 +264,20 @@ int u3d_cross_sample(const void* value, int B, int D, int H, int W, int C,
                      const float* gate_w, float gate_b, int Q, void* out, int dtype,
                      void* stream);
 
+/*
+ * Per-class rotated-BEV-IoU NMS, batched over scenes.
+ * Replaces: the per-class python loop over mmcv.ops.nms3d (iou3d_nms3d_forward) in
+ * Uni3DETRHead.get_bboxes, models/dense_heads/uni3detr_head.py:847-871.
+ *   boxes (B,N,7) f32 [x,y,z,dx,dy,dz,heading], each scene sorted by (label asc, score desc);
+ *   labels (B,N) int32; valid (B,N) uint8 (0 = row not a candidate);
+ *   mask: u3d_nms3d_mask_words(N)*B uint64 scratch; keep (B,N) uint8 (out): 1 = survives.
+ *   A box is suppressed by a kept box of the SAME label earlier in the order when their BEV IoU
+ *   (exact intersection area of the rotated rectangles) exceeds iou_threshold. N <= 8192.
+ */
+size_t u3d_nms3d_mask_words(int N);
+int u3d_nms3d_bev(const float* boxes, const int32_t* labels, const uint8_t* valid, int B, int N,
+                  float iou_threshold, unsigned long long* mask, uint8_t* keep, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

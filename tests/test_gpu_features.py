@@ -309,3 +309,61 @@ def test_spconv_tc_wide_and_ragged(cin, cout, n):
     ref = oracle_conv(x, G.subm_rulebook(coors, dims), w, n, scale, shift, None, False)
     assert relerr(out[:n], ref) < 1e-2, relerr(out[:n], ref)
     assert bool((out[n:] == -5.0).all())
+
+
+def _random_boxes(n, n_cls, seed):
+    rng = np.random.default_rng(seed)
+    centres = rng.random((12, 2)) * 8                      # clustered -> many overlaps
+    which = rng.integers(0, 12, n)
+    b = np.zeros((n, 7), np.float32)
+    b[:, :2] = centres[which] + rng.normal(0, 0.35, (n, 2))
+    b[:, 2] = rng.random(n)
+    b[:, 3:6] = 0.6 + rng.random((n, 3)) * 1.4
+    b[:, 6] = rng.uniform(-np.pi, np.pi, n)
+    return b, rng.random(n).astype(np.float32), rng.integers(0, n_cls, n).astype(np.int64)
+
+
+@pytest.mark.parametrize("n,n_cls,thr", [(200, 3, 0.5), (65, 1, 0.2), (1, 2, 0.5), (300, 10, 0.5)])
+def test_nms3d_bev_vs_oracle(n, n_cls, thr):
+    """u3d_nms3d_bev (all classes, all scenes, one launch pair) == per-class oracle nms3d."""
+    from oracle import postproc as PP
+    from uni3detr_b200 import ops
+    scenes = [_random_boxes(n, n_cls, 10 * n + s) for s in range(2)]
+    bs, ls, vs, refs = [], [], [], []
+    for b, s, l in scenes:
+        valid = np.ones(n, bool)
+        valid[n // 7::9] = False                             # some rows are not candidates
+        order = np.lexsort((-s, np.where(valid, l, n_cls)))  # (label asc, score desc), invalid last
+        b, s, l, valid = b[order], s[order], l[order], valid[order]
+        keep = np.zeros(n, bool)
+        for j in range(n_cls):
+            idx = np.nonzero((l == j) & valid)[0]
+            if len(idx):
+                keep[idx[PP.nms3d(b[idx], s[idx], thr)]] = True
+        bs.append(b); ls.append(l); vs.append(valid); refs.append(keep)
+    keep = ops.nms3d_bev(T(np.stack(bs)).to(DEV), T(np.stack(ls)).int().to(DEV), T(np.stack(vs)).to(DEV), thr)
+    np.testing.assert_array_equal(keep.cpu().numpy(), np.stack(refs))
+
+
+def test_get_bboxes_nms_vs_oracle(golden):
+    """Uni3DETRHead.get_bboxes with post_processing 'nms' (+score_thr, num_thr) vs the oracle's
+    restatement of uni3detr_head.py:827-918, on the reference-generated head outputs."""
+    from oracle import postproc as PP
+    head = head_fixture(golden)
+    outs = {k: T(golden["head_" + k]).to(DEV) for k in ("all_cls_scores", "all_bbox_preds", "all_iou_preds")}
+    # make the decoded boxes overlap: shrink the centre spread, enlarge the sizes
+    outs["all_bbox_preds"] = outs["all_bbox_preds"].clone()
+    outs["all_bbox_preds"][..., [0, 1]] *= 0.3
+    outs["all_bbox_preds"][..., [2, 3, 5]] = outs["all_bbox_preds"][..., [2, 3, 5]].clamp(-1, 1) + 0.5
+    for pp in (dict(type="nms", nms_thr=0.3), dict(type="nms", nms_thr=0.1, score_thr=0.3, num_thr=4),
+               dict(type="nms", nms_thr=0.5, score_thr=[0.2, 0.4, 0.1])):
+        head.post_processing = pp
+        got = head.get_bboxes(outs, [{}, {}])
+        dec = head.bbox_coder.decode(outs)
+        for i, (gb, gs, gl) in enumerate(got):
+            d = {k: v.cpu().numpy() for k, v in dec[i].items()}
+            rb, rs, rl = PP.get_bboxes_nms(d, head.num_classes, pp)
+            assert len(gs) == len(rs), (pp, len(gs), len(rs))
+            np.testing.assert_array_equal(gl.cpu().numpy(), rl)
+            np.testing.assert_allclose(gs.cpu().numpy(), rs, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(gb.cpu().numpy(), rb, rtol=1e-5, atol=1e-5)

@@ -188,3 +188,21 @@ def test_transformer_layer_vs_torch_modules():
         None, None, False, 0.0, sd["attentions.0.attn.out_proj.weight"],
         sd["attentions.0.attn.out_proj.bias"], training=False, need_weights=False)
     torch.testing.assert_close(x + out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_bev_iou_closed_forms():
+    """oracle/postproc.py rotated IoU against analytic cases."""
+    from oracle import postproc as PP
+    a = [0, 0, 0, 2, 2, 1, 0.0]
+    assert abs(PP.bev_iou(a, a) - 1.0) < 1e-12
+    assert abs(PP.bev_iou(a, [1, 0, 0, 2, 2, 1, 0.0]) - (2.0 / 6.0)) < 1e-12        # half overlap
+    assert PP.bev_iou(a, [5, 5, 0, 2, 2, 1, 0.3]) == 0.0
+    # unit square vs itself rotated 45 deg: intersection = regular octagon, area 2*(sqrt2 - 1) * 1
+    sq = [0, 0, 0, 1, 1, 1, 0.0]
+    inter = 2 * (np.sqrt(2) - 1)
+    assert abs(PP.bev_iou(sq, [0, 0, 0, 1, 1, 1, np.pi / 4]) - inter / (2 - inter)) < 1e-12
+    # heading periodicity and dx/dy swap at 90 deg
+    assert abs(PP.bev_iou([0, 0, 0, 4, 2, 1, np.pi / 2], [0, 0, 0, 2, 4, 1, 0.0]) - 1.0) < 1e-12
+    # greedy order: the best box suppresses its neighbour, the far one survives
+    boxes = np.array([[0, 0, 0, 2, 2, 1, 0], [0.2, 0, 0, 2, 2, 1, 0], [5, 0, 0, 2, 2, 1, 0]], float)
+    np.testing.assert_array_equal(PP.nms3d(boxes, [0.5, 0.9, 0.1], 0.5), [1, 2])

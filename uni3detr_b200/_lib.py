@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libu3d_b200.so")
 _SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu",
-            "fps.cu", "decoder.cu", "mha_tc.cu"]
+            "fps.cu", "decoder.cu", "mha_tc.cu", "nms.cu"]
 _HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"),
             os.path.join(_HERE, "..", "include", "u3d.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -81,6 +81,8 @@ SIGNATURES = {
     "u3d_sine_embed": (_i32, [_vp, _i32, _vp, _i32, _vp]),
     "u3d_add_layernorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "u3d_mha_core": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "u3d_nms3d_mask_words": (_sz, [_i32]),
+    "u3d_nms3d_bev": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp]),
     "u3d_cross_sample": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _i32,
                                 _vp, _i32, _vp]),
 }

@@ -425,6 +425,22 @@ def cross_sample(value_ndhwc, ref, query, query_pos, gate_w, gate_b, Q):
     return out
 
 
+@_timed(lambda r, boxes, *a, **k: dict(B=boxes.shape[0], N=boxes.shape[1]))
+def nms3d_bev(boxes, labels, valid, iou_threshold):
+    """boxes (B,N,7) f32 sorted per scene by (label, score desc), labels (B,N) int32, valid (B,N) bool
+    -> keep (B,N) bool. Same-label rotated-BEV-IoU greedy NMS for all scenes in one launch pair."""
+    lib = _lib.load()
+    _req(boxes, torch.float32, "boxes")
+    _req(labels, torch.int32, "labels")
+    B, N = labels.shape
+    v8 = valid.to(torch.uint8).contiguous()
+    mask = torch.empty(max(B * lib.u3d_nms3d_mask_words(N), 1), dtype=torch.int64, device=boxes.device)
+    keep = torch.empty((B, N), dtype=torch.uint8, device=boxes.device)
+    _lib.check(lib.u3d_nms3d_bev(_p(boxes), _p(labels), _p(v8), B, N, float(iou_threshold), _p(mask),
+                                 _p(keep), _stream()))
+    return keep.bool()
+
+
 def launch_count():
     """Kernels launched by libu3d_b200 in this process so far."""
     return int(_lib.load().u3d_launch_count())

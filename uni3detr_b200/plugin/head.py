@@ -272,17 +272,64 @@ class Uni3DETRHead(nn.Module):
                                   "is a 'next' row, SURVEY.md 8f rank 3")
 
     @torch.no_grad()
+    def postprocess_fixed(self, preds_dicts):
+        """Device-resident get_bboxes (uni3detr_head.py:827-918) for post_processing None / 'nms':
+        NMSFreeCoder top-k, gravity-centre -> bottom-centre shift (:842), per-class nms3d for every
+        scene in one launch pair (:847-871), score_thr (:895-908), num_thr (:910-914). Fixed-size
+        outputs, no host synchronisation: returns boxes (B,M,7|9), scores (B,M), labels (B,M) int64
+        and keep (B,M) bool; the kept rows, in order, are the reference's result."""
+        from .. import ops
+        boxes, scores, labels, keep = self.bbox_coder.decode_fixed(preds_dicts)
+        boxes = boxes.clone()
+        boxes[..., 2] = boxes[..., 2] - boxes[..., 5] * 0.5
+        pp = self.post_processing
+        if pp is None:
+            return boxes, scores, labels, keep
+        if pp["type"] != "nms":
+            raise NotImplementedError(f"post_processing type {pp['type']!r}: soft_nms / box_merging are "
+                                      "CPU post-processing outside the device path (SURVEY.md 2.1 rows 5,12)")
+        # class-major, score-descending order inside a class (the reference's output order);
+        # rows the coder dropped sort to the end
+        B, M = scores.shape
+        o1 = torch.sort(scores, dim=1, descending=True, stable=True)[1]
+        lab = torch.where(keep, labels, torch.full_like(labels, self.num_classes))
+        o2 = torch.sort(torch.gather(lab, 1, o1), dim=1, stable=True)[1]
+        order = torch.gather(o1, 1, o2)
+        boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, boxes.shape[-1]))
+        scores, labels, keep = (torch.gather(t, 1, order) for t in (scores, labels, keep))
+        keep = keep & ops.nms3d_bev(boxes[..., :7].float().contiguous(), labels.int().contiguous(), keep,
+                                    pp["nms_thr"])
+        if "score_thr" in pp:
+            thr = pp["score_thr"]
+            if isinstance(thr, (list, tuple)):
+                assert len(thr) == self.num_classes
+                keep = keep & (scores > scores.new_tensor(thr)[labels.clamp(max=self.num_classes - 1)])
+            else:
+                keep = keep & (scores > thr)
+        if "num_thr" in pp:
+            k = min(int(pp["num_thr"]), M)
+            masked = torch.where(keep, scores, scores.new_full((), -1.0))
+            top, order = torch.sort(masked, dim=1, descending=True, stable=True)
+            order, top = order[:, :k], top[:, :k]
+            boxes = torch.gather(boxes, 1, order.unsqueeze(-1).expand(-1, -1, boxes.shape[-1]))
+            scores, labels = torch.gather(scores, 1, order), torch.gather(labels, 1, order)
+            keep = top >= 0
+        return boxes, scores, labels, keep
+
+    @torch.no_grad()
     def get_bboxes(self, preds_dicts, img_metas, rescale=False):
-        """NMSFreeCoder.decode + gravity-centre -> bottom-centre shift (uni3detr_head.py:827-843).
-        The per-class NMS / box-merging that follows in the reference is a 'next' row."""
-        preds = self.bbox_coder.decode(preds_dicts)
+        """Reference API (uni3detr_head.py:827-918): list over scenes of [bboxes, scores, labels].
+        post_processing None / 'nms' run on the device (:meth:`postprocess_fixed`); the only host
+        round trip is the final compaction to exact-size tensors."""
+        boxes, scores, labels, keep = self.postprocess_fixed(preds_dicts)
         ret = []
-        for i, pr in enumerate(preds):
-            bboxes = pr["bboxes"].clone()
-            bboxes[:, 2] = bboxes[:, 2] - bboxes[:, 5] * 0.5
+        for i in range(boxes.shape[0]):
+            k = keep[i]
+            bboxes = boxes[i][k]
             meta = img_metas[i] if img_metas is not None and i < len(img_metas) else {}
             box_type = meta.get("box_type_3d") if isinstance(meta, dict) else None
             if box_type is not None:
                 bboxes = box_type(bboxes, bboxes.shape[-1])
-            ret.append([bboxes, pr["scores"], pr["labels"]])
+            ret.append([bboxes, scores[i][k], labels[i][k]])
         return ret
+
