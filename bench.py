@@ -6,7 +6,7 @@
   python bench.py --impl reference      # CPU arm: the oracle port on the host cores
 
 One "step" = one pass of the hot path (voxelize -> sparse encoder -> dense CNN -> 2x FPS -> decoder
--> heads -> NMSFreeCoder top-k) over a batch of B synthetic 20k-point SUN-RGBD-shaped scenes
+-> heads -> NMSFreeCoder top-k -> per-class NMS) over a batch of B synthetic 20k-point SUN-RGBD-shaped scenes
 (BASELINE config 2: uni3detr_sunrgbd.py, 300 queries x 4 groups, 3 decoder layers, bf16).
 Scenes are sharded whole across ranks (weak scaling: B scenes per rank per step, no data-path
 collective); one all-reduce of the metrics vector ends the job.
@@ -258,7 +258,7 @@ def run_gpu(args):
 
     def eager_step(points):
         outs, _ = model.forward_raw(points, random_point=rp)
-        return coder.decode_fixed(outs)
+        return model.pts_bbox_head.postprocess_fixed(outs)
 
     graphed = None
     if not args.no_graph:
@@ -334,7 +334,7 @@ def run_gpu(args):
             "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "uni3detr_sunrgbd.py synthetic 20k-pt scenes, 300 queries x4 groups, 3 decoder "
-                                   "layers, full forward (voxelize+sparse encoder+dense CNN+FPS+decoder+top-k)",
+                                   "layers, full forward (voxelize+sparse encoder+dense CNN+FPS+decoder+top-k+per-class NMS)",
                        "scenes_per_step_per_gpu": B, "points_per_scene": 20000, "parallelism": f"scenes sharded x{world}",
                        "l2": "256 MiB flush write between timed steps (untimed)", "timing": "CUDA events per step, max over ranks",
                        "launch": "eager" if graphed is None else "CUDA graph replay (uni3detr_b200.GraphedForward)"},

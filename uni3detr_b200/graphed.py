@@ -10,13 +10,14 @@ import torch
 
 
 class GraphedForward:
-    """forward + NMSFreeCoder top-k for batches of a fixed signature (points per scene, C, dtype).
+    """forward + NMSFreeCoder top-k (+ device post-processing: bottom-centre shift, per-class NMS,
+    thresholds) for batches of a fixed signature (points per scene, C, dtype).
 
     run(host_points=None) copies the (pinned) host batch into the static device buffer, replays the
     graph and returns the static outputs (boxes (B,max_num,7|9), scores, labels, mask); the caller
     reads them back / synchronises as needed."""
 
-    def __init__(self, model, lens, channels, random_point=None, warmup=3):
+    def __init__(self, model, lens, channels, random_point=None, warmup=3, postprocess=True):
         dev = next(model.parameters()).device
         self.model, self.lens = model, [int(n) for n in lens]
         B, nq = len(self.lens), model.num_query
@@ -26,6 +27,10 @@ class GraphedForward:
         self.random_point = random_point.to(dev) if random_point is not None else \
             torch.rand(B, nq, 3, device=dev)
         self.coder = model.pts_bbox_head.bbox_coder
+        pp = model.pts_bbox_head.post_processing
+        # the device-side get_bboxes (per-class NMS ...) rides in the same graph when the config's
+        # post-processing is one the device path implements; otherwise the graph ends at the top-k
+        self.postprocess = bool(postprocess) and (pp is None or pp.get("type") == "nms")
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):       # warm-up: cuDNN plans, weight packing, allocator pools
@@ -43,6 +48,8 @@ class GraphedForward:
     def _forward(self):
         outs, _ = self.model.forward_raw(None, random_point=self.random_point,
                                          concat=(self.points, self.pt_off, self.lens))
+        if self.postprocess:
+            return self.model.pts_bbox_head.postprocess_fixed(outs)
         return self.coder.decode_fixed(outs)
 
     def load(self, host_points):
