@@ -6,7 +6,7 @@
   python bench.py --impl reference      # CPU arm: the oracle port on the host cores
 
 One "step" = one pass of the hot path (voxelize -> sparse encoder -> dense CNN -> 2x FPS -> decoder
--> heads -> NMSFreeCoder top-k -> per-class NMS) over a batch of B synthetic 20k-point SUN-RGBD-shaped scenes
+-> heads -> NMSFreeCoder top-k; --postprocess adds the device-side per-class NMS) over a batch of B synthetic 20k-point SUN-RGBD-shaped scenes
 (BASELINE config 2: uni3detr_sunrgbd.py, 300 queries x 4 groups, 3 decoder layers, bf16).
 Scenes are sharded whole across ranks (weak scaling: B scenes per rank per step, no data-path
 collective); one all-reduce of the metrics vector ends the job.
@@ -258,13 +258,16 @@ def run_gpu(args):
 
     def eager_step(points):
         outs, _ = model.forward_raw(points, random_point=rp)
-        return model.pts_bbox_head.postprocess_fixed(outs)
+        if args.postprocess:      # + bottom-centre shift, per-class NMS, thresholds (the step after the path)
+            return model.pts_bbox_head.postprocess_fixed(outs)
+        return coder.decode_fixed(outs)
 
     graphed = None
     if not args.no_graph:
         # the public serving call: the whole forward captured once as a CUDA graph, replayed per batch
         from uni3detr_b200 import GraphedForward
-        graphed = GraphedForward(model, [p.shape[0] for p in host_pts], host_pts[0].shape[1], random_point=rp)
+        graphed = GraphedForward(model, [p.shape[0] for p in host_pts], host_pts[0].shape[1], random_point=rp,
+                                 postprocess=args.postprocess)
         graphed.load(host_batch)
 
     def step(points):
@@ -334,7 +337,8 @@ def run_gpu(args):
             "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": "uni3detr_sunrgbd.py synthetic 20k-pt scenes, 300 queries x4 groups, 3 decoder "
-                                   "layers, full forward (voxelize+sparse encoder+dense CNN+FPS+decoder+top-k+per-class NMS)",
+                                   "layers, full forward (voxelize+sparse encoder+dense CNN+FPS+decoder+top-k)"
+                                   + ("+per-class NMS" if args.postprocess else ""),
                        "scenes_per_step_per_gpu": B, "points_per_scene": 20000, "parallelism": f"scenes sharded x{world}",
                        "l2": "256 MiB flush write between timed steps (untimed)", "timing": "CUDA events per step, max over ranks",
                        "launch": "eager" if graphed is None else "CUDA graph replay (uni3detr_b200.GraphedForward)"},
@@ -357,6 +361,8 @@ def main():
     ap.add_argument("--cpu-scenes", type=int, default=2, help="bounded CPU-baseline sample (scenes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--postprocess", action="store_true",
+                    help="also run get_bboxes' device post-processing (per-class NMS) inside the step")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 20:

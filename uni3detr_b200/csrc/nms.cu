@@ -65,72 +65,127 @@ __device__ float rect_intersection(const float* a, const float* b) {
 }
 
 __device__ __forceinline__ float bev_iou(const float* a, const float* b) {
+  // bounding circles apart -> the rectangles cannot meet (exact: IoU is 0 either way)
+  const float dx = a[0] - b[0], dy = a[1] - b[1];
+  const float ra = 0.5f * sqrtf(a[3] * a[3] + a[4] * a[4]), rb = 0.5f * sqrtf(b[3] * b[3] + b[4] * b[4]);
+  if (dx * dx + dy * dy > (ra + rb) * (ra + rb)) return 0.f;
   const float sa = a[3] * a[4], sb = b[3] * b[4];
   const float so = rect_intersection(a, b);
   return so / fmaxf(sa + sb - so, 1e-8f);
 }
 
-// grid (col blocks, row blocks, scenes), 64 threads: thread i = row box, 64 column boxes in smem
+// grid (col blocks, row blocks, scenes), 64 threads: thread i = row box, 64 column boxes in smem.
+// Boxes are sorted by label, so a 64 x 64 block whose row and column label ranges do not meet has
+// nothing to do (with 10 classes ~90 % of the blocks): it writes zeros and leaves.
 __global__ void __launch_bounds__(64)
 k_nms_mask(const float* __restrict__ boxes, const int32_t* __restrict__ labels,
            const uint8_t* __restrict__ valid, int N, float thr, unsigned long long* __restrict__ mask) {
   const int cb = blockIdx.x, rb = blockIdx.y, s = blockIdx.z;
   if (cb < rb) return;  // strictly-lower blocks are never read
   const int nblk = (N + 63) >> 6;
-  __shared__ float s_box[64][7];
+  __shared__ float s_box[64][8];
   __shared__ int s_lab[64];
+  const int r = rb * 64 + threadIdx.x;
   const int c = cb * 64 + threadIdx.x;
-  if (c < N) {
-#pragma unroll
-    for (int j = 0; j < 7; ++j) s_box[threadIdx.x][j] = boxes[((size_t)s * N + c) * 7 + j];
-    s_lab[threadIdx.x] = valid[(size_t)s * N + c] ? labels[(size_t)s * N + c] : -1;
-  } else {
-    s_lab[threadIdx.x] = -1;
+  const int lab = (r < N && valid[(size_t)s * N + r]) ? labels[(size_t)s * N + r] : -2;
+  const int clab = (c < N && valid[(size_t)s * N + c]) ? labels[(size_t)s * N + c] : -1;
+  s_lab[threadIdx.x] = clab;
+  // label ranges of the block's rows / columns (valid entries only)
+  const int rmin = __reduce_min_sync(0xffffffffu, lab >= 0 ? lab : 0x7fffffff);
+  const int rmax = __reduce_max_sync(0xffffffffu, lab);
+  const int cmin = __reduce_min_sync(0xffffffffu, clab >= 0 ? clab : 0x7fffffff);
+  const int cmax = __reduce_max_sync(0xffffffffu, clab);
+  __shared__ int s_rng[2][4];
+  if ((threadIdx.x & 31) == 0) {
+    int* q = s_rng[threadIdx.x >> 5];
+    q[0] = rmin; q[1] = rmax; q[2] = cmin; q[3] = cmax;
   }
   __syncthreads();
-  const int r = rb * 64 + threadIdx.x;
-  if (r >= N) return;
+  const int Rmin = min(s_rng[0][0], s_rng[1][0]), Rmax = max(s_rng[0][1], s_rng[1][1]);
+  const int Cmin = min(s_rng[0][2], s_rng[1][2]), Cmax = max(s_rng[0][3], s_rng[1][3]);
+  const bool overlap = Rmax >= 0 && Cmax >= 0 && Rmin <= Cmax && Cmin <= Rmax;   // block-uniform
   unsigned long long bits = 0ull;
-  const int lab = valid[(size_t)s * N + r] ? labels[(size_t)s * N + r] : -2;
-  if (lab >= 0) {
-    float a[7];
+  if (overlap) {
+    if (c < N) {
 #pragma unroll
-    for (int j = 0; j < 7; ++j) a[j] = boxes[((size_t)s * N + r) * 7 + j];
-    const int j0 = (cb == rb) ? threadIdx.x + 1 : 0;
-    for (int j = j0; j < 64; ++j)
-      if (s_lab[j] == lab && bev_iou(a, s_box[j]) > thr) bits |= 1ull << j;
+      for (int j = 0; j < 7; ++j) s_box[threadIdx.x][j] = boxes[((size_t)s * N + c) * 7 + j];
+    }
+    __syncthreads();
+    if (lab >= 0) {
+      float a[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) a[j] = boxes[((size_t)s * N + r) * 7 + j];
+      const int j0 = (cb == rb) ? threadIdx.x + 1 : 0;
+      for (int j = j0; j < 64; ++j)
+        if (s_lab[j] == lab && bev_iou(a, s_box[j]) > thr) bits |= 1ull << j;
+    }
   }
-  mask[((size_t)s * N + r) * nblk + cb] = bits;
+  if (r < N) mask[((size_t)s * N + r) * nblk + cb] = bits;
 }
 
-// one warp per scene: greedy sweep in (label, score) order
+// one warp per scene, block-wise greedy sweep in (label, score) order: the 64 boxes of a block are
+// resolved serially against each other with register-only work on lane 0 (their 64 diagonal words are
+// loaded up front, off the serial chain); the kept boxes' rows are then OR-ed into the removed-bits
+// of the later blocks by all lanes in parallel.
 __global__ void __launch_bounds__(32)
 k_nms_sweep(const unsigned long long* __restrict__ mask, const uint8_t* __restrict__ valid, int N,
             uint8_t* __restrict__ keep) {
   const int s = blockIdx.x, lane = threadIdx.x;
   const int nblk = (N + 63) >> 6;
-  // removed-bits words: lane l owns words l, l+32, ... (N <= 64*32*kW)
-  constexpr int kW = 4;
+  constexpr int kW = 4;                 // lane l owns removed-bits words l, l+32, ... (N <= 8192)
   unsigned long long remv[kW];
 #pragma unroll
   for (int w = 0; w < kW; ++w) remv[w] = 0ull;
-  for (int i = 0; i < N; ++i) {
-    const int word = i >> 6;
+  __shared__ unsigned long long s_diag[64];
+  __shared__ unsigned long long s_kept;
+  for (int b = 0; b < nblk; ++b) {
+    const int i0 = b * 64;
+    // diagonal words of this block's rows + validity bits
+    unsigned long long vbits = 0ull;
+    for (int j = lane; j < 64; j += 32) {
+      const int i = i0 + j;
+      s_diag[j] = i < N ? mask[((size_t)s * N + i) * nblk + b] : 0ull;
+    }
+    const unsigned v0 = __ballot_sync(0xffffffffu, i0 + lane < N && valid[(size_t)s * N + i0 + lane]);
+    const unsigned v1 = __ballot_sync(0xffffffffu, i0 + 32 + lane < N && valid[(size_t)s * N + i0 + 32 + lane]);
+    vbits = (unsigned long long)v0 | ((unsigned long long)v1 << 32);
     unsigned long long rw = 0ull;
 #pragma unroll
     for (int w = 0; w < kW; ++w)
-      if ((word >> 5) == w) rw = remv[w];
-    rw = __shfl_sync(0xffffffffu, rw, word & 31);
-    const bool k = valid[(size_t)s * N + i] && !((rw >> (i & 63)) & 1ull);
-    if (lane == 0) keep[(size_t)s * N + i] = k ? 1 : 0;
-    if (k) {
-      const unsigned long long* row = mask + ((size_t)s * N + i) * nblk;
-#pragma unroll
-      for (int w = 0; w < kW; ++w) {
-        const int b = w * 32 + lane;
-        if (b < nblk && b >= word) remv[w] |= row[b];
+      if ((b >> 5) == w) rw = remv[w];
+    rw = __shfl_sync(0xffffffffu, rw, b & 31);
+    __syncwarp();
+    if (lane == 0) {
+      unsigned long long kept = 0ull;
+      for (int j = 0; j < 64; ++j) {
+        if (((vbits >> j) & 1ull) && !((rw >> j) & 1ull)) {
+          kept |= 1ull << j;
+          rw |= s_diag[j];
+        }
       }
+      s_kept = kept;
     }
+    __syncwarp();
+    const unsigned long long kept = s_kept;
+    for (int j = lane; j < 64; j += 32)
+      if (i0 + j < N) keep[(size_t)s * N + i0 + j] = (kept >> j) & 1ull;
+    // rows of the kept boxes -> removed bits of the later blocks: lane l loads the rows of boxes l
+    // and l+32 (independent, pipelined loads), one warp OR-reduction per later word
+    const bool k0 = (kept >> lane) & 1ull, k1 = (kept >> (lane + 32)) & 1ull;
+    const unsigned long long* row0 = mask + ((size_t)s * N + i0 + lane) * nblk;
+    const unsigned long long* row1 = mask + ((size_t)s * N + i0 + lane + 32) * nblk;
+    for (int wb = b + 1; wb < nblk; ++wb) {
+      unsigned long long v = 0ull;
+      if (k0) v |= row0[wb];
+      if (k1) v |= row1[wb];
+      const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v);
+      const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v >> 32));
+      const unsigned long long r = (unsigned long long)lo | ((unsigned long long)hi << 32);
+#pragma unroll
+      for (int w = 0; w < kW; ++w)
+        if ((wb >> 5) == w && (wb & 31) == lane) remv[w] |= r;
+    }
+    __syncwarp();
   }
 }
 
