@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="scenes per step per GPU")
+    ap.add_argument("--batch", type=int, default=32, help="scenes per step per GPU")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-scenes", type=int, default=2, help="bounded CPU-baseline sample (scenes)")

@@ -11,6 +11,6 @@ echo "smoke exit: $?" >> gpurun_out/smoke.log
 timeout 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "bench exit: $?" >> gpurun_out/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
-  --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+  --log-file gpurun_out/launches.csv python bench.py --no-graph --batch 8 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
 echo "ncu exit: $?" >> gpurun_out/bench_ncu.log
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log | tail -3; cat gpurun_out/bench.json | cut -c1-600
