@@ -163,3 +163,28 @@ def test_grid_size_matches_sparse_shape(model_cfgs):
         ss = list(mc["pts_middle_encoder"]["sparse_shape"])
         # SECOND-style configs declare sparse_shape one cell deeper in z than the voxel grid
         assert list(g[1:]) == ss[1:] and g[0] in (ss[0], ss[0] - 1), name
+
+
+def test_bench_reference_arm_emits_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): exactly one JSON line on
+    stdout with the contract's keys."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def test_rulebook_buffer_layout():
+    """Rulebook.alloc: row stride padded to whole 128-row tiles (the conv bulk-copies 512-byte rows)."""
+    from uni3detr_b200 import ops
+    r = ops.Rulebook.alloc(300, "cpu")
+    assert tuple(r.shape) == (27, 300) and r.stride(0) == 384 and r.stride(0) % 4 == 0
+    assert r.tile_mask.numel() == 3 and type(r[:, :5]) is torch.Tensor

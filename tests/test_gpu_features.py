@@ -367,3 +367,21 @@ def test_get_bboxes_nms_vs_oracle(golden):
             np.testing.assert_array_equal(gl.cpu().numpy(), rl)
             np.testing.assert_allclose(gs.cpu().numpy(), rs, rtol=1e-5, atol=1e-6)
             np.testing.assert_allclose(gb.cpu().numpy(), rb, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_add_layernorm(dtype, tol):
+    from uni3detr_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    a, b, c = (torch.randn(1000, 256, generator=g).to(dtype) for _ in range(3))
+    w, bias = (1 + 0.1 * torch.randn(256, generator=g)).to(dtype), (0.1 * torch.randn(256, generator=g)).to(dtype)
+    for res, relu in [((None, None), False), ((b, None), False), ((b, c), False), ((None, None), True)]:
+        x = a.float()
+        for t in res:
+            if t is not None:
+                x = x + t.float()
+        ref = F.layer_norm(x, (256,), w.float(), bias.float(), 1e-5)
+        ref = F.relu(ref) if relu else ref
+        out = ops.add_layernorm(a.to(DEV), None if res[0] is None else res[0].to(DEV),
+                                None if res[1] is None else res[1].to(DEV), w.to(DEV), bias.to(DEV), 1e-5, relu)
+        assert relerr(out, ref) < tol

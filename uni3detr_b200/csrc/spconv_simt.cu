@@ -5,9 +5,9 @@
 // SparseBasicBlock identity add), called for every layer of
 // projects/mmdet3d_plugin/models/pts_encoder/sparse_encoder_hd.py:106-133.
 //
-// This kernel is (a) the fp32 parity path (BASELINE config 3 tolerance 1e-3) and (b) the
-// path for the K-starved layers (Cin in {4,5,16}) that are HBM-bound anyway. Layers with
-// Cin>=32 in bf16 go to the tcgen05 kernel in spconv_tc.cu.
+// This kernel is the fp32 parity path (BASELINE config 3 tolerance 1e-3; also bf16 shapes the
+// tensor-core kernel does not take). In bf16 every encoder layer - the stem included, its
+// reduction dim zero-padded to 16 - runs on the tcgen05 kernel in spconv_tc.cu.
 //
 // Tile: 64 output rows x BN output channels per CTA, 256 threads, each thread owns a
 // 4 x (BN/16) micro-tile. Offsets whose 64-row slice of the rulebook is empty are skipped.
