@@ -36,17 +36,29 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into libu3d_b200.so (nvcc cross-compiles on CPU)."""
+    """Compile every CUDA source for sm_100a into libu3d_b200.so (nvcc cross-compiles on CPU).
+    Serialised across processes (one rank per GPU may import at the same time): the first one
+    builds into a temporary file and renames it, the others find a fresh library."""
     if not force and not _stale():
         return _SO
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + \
-        [os.path.join(_CSRC, s) for s in _SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    import fcntl
+    with open(_SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return _SO
+            nvcc = os.environ.get("NVCC", "nvcc")
+            tmp = _SO + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+                [os.path.join(_CSRC, s) for s in _SOURCES]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, _SO)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 

@@ -45,7 +45,7 @@ constexpr int kSliceWarp = 5;          // warp 5: rulebook-slice loader
 constexpr int kProdWarp0 = 6;          // warps 6-13: producers
 constexpr int kNumProd = 8;            // producer warps with one CTA per SM (4 with two)
 constexpr int kThreads = (kProdWarp0 + kNumProd) * 32;   // 448
-constexpr int kSliceBufs = 3;
+constexpr int kSliceBufs = 2;
 constexpr int kMaxK = 27;
 constexpr int kMaxStages = 16;
 
