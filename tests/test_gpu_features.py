@@ -47,6 +47,27 @@ def oracle_conv(x, nbr, w, n_out, scale, shift, residual, relu):
     return F.relu(y) if relu else y
 
 
+TC_KERNELS = ("0", "1")   # U3D_TC_KERNEL: 0 = rows-on-N (spconv_tn.cu) where it applies, 1 = rows-on-M (spconv_tc.cu)
+
+
+class tc_kernel:
+    """Select the tcgen05 sparse-conv kernel variant for the calls inside the block."""
+    def __init__(self, which):
+        self.which = which
+
+    def __enter__(self):
+        import os
+        self.prev = os.environ.get("U3D_TC_KERNEL")
+        os.environ["U3D_TC_KERNEL"] = self.which
+
+    def __exit__(self, *a):
+        import os
+        if self.prev is None:
+            os.environ.pop("U3D_TC_KERNEL", None)
+        else:
+            os.environ["U3D_TC_KERNEL"] = self.prev
+
+
 CONV_SHAPES = [(4, 16), (5, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (128, 128)]
 
 
@@ -75,10 +96,13 @@ def test_spconv_subm(cin, cout, dtype, tol):
             assert relerr(y, ref) < tol, (impl, residual is not None, relu, relerr(y, ref))
         if dtype == torch.bfloat16 and ops.spconv_tc_supported(27, cin, cout):     # tcgen05 kernel
             wp = ops.spconv_pack_weights(w.reshape(27, cin, cout).to(DEV, dtype).contiguous())
-            y = ops.spconv_fwd_packed(x.to(DEV, dtype), nbr, n_rows, n, wp, 27, cin, cout, scale.to(DEV),
-                                      shift.to(DEV), residual=None if residual is None else residual.to(DEV, dtype),
-                                      relu=relu)
-            assert relerr(y, ref) < tol, ("tc", residual is not None, relu, relerr(y, ref))
+            for kern in TC_KERNELS:
+                with tc_kernel(kern):
+                    y = ops.spconv_fwd_packed(x.to(DEV, dtype), nbr, n_rows, n, wp, 27, cin, cout, scale.to(DEV),
+                                              shift.to(DEV),
+                                              residual=None if residual is None else residual.to(DEV, dtype),
+                                              relu=relu)
+                assert relerr(y, ref) < tol, ("tc", kern, residual is not None, relu, relerr(y, ref))
 
 
 @pytest.mark.parametrize("cin,cout", [(16, 32), (32, 64), (64, 128)])
@@ -102,9 +126,11 @@ def test_spconv_down(cin, cout, dtype, tol):
         assert relerr(y[:m], ref) < tol, (impl, relerr(y[:m], ref))
     if dtype == torch.bfloat16:
         wp = ops.spconv_pack_weights(w.reshape(27, cin, cout).to(DEV, dtype).contiguous())
-        y = ops.spconv_fwd_packed(x.to(DEV, dtype), nbr, n_out, ocap, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV),
-                                  relu=True)
-        assert relerr(y[:m], ref) < tol, ("tc", relerr(y[:m], ref))
+        for kern in TC_KERNELS:
+            with tc_kernel(kern):
+                y = ops.spconv_fwd_packed(x.to(DEV, dtype), nbr, n_out, ocap, wp, 27, cin, cout, scale.to(DEV),
+                                          shift.to(DEV), relu=True)
+            assert relerr(y[:m], ref) < tol, ("tc", kern, relerr(y[:m], ref))
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
@@ -291,9 +317,12 @@ def test_decode_fixed_equals_decode(golden):
         assert bool((labels[i][mask[i]] == r["labels"]).all())
 
 
-@pytest.mark.parametrize("cin,cout,n", [(256, 256, 700), (256, 512, 300), (128, 256, 129), (64, 64, 1), (16, 16, 128)])
-def test_spconv_tc_wide_and_ragged(cin, cout, n):
-    """tcgen05 kernel: Cin blocks > 1, Cout = 512 (two UMMA N halves), partial last tile, live count < capacity."""
+@pytest.mark.parametrize("kern", TC_KERNELS)
+@pytest.mark.parametrize("cin,cout,n", [(256, 256, 700), (256, 512, 300), (128, 256, 129), (64, 64, 1), (16, 16, 128),
+                                        (128, 64, 257), (256, 128, 385), (32, 16, 255), (64, 32, 513)])
+def test_spconv_tc_wide_and_ragged(cin, cout, n, kern):
+    """tcgen05 kernels: Cin blocks > 1, Cout = 512 (two UMMA N halves), Cout < Cin, partial last tile (128- and
+    256-row tiles), live count < capacity."""
     from uni3detr_b200 import ops
     dims, B, cap = (6, 12, 12), 1, n + 77
     coors, x, w, scale, shift = conv_case(n, dims, B, cin, cout, n)
@@ -305,10 +334,36 @@ def test_spconv_tc_wide_and_ragged(cin, cout, n):
     wp = ops.spconv_pack_weights(w.reshape(27, cin, cout).to(DEV, torch.bfloat16).contiguous())
     xin = torch.cat([x, torch.full((cap - n, cin), float("nan"))]).to(DEV, torch.bfloat16)
     out = torch.full((cap, cout), -5.0, device=DEV, dtype=torch.bfloat16)
-    ops.spconv_fwd_packed(xin, nbr, n_rows, cap, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV), relu=False, out=out)
+    with tc_kernel(kern):
+        ops.spconv_fwd_packed(xin, nbr, n_rows, cap, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV), relu=False,
+                              out=out)
     ref = oracle_conv(x, G.subm_rulebook(coors, dims), w, n, scale, shift, None, False)
     assert relerr(out[:n], ref) < 1e-2, relerr(out[:n], ref)
     assert bool((out[n:] == -5.0).all())
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 32), (64, 64), (128, 128)])
+def test_spconv_tc_many_tiles_per_cta(cin, cout):
+    """Persistent loop: more 256-row tiles than SMs (every CTA runs several tiles, both accumulator
+    buffers, ring wrap-around, rulebook-slice double buffer), residual + ReLU; the two tcgen05 kernels
+    must agree with the fp32-accumulate SIMT kernel on the same bf16 operands."""
+    from uni3detr_b200 import ops
+    dims, B, n = (24, 64, 64), 2, 100_000
+    coors, x, w, scale, shift = conv_case(n, dims, B, cin, cout, 11 + cin)
+    c = T(coors).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, n, B, dims)
+    nbr = ops.rulebook_subm(c, n_rows, n, vm)
+    xb = x.to(DEV, torch.bfloat16)
+    wb = w.reshape(27, cin, cout).to(DEV, torch.bfloat16).contiguous()
+    res = torch.randn(n, cout, generator=torch.Generator().manual_seed(2)).to(DEV, torch.bfloat16)
+    ref = ops.spconv_fwd(xb, nbr, n_rows, n, wb, scale.to(DEV), shift.to(DEV), residual=res, relu=True, impl=1)
+    wp = ops.spconv_pack_weights(wb)
+    for kern in TC_KERNELS:
+        with tc_kernel(kern):
+            y = ops.spconv_fwd_packed(xb, nbr, n_rows, n, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV),
+                                      residual=res, relu=True)
+        assert relerr(y, ref) < 1e-2, (kern, relerr(y, ref))
 
 
 def _random_boxes(n, n_cls, seed):

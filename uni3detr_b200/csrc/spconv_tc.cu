@@ -360,6 +360,14 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
                   const float* scale, const float* shift, const void* residual, int relu, void* out,
                   int Cin, int Cout, cudaStream_t st) {
   using namespace tc;
+  // Cout <= 128 with a rulebook: the rows-on-N kernel (spconv_tn.cu) - full-size MMAs, half the
+  // weight traffic. U3D_TC_KERNEL=1 forces this rows-on-M kernel (A/B timing, tests).
+  {
+    const char* e = getenv("U3D_TC_KERNEL");
+    if (!(e && atoi(e) == 1) && spconv_tn_supported(Cin, Cout, nbr))
+      return spconv_fwd_tn(in, nbr, nbr_stride, tile_mask, n_out, out_cap, K, wpk, scale, shift, residual,
+                           relu, out, Cin, Cout, st);
+  }
   U3D_CHECK_ARG(K >= 1 && K <= kMaxK, "spconv tc: K=%d unsupported", K);
   U3D_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)wpk | (uintptr_t)residual) & 15) == 0,
                 "spconv tc: buffers must be 16-byte aligned");

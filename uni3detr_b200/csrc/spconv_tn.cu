@@ -1,0 +1,366 @@
+// K3 (tensor-core flavour, rows-on-N variant) — the sparse-conv gather-GEMM with the operand roles
+// swapped: D^T[Cout, rows] = W_k^T[Cout, Cin] x X_k^T[Cin, rows].
+//
+// Why: a tcgen05.mma with both operands in shared memory costs about as long as reading its A
+// operand (128 rows x 32 B at ~32 B/clk = ~128 cycles) no matter how small N is, so the
+// rows-on-M kernel of spconv_tc.cu (M = 128 rows, N = Cout <= 128) pays a full-size instruction
+// for a quarter (Cout = 64) or less of its work. Here the WEIGHT tile is the A operand (M = 128
+// lanes, of which the first Cout hold channels) and 256 gathered rows are the B operand
+// (N = 256): every instruction carries 128 x 256 x 16 MACs, and a weight tile is fetched once
+// per 256 rows instead of once per 128.
+//
+// Reference semantics as spconv_tc.cu: SURVEY.md A.3/A.4 (spconv indice_conv + BatchNorm1d(eval)
+// + ReLU, SparseBasicBlock identity add), projects/mmdet3d_plugin/models/pts_encoder/
+// sparse_encoder_hd.py:106-132.
+//
+// Persistent, warp-specialised, one CTA per SM, 256-row output tiles:
+//   warps 0-7    epilogue: TMEM lane = output channel, TMEM column = row of the tile. Warp w reads
+//                lane quarter w%4 (hardware rule) of column half w/4 with tcgen05.ld 32x32b.x32,
+//                applies scale/shift (per-lane constants), pairs adjacent channels by one
+//                shuffle so that a lane stores bf16x2, adds the residual, ReLU, stores (64
+//                contiguous bytes per row per warp). Residuals are prefetched one chunk ahead.
+//   warp 8       MMA issue (one thread), accumulators double-buffered in TMEM (2 x 256 columns).
+//   warp 9       rulebook-slice loader (cp.async.bulk of the active 1 KB rulebook rows).
+//   warps 10-17  producers: two warps per stage (128 rows each), 16-byte cp.async gathers with
+//                zero fill into the K-major swizzled B tile, published with
+//                cp.async.mbarrier.arrive.noinc; the first warp of the pair also bulk-copies the
+//                stage's weight images (the packed format of u3d_spconv_pack_weights, unchanged).
+// For Cout < 128 the MMA still runs M = 128: lanes >= Cout multiply whatever bytes follow the
+// weight image inside the same stage (its own B tile) and are never read back.
+#include <stdlib.h>
+#include "tc_common.cuh"
+
+namespace u3d {
+
+namespace tn {
+
+using namespace tc;
+
+constexpr int kTile = 256;             // rows per tile = UMMA N
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kMmaWarp = 8;
+constexpr int kSliceWarp = 9;
+constexpr int kProdWarp0 = 10;
+constexpr int kNumProd = 8;            // 4 pairs
+constexpr int kThreads = (kProdWarp0 + kNumProd) * 32;   // 576
+constexpr int kSliceBufs = 2;
+constexpr int kMaxK = 27;
+constexpr int kMaxStages = 4;      // one ring slot per producer warp pair
+
+struct Smem {
+  uint64_t full[kMaxStages];    // 64 cp.async arrives (the stage's two warps) + 1 arrive.expect_tx
+  uint64_t empty[kMaxStages];   // tcgen05.commit: the MMAs that read the stage have retired
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint64_t slice_full[kSliceBufs];
+  uint64_t slice_empty[kSliceBufs];
+  uint32_t tmem_base;
+  alignas(128) int nbr[kSliceBufs][kMaxK][kTile];
+};
+
+__device__ __forceinline__ uint32_t mask_of_tile(const uint32_t* __restrict__ tile_mask, int tile,
+                                                 int n_tiles128, uint32_t all_mask) {
+  if (!tile_mask) return all_mask;
+  uint32_t m = __ldg(&tile_mask[2 * tile]);
+  if (2 * tile + 1 < n_tiles128) m |= __ldg(&tile_mask[2 * tile + 1]);
+  return m & all_mask;
+}
+
+template <int CIN_BLK>
+__global__ void __launch_bounds__(kThreads, 1)
+k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
+            const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ n_out_p, int K,
+            const __nv_bfloat16* __restrict__ wpk, const float* __restrict__ scale,
+            const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
+            __nv_bfloat16* __restrict__ out, int Cin, int Cout, int stages) {
+  using SW = Swz<CIN_BLK>;
+  constexpr int kChunks = CIN_BLK / 8;            // 16-byte chunks per gathered row
+  constexpr int kRowsPerPass = 32 / kChunks;      // rows one warp-wide cp.async covers
+  constexpr int kPasses = 128 / kRowsPerPass;     // copies per lane per unit (a warp fills 128 rows)
+  constexpr int kG = 64 / CIN_BLK;                // (offset, Cin-block) units per stage: K = 64
+  constexpr int kUnitX = kTile * SW::P;           // one 256-row feature sub-tile
+  constexpr int kXBytes = kG * kUnitX;            // 32 KB for every CIN_BLK
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr uint32_t kHeader = (uint32_t)((sizeof(Smem) + 1023) & ~(size_t)1023);
+
+  const int n_out = *n_out_p;
+  const int n_tiles = (n_out + kTile - 1) / kTile;
+  const int n_tiles128 = (n_out + 127) / 128;
+  if ((int)blockIdx.x >= n_tiles) return;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = Cin / CIN_BLK;
+  const uint32_t w_bytes = (uint32_t)Cout * SW::P;                        // one weight image
+  const uint32_t w_unit = (w_bytes + 1023u) & ~1023u;                      // 1024-aligned images
+  const uint32_t w_region = kG * w_unit;
+  const uint32_t stage_bytes = w_region + kXBytes;
+  const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;                   // 1024-aligned
+  const uint32_t all_mask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&S.full[s], 64 + 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.acc_full[b], 1);
+      mbar_init(&S.acc_empty[b], kEpiThreads);
+    }
+    for (int b = 0; b < kSliceBufs; ++b) {
+      mbar_init(&S.slice_full[b], 1);
+      mbar_init(&S.slice_empty[b], kNumProd);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&S.tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp >= kProdWarp0) {
+    // ======================= producers: a warp pair per stage =======================
+    const int w = warp - kProdWarp0;
+    const int pair = w >> 1, half = w & 1;
+    const int chunk = lane % kChunks;
+    const int rsub = lane / kChunks;
+    const uint32_t off_even = SW::offset(rsub, chunk);
+    const uint32_t off_odd = SW::offset(rsub + kRowsPerPass, chunk) - (uint32_t)(kRowsPerPass * SW::P);
+    const uint64_t row_bytes = (uint64_t)Cin * 2;
+    // pair p OWNS ring slot p (stages <= 4 pairs): it fills the global stages g = p, p + stages, ...
+    // so it meets the generations of its slot in order and the 1-bit mbarrier parity is never
+    // ambiguous; with a 3-slot ring the fourth pair only passes through the slices
+    int g = pair < stages ? pair : 0x7fffffff;
+    int g0 = 0;          // global index of the first stage of the current tile
+    int t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int buf = t % kSliceBufs;
+      const int m0 = tile * kTile;
+      const uint32_t mask = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
+      const int n_units = __popc(mask) * nkb;
+      const int n_st = (n_units + kG - 1) / kG;
+      const int rows_live = n_out - m0 - half * 128;   // rulebook entries of rows >= n_out are uninitialised
+      mbar_wait(&S.slice_full[buf], (uint32_t)(t / kSliceBufs) & 1u);
+      for (; g < g0 + n_st; g += stages) {
+        const int slot = pair;
+        const uint32_t gen = (uint32_t)(g / stages);
+        const int u0 = (g - g0) * kG;
+        const int cnt = n_units - u0 < kG ? n_units - u0 : kG;
+        mbar_wait(&S.empty[slot], (gen & 1u) ^ 1u);
+        const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
+        if (half == 0 && lane == 0) mbar_expect_tx(&S.full[slot], (uint32_t)cnt * w_bytes);
+#pragma unroll
+        for (int j = 0; j < kG; ++j) {
+          if (j < cnt) {
+            const int u = u0 + j;
+            const int ki = u / nkb, kb = u - ki * nkb;
+            const int k = __fns(mask, 0, ki + 1);            // position of the ki-th set bit
+            if (half == 0 && lane == 0)
+              bulk_g2s(st_s + (uint32_t)j * w_unit,
+                       (const uint8_t*)wpk + ((size_t)k * nkb + kb) * w_bytes, w_bytes, &S.full[slot]);
+            const uint8_t* src_base =
+                reinterpret_cast<const uint8_t*>(in) + (size_t)(kb * CIN_BLK + chunk * 8) * 2;
+            const int* nb = &S.nbr[buf][k][half * 128 + rsub];
+            const uint32_t x_u = st_s + w_region + (uint32_t)(j * kUnitX) + (uint32_t)(half * 128 * SW::P);
+#pragma unroll
+            for (int i = 0; i < kPasses; ++i) {
+              const int src_row = nb[i * kRowsPerPass];
+              const bool ok = src_row >= 0 && i * kRowsPerPass + rsub < rows_live;
+              const uint8_t* src = src_base + (ok ? (uint64_t)(uint32_t)src_row * row_bytes : 0ull);
+              cp_async16(x_u + ((i & 1) ? off_odd : off_even) + (uint32_t)(i * kRowsPerPass * SW::P), src,
+                         ok ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_arrive(&S.full[slot]);
+      }
+      g0 += n_st;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.slice_empty[buf]);
+    }
+  } else if (warp == kSliceWarp) {
+    // ======================= rulebook-slice loader (one thread) =======================
+    if (lane == 0) {
+      int t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const int buf = t % kSliceBufs;
+        mbar_wait(&S.slice_empty[buf], (((uint32_t)(t / kSliceBufs)) & 1u) ^ 1u);
+        uint32_t m = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
+        int ents = nbr_stride - tile * kTile;     // the last tile of a row may hold 128 entries only
+        if (ents > kTile) ents = kTile;
+        const uint32_t bytes = (uint32_t)ents * 4u;
+        mbar_expect_tx(&S.slice_full[buf], (uint32_t)__popc(m) * bytes);
+        while (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1;
+          bulk_g2s(smem_u32(&S.nbr[buf][k][0]), nbr + (size_t)k * nbr_stride + (size_t)tile * kTile, bytes,
+                   &S.slice_full[buf]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ======================= MMA issuer (one thread) =======================
+    if (lane == 0) {
+      // kind::f16: D = f32, A = B = bf16, both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      int g = 0, t = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const int ab = t & 1;
+        const uint32_t mask = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
+        const int n_units = __popc(mask) * nkb;
+        const int n_st = (n_units + kG - 1) / kG;
+        mbar_wait(&S.acc_empty[ab], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)(ab * kTile);
+        for (int st = 0; st < n_st; ++st, ++g) {
+          const int slot = g % stages;
+          const int cnt = n_units - st * kG < kG ? n_units - st * kG : kG;
+          mbar_wait(&S.full[slot], (uint32_t)(g / stages) & 1u);
+          tc_fence_after();
+          const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
+#pragma unroll
+          for (int j = 0; j < kG; ++j) {
+            if (j < cnt) {
+              const uint64_t w_desc = SW::desc(st_s + (uint32_t)j * w_unit);
+              const uint64_t x_desc = SW::desc(st_s + w_region + (uint32_t)(j * kUnitX));
+#pragma unroll
+              for (int kk = 0; kk < CIN_BLK / 16; ++kk)
+                umma_bf16(d_tmem, w_desc + (uint64_t)(kk * 2), x_desc + (uint64_t)(kk * 2), idesc,
+                          (st > 0 || j > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&S.empty[slot]);
+        }
+        umma_commit(&S.acc_full[ab]);
+      }
+      tc_fence_before();
+    }
+  } else {
+    // ======================= epilogue: TMEM -> registers -> global =======================
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int h = warp >> 2;           // column (= row of the tile) half
+    const int c = q * 32 + lane;       // output channel of this lane
+    const bool warp_live = q * 32 < Cout;
+    const bool lane_live = c < Cout;
+    const bool odd = lane & 1;
+    const int cb = c & ~1;             // channel pair this lane stores
+    const float sc = (lane_live && scale) ? __ldg(&scale[c]) : 1.f;
+    const float sh = (lane_live && shift) ? __ldg(&shift[c]) : 0.f;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int ab = t & 1;
+      const int row0 = tile * kTile + h * 128 + (odd ? 1 : 0);   // + col + 2p
+      uint32_t res[16];
+      auto load_res = [&](int col) {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+          const int o = row0 + col + 2 * p;
+          res[p] = (residual && lane_live && o < n_out)
+                       ? __ldg(reinterpret_cast<const uint32_t*>(residual + (size_t)o * Cout + cb))
+                       : 0u;
+        }
+      };
+      if (warp_live) load_res(0);
+      mbar_wait(&S.acc_full[ab], (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      if (warp_live) {
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * kTile + h * 128);
+#pragma unroll 1
+        for (int col = 0; col < 128; col += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + (uint32_t)col, v);   // warp-collective
+          tmem_ld_wait();
+          uint32_t cur[16];
+#pragma unroll
+          for (int p = 0; p < 16; ++p) cur[p] = res[p];
+          if (col + 32 < 128) load_res(col + 32);     // prefetch the next chunk's residuals
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const float fe = __uint_as_float(v[2 * p]) * sc + sh;        // row col+2p
+            const float fo = __uint_as_float(v[2 * p + 1]) * sc + sh;    // row col+2p+1
+            const float recv = __shfl_xor_sync(0xffffffffu, odd ? fe : fo, 1);
+            float lo = odd ? recv : fe;     // channel cb
+            float hi = odd ? fo : recv;     // channel cb+1
+            const int o = row0 + col + 2 * p;
+            if (lane_live && o < n_out) {
+              const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cur[p]));
+              lo += r.x;
+              hi += r.y;
+              if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+              *reinterpret_cast<__nv_bfloat162*>(out + (size_t)o * Cout + cb) = __floats2bfloat162_rn(lo, hi);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&S.acc_empty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace tn
+
+bool spconv_tn_supported(int Cin, int Cout, const int32_t* nbr) {
+  if (nbr == nullptr) return false;                       // pointwise convs stay on the rows-on-M kernel
+  if (Cout > 128 || (Cout & 1)) return false;             // one M = 128 accumulator
+  return spconv_tc_supported(Cin, Cout, U3D_BF16);
+}
+
+int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint32_t* tile_mask,
+                  const int32_t* n_out, int out_cap, int K, const void* wpk, const float* scale,
+                  const float* shift, const void* residual, int relu, void* out, int Cin, int Cout,
+                  cudaStream_t st) {
+  using namespace tn;
+  U3D_CHECK_ARG(K >= 1 && K <= kMaxK, "spconv tn: K=%d unsupported", K);
+  U3D_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)wpk | (uintptr_t)residual) & 15) == 0,
+                "spconv tn: buffers must be 16-byte aligned");
+  const int tiles = cdiv(out_cap, kTile);
+  if (tiles < 1) return U3D_OK;
+  U3D_CHECK_ARG((((uintptr_t)nbr) & 15) == 0 && nbr_stride % 4 == 0 && nbr_stride >= 128 * cdiv(out_cap, 128),
+                "spconv tn: the rulebook must be 16-byte aligned with a row stride that is a multiple of 4 "
+                "and >= 128*ceil(out_cap/128) (stride=%d, out_cap=%d)", nbr_stride, out_cap);
+  const int blk = Cin % 64 == 0 ? 64 : Cin;
+  const uint32_t P = 2 * blk;
+  const uint32_t kg = 64 / blk;
+  const uint32_t w_unit = ((uint32_t)Cout * P + 1023u) & ~1023u;
+  const uint32_t stage_bytes = kg * w_unit + kg * kTile * P;
+  const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
+  int stages = (int)((227u * 1024u - header) / stage_bytes);
+  if (const char* e = getenv("U3D_TN_STAGES")) stages = atoi(e);
+  if (stages > kMaxStages) stages = kMaxStages;
+  U3D_CHECK_ARG(stages >= 2, "spconv tn: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
+  const size_t smem = header + (size_t)stages * stage_bytes;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+
+#define U3D_TN_LAUNCH(BLK)                                                                          \
+  do {                                                                                              \
+    static int cur_smem = 0;                                                                        \
+    U3D_CUDA(ensure_dynamic_smem(k_spconv_tn<BLK>, smem, &cur_smem));                               \
+    k_spconv_tn<BLK><<<grid, kThreads, smem, st>>>(                                                 \
+        (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, n_out, K, (const __nv_bfloat16*)wpk,  \
+        scale, shift, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages); \
+  } while (0)
+  if (blk == 64) U3D_TN_LAUNCH(64);
+  else if (blk == 32) U3D_TN_LAUNCH(32);
+  else U3D_TN_LAUNCH(16);
+#undef U3D_TN_LAUNCH
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+}  // namespace u3d
