@@ -20,7 +20,7 @@ cut -c1-400 gpurun_out/bench.json
 if [ "$rc" == "0" ]; then
   U3D_TC_KERNEL=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_rows_on_m.json 2> gpurun_out/bench_rows_on_m.err
   cut -c1-300 gpurun_out/bench_rows_on_m.json
-  timeout 400 ncu --set full --clock-control none -k regex:k_spconv_tn -c 21 -o gpurun_out/ncu_spconv_tn \
+  timeout 400 ncu --set full --clock-control none -k regex:k_spconv_tn -c 18 -o gpurun_out/ncu_spconv_tn \
     python bench.py --no-graph --batch 32 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_tn.log 2>&1
   echo "ncu full exit: $?" >> gpurun_out/ncu_tn.log
 fi

@@ -7,7 +7,7 @@
 // The rulebook is kept output-stationary: nbr[k][o] = input row feeding output row o
 // through kernel offset k (or -1). That is the form the gather-GEMM consumes without
 // atomics; u3d_rulebook_pairs converts it to spconv-1.x pair lists for API parity.
-// All lookups go through the VoxelMap (one 8-byte load + popcount each), output
+// All lookups go through the VoxelMap (an 8-byte load + popcount, shared by x-neighbours), output
 // coordinates of a strided conv come out in ascending linear index for free.
 // Integer/HBM-bound: reads 16 B/row coords, writes 4 B per (row, offset).
 #include "common.cuh"
@@ -16,66 +16,105 @@ namespace u3d {
 
 struct Dims3 { int d[3]; };  // z,y,x
 
+// One thread per OUTPUT row: the coordinate row is loaded once, the 27 lookups run out of
+// registers (the three kx neighbours of a (kz,ky) line usually share one 8-byte map word, so a
+// row costs ~9-12 map loads instead of 27), each k-plane of the table is written coalesced, and
+// the warp's 27-bit "which offsets feed these rows" mask costs ONE atomicOr per warp.
 __global__ void __launch_bounds__(256)
 k_nbr_build(const int32_t* __restrict__ out_coors, const int32_t* __restrict__ n_out_p,
             const uint2* __restrict__ in_map, const int32_t* __restrict__ in_perm, Dims3 in_dims,
             Dims3 stride, Dims3 pad, int32_t* __restrict__ nbr, int nbr_stride,
             uint32_t* __restrict__ tile_mask) {
   const int n_out = *n_out_p;
-  const int k = blockIdx.y;
-  const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
   const int D = in_dims.d[0], H = in_dims.d[1], W = in_dims.d[2];
-  // uniform trip count: whole warps stay converged for the ballot behind the tile masks
+  // uniform trip count: whole warps stay converged for the reduction behind the tile masks
   const int per_round = gridDim.x * blockDim.x;
   const int nrounds = (n_out + per_round - 1) / per_round;
   for (int r = 0; r < nrounds; ++r) {
     const int o = r * per_round + blockIdx.x * blockDim.x + threadIdx.x;
-    int row = -1;
+    uint32_t rowmask = 0u;
     if (o < n_out) {
-      int4 c = __ldg(reinterpret_cast<const int4*>(out_coors) + o);  // b,z,y,x
-      int z = c.y * stride.d[0] - pad.d[0] + kz;
-      int y = c.z * stride.d[1] - pad.d[1] + ky;
-      int x = c.w * stride.d[2] - pad.d[2] + kx;
-      if (z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W) {
-        uint32_t lin = (uint32_t)((((size_t)c.x * D + z) * H + y) * W + x);
-        row = map_lookup(in_map, in_perm, lin);
+      const int4 c = __ldg(reinterpret_cast<const int4*>(out_coors) + o);  // b,z,y,x
+      const int z0 = c.y * stride.d[0] - pad.d[0];
+      const int y0 = c.z * stride.d[1] - pad.d[1];
+      const int x0 = c.w * stride.d[2] - pad.d[2];
+      int32_t* dst = nbr + o;
+#pragma unroll
+      for (int kz = 0; kz < 3; ++kz) {
+        const int z = z0 + kz;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int y = y0 + ky;
+          const bool line_ok = z >= 0 && z < D && y >= 0 && y < H;
+          const uint32_t lin0 = line_ok ? (uint32_t)((((size_t)c.x * D + z) * H + y) * W) : 0u;
+          uint32_t cached = 0xffffffffu;
+          uint2 w = make_uint2(0u, 0u);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int k = (kz * 3 + ky) * 3 + kx;
+            const int x = x0 + kx;
+            int row = -1;
+            if (line_ok && x >= 0 && x < W) {
+              const uint32_t lin = lin0 + (uint32_t)x;
+              const uint32_t wi = lin >> 5, bit = lin & 31u;
+              if (wi != cached) { w = __ldg(&in_map[wi]); cached = wi; }
+              if ((w.x >> bit) & 1u) {
+                const int rank = (int)w.y + __popc(w.x & ((1u << bit) - 1u));
+                row = in_perm ? __ldg(&in_perm[rank]) : rank;
+              }
+            }
+            dst[(size_t)k * nbr_stride] = row;
+            rowmask |= (row >= 0 ? 1u : 0u) << k;
+          }
+        }
       }
-      nbr[(size_t)k * nbr_stride + o] = row;
     }
     // bit k of tile_mask[t] = "offset k feeds at least one of output rows [128t, 128t+128)";
-    // a warp covers 32 consecutive rows of one tile, so one atomicOr per warp at most
-    const unsigned any = __ballot_sync(0xffffffffu, row >= 0);
-    if (tile_mask && any && (threadIdx.x & 31) == 0) atomicOr(&tile_mask[o >> 7], 1u << k);
+    // a warp covers 32 consecutive rows of one tile
+    const uint32_t m = __reduce_or_sync(0xffffffffu, rowmask);
+    if (tile_mask && m && (threadIdx.x & 31) == 0) atomicOr(&tile_mask[o >> 7], m);
   }
 }
 
-// every (input row, offset) marks its candidate output cell
+// every input row marks its candidate output cells: per axis only the offsets k with
+// (c + pad - k) divisible by the stride qualify (at most 2 of 3 for stride 2), so a row issues
+// <= 8 atomicOr instead of testing 27 combinations.
 __global__ void __launch_bounds__(256)
 k_down_mark(const int32_t* __restrict__ in_coors, const int32_t* __restrict__ n_in_p,
             Dims3 out_dims, Dims3 stride, Dims3 pad, uint2* __restrict__ out_map) {
   const int n_in = *n_in_p;
-  const int k = blockIdx.y;
-  const int kz = k / 9, ky = (k / 3) % 3, kx = k % 3;
   const int D = out_dims.d[0], H = out_dims.d[1], W = out_dims.d[2];
-  const int per_round = gridDim.x * blockDim.x;
-  const int nrounds = (n_in + per_round - 1) / per_round;
-  for (int r = 0; r < nrounds; ++r) {
-    int i = r * per_round + blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = false;
-    uint32_t lin = 0xffffffffu;
-    if (i < n_in) {
-      int4 c = __ldg(reinterpret_cast<const int4*>(in_coors) + i);
-      int z = c.y + pad.d[0] - kz, y = c.z + pad.d[1] - ky, x = c.w + pad.d[2] - kx;
-      if (z >= 0 && y >= 0 && x >= 0 && z % stride.d[0] == 0 && y % stride.d[1] == 0 &&
-          x % stride.d[2] == 0) {
-        z /= stride.d[0]; y /= stride.d[1]; x /= stride.d[2];
-        if (z < D && y < H && x < W) {
-          valid = true;
-          lin = (uint32_t)((((size_t)c.x * D + z) * H + y) * W + x);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(in_coors) + i);
+    int oz[3], oy[3], ox[3];   // output coordinate per kernel offset, or -1
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int z = c.y + pad.d[0] - k, y = c.z + pad.d[1] - k, x = c.w + pad.d[2] - k;
+      oz[k] = (z >= 0 && z % stride.d[0] == 0 && z / stride.d[0] < D) ? z / stride.d[0] : -1;
+      oy[k] = (y >= 0 && y % stride.d[1] == 0 && y / stride.d[1] < H) ? y / stride.d[1] : -1;
+      ox[k] = (x >= 0 && x % stride.d[2] == 0 && x / stride.d[2] < W) ? x / stride.d[2] : -1;
+    }
+#pragma unroll
+    for (int kz = 0; kz < 3; ++kz) {
+      if (oz[kz] < 0) continue;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        if (oy[ky] < 0) continue;
+        const uint32_t line = (uint32_t)((((size_t)c.x * D + oz[kz]) * H + oy[ky]) * W);
+        // the (up to 3) x candidates of one line fall into one or two map words: merge them
+        uint32_t w0 = 0xffffffffu, b0 = 0u, w1 = 0xffffffffu, b1 = 0u;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          if (ox[kx] < 0) continue;
+          const uint32_t lin = line + (uint32_t)ox[kx];
+          const uint32_t wi = lin >> 5, bit = 1u << (lin & 31u);
+          if (w0 == 0xffffffffu || w0 == wi) { w0 = wi; b0 |= bit; }
+          else { w1 = wi; b1 |= bit; }
         }
+        if (b0) atomicOr(&out_map[w0].x, b0);
+        if (b1) atomicOr(&out_map[w1].x, b1);
       }
     }
-    map_set_bit_aggregated(out_map, valid, lin);
   }
 }
 
@@ -210,7 +249,7 @@ extern "C" int u3d_rulebook_subm(const int32_t* coors, const int32_t* n_rows, in
   U3D_CHECK_ARG(u3d_voxmap_words(B, D, H, W) != 0, "u3d_rulebook_subm: bad grid");
   Dims3 dims{{D, H, W}}, one{{1, 1, 1}};
   if (tile_mask) U3D_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)cdiv(cap > 0 ? cap : 1, 128) * 4, st));
-  dim3 grid(grid_x_for(cap, 256, kNumSMs * 2), 27);
+  const int grid = grid_x_for(cap, 256, kNumSMs * 8);
   k_nbr_build<<<grid, 256, 0, st>>>(coors, n_rows, (const uint2*)map, perm, dims, one, one, nbr,
                                     nbr_stride, tile_mask);
   U3D_LAUNCH_CHECK();
@@ -240,7 +279,7 @@ extern "C" int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, i
   U3D_CHECK_ARG(words != 0, "u3d_rulebook_down: bad out grid");
   uint2* out_map = (uint2*)out_map_;
   U3D_CUDA(cudaMemsetAsync(out_map, 0, words * sizeof(uint2), st));
-  dim3 gmark(grid_x_for(in_cap, 256, kNumSMs * 2), 27);
+  const int gmark = grid_x_for(in_cap, 256, kNumSMs * 8);
   k_down_mark<<<gmark, 256, 0, st>>>(in_coors, n_in, od, s, p, out_map);
   U3D_LAUNCH_CHECK();
   int rc = voxmap_scan(out_map, words, scan_scratch, n_out, st);
@@ -249,7 +288,7 @@ extern "C" int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, i
       out_map, words, od.d[0], od.d[1], od.d[2], out_coors, out_cap);
   U3D_LAUNCH_CHECK();
   if (tile_mask) U3D_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)cdiv(out_cap > 0 ? out_cap : 1, 128) * 4, st));
-  dim3 gn(grid_x_for(out_cap, 256, kNumSMs * 2), 27);
+  const int gn = grid_x_for(out_cap, 256, kNumSMs * 8);
   k_nbr_build<<<gn, 256, 0, st>>>(out_coors, n_out, (const uint2*)in_map, in_perm, id, s, p, nbr,
                                   nbr_stride, tile_mask);
   U3D_LAUNCH_CHECK();

@@ -128,55 +128,75 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
 
   if (warp >= kProdWarp0) {
     // ======================= producers: a warp pair per stage =======================
+    // Lane (rsub, chunk) copies the 16-byte chunk `chunk` of the tile rows rsub*kPasses + i,
+    // i = 0..kPasses-1, of its half: the kPasses rulebook entries it needs are CONTIGUOUS, so they
+    // come in with kPasses/4 independent 16-byte shared loads issued before the first cp.async
+    // (a load per pass, as in the first version of this loop, serialises LDS -> address -> LDGSTS
+    // behind the asm memory clobbers: ~45 cycles per pass instead of ~8).
     const int w = warp - kProdWarp0;
     const int pair = w >> 1, half = w & 1;
     const int chunk = lane % kChunks;
     const int rsub = lane / kChunks;
-    const uint32_t off_even = SW::offset(rsub, chunk);
-    const uint32_t off_odd = SW::offset(rsub + kRowsPerPass, chunk) - (uint32_t)(kRowsPerPass * SW::P);
+    const int rbase = half * 128 + rsub * kPasses;      // first tile row of this lane
+    const uint32_t chunk16 = (uint32_t)chunk * 16u;
+    const uint32_t lane_off = (uint32_t)(rbase * SW::P);
     const uint64_t row_bytes = (uint64_t)Cin * 2;
+    const int nkb_log2 = __ffs(nkb) - 1;                // Cin / CIN_BLK is a power of two
     // pair p OWNS ring slot p (stages <= 4 pairs): it fills the global stages g = p, p + stages, ...
     // so it meets the generations of its slot in order and the 1-bit mbarrier parity is never
     // ambiguous; with a 3-slot ring the fourth pair only passes through the slices
+    const int slot = pair;
     int g = pair < stages ? pair : 0x7fffffff;
+    uint32_t eph = 1u;   // parity to wait for on empty[slot]; flips on every visit
     int g0 = 0;          // global index of the first stage of the current tile
     int t = 0;
+    const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int buf = t % kSliceBufs;
       const int m0 = tile * kTile;
       const uint32_t mask = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
       const int n_units = __popc(mask) * nkb;
       const int n_st = (n_units + kG - 1) / kG;
-      const int rows_live = n_out - m0 - half * 128;   // rulebook entries of rows >= n_out are uninitialised
+      const int rows_live = n_out - m0 - rbase;   // rulebook entries of rows >= n_out are uninitialised
+      // rank of this lane's bit among the set bits of the mask: "position of the r-th set bit" is
+      // then one ballot away
+      const bool my_bit = (mask >> lane) & 1u;
+      const int my_rank = __popc(mask & ((1u << lane) - 1u));
       mbar_wait(&S.slice_full[buf], (uint32_t)(t / kSliceBufs) & 1u);
       for (; g < g0 + n_st; g += stages) {
-        const int slot = pair;
-        const uint32_t gen = (uint32_t)(g / stages);
         const int u0 = (g - g0) * kG;
         const int cnt = n_units - u0 < kG ? n_units - u0 : kG;
-        mbar_wait(&S.empty[slot], (gen & 1u) ^ 1u);
-        const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
+        mbar_wait(&S.empty[slot], eph);
+        eph ^= 1u;
         if (half == 0 && lane == 0) mbar_expect_tx(&S.full[slot], (uint32_t)cnt * w_bytes);
 #pragma unroll
         for (int j = 0; j < kG; ++j) {
           if (j < cnt) {
             const int u = u0 + j;
-            const int ki = u / nkb, kb = u - ki * nkb;
-            const int k = __fns(mask, 0, ki + 1);            // position of the ki-th set bit
+            const int ki = u >> nkb_log2, kb = u & (nkb - 1);
+            const int k = __ffs(__ballot_sync(0xffffffffu, my_bit && my_rank == ki)) - 1;
             if (half == 0 && lane == 0)
               bulk_g2s(st_s + (uint32_t)j * w_unit,
                        (const uint8_t*)wpk + ((size_t)k * nkb + kb) * w_bytes, w_bytes, &S.full[slot]);
             const uint8_t* src_base =
                 reinterpret_cast<const uint8_t*>(in) + (size_t)(kb * CIN_BLK + chunk * 8) * 2;
-            const int* nb = &S.nbr[buf][k][half * 128 + rsub];
-            const uint32_t x_u = st_s + w_region + (uint32_t)(j * kUnitX) + (uint32_t)(half * 128 * SW::P);
+            int idx[kPasses];
+            const int4* nb4 = reinterpret_cast<const int4*>(&S.nbr[buf][k][rbase]);
+#pragma unroll
+            for (int v = 0; v < kPasses / 4; ++v) {
+              const int4 q4 = nb4[v];
+              idx[4 * v] = q4.x; idx[4 * v + 1] = q4.y; idx[4 * v + 2] = q4.z; idx[4 * v + 3] = q4.w;
+            }
+            const uint32_t x_u = st_s + w_region + (uint32_t)(j * kUnitX) + lane_off;
 #pragma unroll
             for (int i = 0; i < kPasses; ++i) {
-              const int src_row = nb[i * kRowsPerPass];
-              const bool ok = src_row >= 0 && i * kRowsPerPass + rsub < rows_live;
-              const uint8_t* src = src_base + (ok ? (uint64_t)(uint32_t)src_row * row_bytes : 0ull);
-              cp_async16(x_u + ((i & 1) ? off_odd : off_even) + (uint32_t)(i * kRowsPerPass * SW::P), src,
-                         ok ? 16u : 0u);
+              // swizzle: 16-byte chunk index XOR address bits [7, 7+log2(P/16)); the row base of a
+              // lane is a multiple of 8 rows, so the XOR term depends on i only
+              constexpr uint32_t kSwzMask = SW::kMask;
+              const uint32_t sw = (((uint32_t)(i * SW::P)) >> 7) & kSwzMask;
+              const bool ok = idx[i] >= 0 && i < rows_live;
+              const uint8_t* src = src_base + (ok ? (uint64_t)(uint32_t)idx[i] * row_bytes : 0ull);
+              cp_async16(x_u + (uint32_t)(i * SW::P) + (chunk16 ^ (sw << 4)), src, ok ? 16u : 0u);
             }
           }
         }
@@ -192,7 +212,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       int t = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
         const int buf = t % kSliceBufs;
-        mbar_wait(&S.slice_empty[buf], (((uint32_t)(t / kSliceBufs)) & 1u) ^ 1u);
+        mbar_wait_relaxed(&S.slice_empty[buf], (((uint32_t)(t / kSliceBufs)) & 1u) ^ 1u, 2000u);
         uint32_t m = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
         int ents = nbr_stride - tile * kTile;     // the last tile of a row may hold 128 entries only
         if (ents > kTile) ents = kTile;
@@ -212,7 +232,8 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       // kind::f16: D = f32, A = B = bf16, both K-major, N = 256, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
-      int g = 0, t = 0;
+      int slot = 0, t = 0;
+      uint32_t fph = 0u;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
         const int ab = t & 1;
         const uint32_t mask = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
@@ -221,10 +242,9 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         mbar_wait(&S.acc_empty[ab], ((uint32_t)(t >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem + (uint32_t)(ab * kTile);
-        for (int st = 0; st < n_st; ++st, ++g) {
-          const int slot = g % stages;
+        for (int st = 0; st < n_st; ++st) {
           const int cnt = n_units - st * kG < kG ? n_units - st * kG : kG;
-          mbar_wait(&S.full[slot], (uint32_t)(g / stages) & 1u);
+          mbar_wait(&S.full[slot], fph);
           tc_fence_after();
           const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
 #pragma unroll
@@ -239,6 +259,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
             }
           }
           umma_commit(&S.empty[slot]);
+          if (++slot == stages) { slot = 0; fph ^= 1u; }
         }
         umma_commit(&S.acc_full[ab]);
       }
@@ -270,7 +291,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         }
       };
       if (warp_live) load_res(0);
-      mbar_wait(&S.acc_full[ab], (uint32_t)(t >> 1) & 1u);
+      mbar_wait_relaxed(&S.acc_full[ab], (uint32_t)(t >> 1) & 1u, 2000u);
       tc_fence_after();
       if (warp_live) {
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * kTile + h * 128);

@@ -33,6 +33,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// long waits (an epilogue warp waiting for a whole tile of MMAs): let the hardware suspend the
+// thread for up to `ns` nanoseconds per probe instead of polling the barrier at issue rate
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP_R:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_R;\n\t"
+      "bra WAIT_LOOP_R;\n\t"
+      "DONE_R:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(ns)
+      : "memory");
+}
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
