@@ -229,6 +229,18 @@ int u3d_coors_to_float(const int32_t* coors, int rows, float* out, void* stream)
 int u3d_sine_embed(const float* ref, int rows, void* out, int dtype, void* stream);
 
 /*
+ * Fused level merge of SECOND3DFPN: out = sum_i act_i(x_i + bias_i), i < 3, one pass over NDHWC rows.
+ * Replaces the `ups[0] + ups[1] + ups[2]` sum of necks/second3d_fpn.py:125-126 together with the
+ * BatchNorm3d(eval) shift and ReLU of the ConvTranspose3d branches (:56-72), which then run without
+ * an epilogue of their own.
+ *   x0..x2, out: (rows, C) `dtype` (x1, x2 may be NULL); b0..b2: (C) f32 or NULL;
+ *   relu_mask bit i: apply ReLU to operand i after its bias. C a multiple of 8 (bf16) / 4 (f32).
+ */
+int u3d_bias_act_sum(const void* x0, const void* x1, const void* x2, const float* b0, const float* b1,
+                     const float* b2, int relu_mask, long long rows, int C, int dtype, void* out,
+                     void* stream);
+
+/*
  * Fused residual add + LayerNorm (+ReLU): out = act(LN(a (+b) (+c)) * gamma + beta), rows of C.
  * Replaces the `identity + x` adds and nn.LayerNorm launches of mmcv's BaseTransformerLayer
  * (operation_order self_attn/norm/cross_attn/norm/ffn/norm, config uni3detr_sunrgbd.py:76-100), the

@@ -440,3 +440,22 @@ def test_add_layernorm(dtype, tol):
         out = ops.add_layernorm(a.to(DEV), None if res[0] is None else res[0].to(DEV),
                                 None if res[1] is None else res[1].to(DEV), w.to(DEV), bias.to(DEV), 1e-5, relu)
         assert relerr(out, ref) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)])
+def test_bias_act_sum(dtype, tol):
+    """Fused SECOND3DFPN level merge: sum_i act_i(x_i + b_i) vs torch (fp32 math, one rounding)."""
+    from uni3detr_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    shape, C = (2, 3, 5, 7, 256), 256
+    xs = [torch.randn(shape, generator=g).to(dtype) for _ in range(3)]
+    bs = [None, torch.randn(C, generator=g), torch.randn(C, generator=g)]
+    relus = [False, True, True]
+    ref = torch.zeros(shape)
+    for x, b, r in zip(xs, bs, relus):
+        t = x.float() + (b if b is not None else 0.0)
+        ref = ref + (F.relu(t) if r else t)
+    y = ops.bias_act_sum([x.to(DEV) for x in xs], [None if b is None else b.to(DEV) for b in bs], relus)
+    assert relerr(y, ref) < tol
+    y1 = ops.bias_act_sum([xs[0].to(DEV)], [bs[1].to(DEV)], [True])          # single operand
+    assert relerr(y1, F.relu(xs[0].float() + bs[1])) < tol

@@ -92,6 +92,7 @@ SIGNATURES = {
     "u3d_coors_to_float": (_i32, [_vp, _i32, _vp, _vp]),
     "u3d_sine_embed": (_i32, [_vp, _i32, _vp, _i32, _vp]),
     "u3d_add_layernorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "u3d_bias_act_sum": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, ctypes.c_longlong, _i32, _i32, _vp, _vp]),
     "u3d_mha_core": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "u3d_nms3d_mask_words": (_sz, [_i32]),
     "u3d_nms3d_bev": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp]),

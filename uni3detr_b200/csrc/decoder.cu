@@ -324,6 +324,48 @@ k_add_layernorm(const T* __restrict__ a, const T* __restrict__ b, const T* __res
   }
 }
 
+// out = sum_i act_i(x_i + bias_i) over up to three (rows, C) operands, one pass: the level merge of
+// SECOND3DFPN (necks/second3d_fpn.py:125-126) with the folded-BN bias and ReLU of the two
+// ConvTranspose3d branches applied on the fly (the transposed convs run without an epilogue).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bias_act_sum(const T* __restrict__ x0, const T* __restrict__ x1, const T* __restrict__ x2,
+               const float* __restrict__ b0, const float* __restrict__ b1, const float* __restrict__ b2,
+               int relu_mask, long long nvec, int C, T* __restrict__ out) {
+  typedef Vec<T> V;
+  typedef typename V::type vec_t;
+  constexpr int VN = V::N;
+  const T* xs[3] = {x0, x1, x2};
+  const float* bs[3] = {b0, b1, b2};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)((i * VN) % C);
+    float acc[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (xs[j] == nullptr) continue;
+      float v[VN];
+      V::unpack(__ldg(reinterpret_cast<const vec_t*>(xs[j]) + i), v);
+      if (bs[j]) {
+#pragma unroll
+        for (int e = 0; e < VN; e += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bs[j] + ch + e));
+          v[e] += bb.x; v[e + 1] += bb.y; v[e + 2] += bb.z; v[e + 3] += bb.w;
+        }
+      }
+      if ((relu_mask >> j) & 1) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) v[e] = fmaxf(v[e], 0.f);
+      }
+#pragma unroll
+      for (int e = 0; e < VN; ++e) acc[e] += v[e];
+    }
+    reinterpret_cast<vec_t*>(out)[i] = V::pack(acc);
+  }
+}
+
 }  // namespace u3d
 
 using namespace u3d;
@@ -347,6 +389,32 @@ extern "C" int u3d_add_layernorm(const void* a, const void* b, const void* c, co
     k_add_layernorm<__nv_bfloat16><<<grid, 256, 0, st>>>(
         (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)c, (const __nv_bfloat16*)gamma,
         (const __nv_bfloat16*)beta, eps, rows, C, relu, (__nv_bfloat16*)out);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+extern "C" int u3d_bias_act_sum(const void* x0, const void* x1, const void* x2, const float* b0,
+                                const float* b1, const float* b2, int relu_mask, long long rows, int C,
+                                int dtype, void* out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  U3D_CHECK_ARG(x0 && out && rows >= 0 && C >= 1, "u3d_bias_act_sum: bad argument");
+  U3D_CHECK_ARG(dtype == U3D_F32 || dtype == U3D_BF16, "u3d_bias_act_sum: bad dtype");
+  const int vn = dtype == U3D_BF16 ? 8 : 4;
+  U3D_CHECK_ARG(C % vn == 0, "u3d_bias_act_sum: C=%d must be a multiple of %d", C, vn);
+  U3D_CHECK_ARG((((uintptr_t)x0 | (uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out | (uintptr_t)b0 |
+                  (uintptr_t)b1 | (uintptr_t)b2) & 15) == 0,
+                "u3d_bias_act_sum: buffers must be 16-byte aligned");
+  if (rows == 0) return U3D_OK;
+  const long long nvec = rows * C / vn;
+  long long g = (nvec + 255) / 256;
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  if (dtype == U3D_F32)
+    k_bias_act_sum<float><<<(int)g, 256, 0, st>>>((const float*)x0, (const float*)x1, (const float*)x2, b0, b1,
+                                                  b2, relu_mask, nvec, C, (float*)out);
+  else
+    k_bias_act_sum<__nv_bfloat16><<<(int)g, 256, 0, st>>>(
+        (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, (const __nv_bfloat16*)x2, b0, b1, b2, relu_mask,
+        nvec, C, (__nv_bfloat16*)out);
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }

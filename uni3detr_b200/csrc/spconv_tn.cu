@@ -14,19 +14,25 @@
 // sparse_encoder_hd.py:106-132.
 //
 // Persistent, warp-specialised, one CTA per SM, 256-row output tiles:
-//   warps 0-7    epilogue: TMEM lane = output channel, TMEM column = row of the tile. Warp w reads
-//                lane quarter w%4 (hardware rule) of column half w/4 with tcgen05.ld 32x32b.x32,
-//                applies scale/shift (per-lane constants), pairs adjacent channels by one
-//                shuffle so that a lane stores bf16x2, adds the residual, ReLU, stores (64
-//                contiguous bytes per row per warp). Residuals are prefetched one chunk ahead.
+//   warps 0-7    epilogue: TMEM lane = output channel, TMEM column = row of the tile. A warp may
+//                only read the lane quarter warp%4 (hardware rule), so for Cout < 128 the weight
+//                image is replicated every 32 / 64 A rows: every quarter then holds all channels and
+//                the eight warps split the 256 columns (32 / 64 / 128 each for Cout <= 32 / 64 / 128).
+//                tcgen05.ld 32x32b.x32, scale/shift (per-lane constants), adjacent channels paired
+//                by one shuffle so that a lane stores bf16x2, residual (prefetched one chunk ahead),
+//                ReLU, 64 contiguous bytes per row per warp.
 //   warp 8       MMA issue (one thread), accumulators double-buffered in TMEM (2 x 256 columns).
 //   warp 9       rulebook-slice loader (cp.async.bulk of the active 1 KB rulebook rows).
-//   warps 10-17  producers: two warps per stage (128 rows each), 16-byte cp.async gathers with
-//                zero fill into the K-major swizzled B tile, published with
-//                cp.async.mbarrier.arrive.noinc; the first warp of the pair also bulk-copies the
-//                stage's weight images (the packed format of u3d_spconv_pack_weights, unchanged).
-// For Cout < 128 the MMA still runs M = 128: lanes >= Cout multiply whatever bytes follow the
-// weight image inside the same stage (its own B tile) and are never read back.
+//   warps 10-15  producers: two warps per stage (128 rows each), three stages of 48 KB (16 KB weight
+//                images + 32 KB gathered rows). A lane owns a CONTIGUOUS run of tile rows, so its
+//                rulebook entries arrive with a few 16-byte shared loads up front, followed by
+//                back-to-back 16-byte cp.async gathers (zero fill for missing neighbours) into the
+//                K-major swizzled B tile, published with cp.async.mbarrier.arrive.noinc; the first
+//                warp of the pair also bulk-copies the stage's weight images (the packed format of
+//                u3d_spconv_pack_weights, unchanged) once per replica.
+// Measured (profiles/): first version (one rulebook load per pass, one weight copy) 0.47 ms on the
+// 64->64 layers at batch 32 vs 0.64 ms rows-on-M; batched rulebook loads 0.33 ms; the replicated
+// image removes the epilogue bound of the 16- and 32-channel layers.
 #include <stdlib.h>
 #include "tc_common.cuh"
 
@@ -42,11 +48,11 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = 8;
 constexpr int kSliceWarp = 9;
 constexpr int kProdWarp0 = 10;
-constexpr int kNumProd = 8;            // 4 pairs
-constexpr int kThreads = (kProdWarp0 + kNumProd) * 32;   // 576
+constexpr int kNumProd = 6;            // 3 pairs = 3 ring slots (a stage is always 48 KB)
+constexpr int kThreads = (kProdWarp0 + kNumProd) * 32;   // 512
 constexpr int kSliceBufs = 2;
 constexpr int kMaxK = 27;
-constexpr int kMaxStages = 4;      // one ring slot per producer warp pair
+constexpr int kMaxStages = 3;      // one ring slot per producer warp pair
 
 struct Smem {
   uint64_t full[kMaxStages];    // 64 cp.async arrives (the stage's two warps) + 1 arrive.expect_tx
@@ -92,9 +98,15 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkb = Cin / CIN_BLK;
-  const uint32_t w_bytes = (uint32_t)Cout * SW::P;                        // one weight image
-  const uint32_t w_unit = (w_bytes + 1023u) & ~1023u;                      // 1024-aligned images
-  const uint32_t w_region = kG * w_unit;
+  const uint32_t w_bytes = (uint32_t)Cout * SW::P;                        // one packed weight image
+  // The A tile always spans the 128 TMEM lanes. For Cout < 128 the image is REPLICATED (n_rep bulk
+  // copies of the same source) every rep_span rows, so every TMEM lane quarter holds a copy of the
+  // channels and all eight epilogue warps drain a tile (with one copy only the warps of the first
+  // quarter(s) can, and a 16/32-channel layer becomes epilogue-bound).
+  const int rep_span = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);           // rows between replicas
+  const int n_rep = 128 / rep_span;                                         // 4 / 2 / 1
+  constexpr uint32_t w_unit = 128u * SW::P;                                 // 4 / 8 / 16 KB
+  constexpr uint32_t w_region = kG * w_unit;                                // 16 KB for every CIN_BLK
   const uint32_t stage_bytes = w_region + kXBytes;
   const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;                   // 1024-aligned
   const uint32_t all_mask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
@@ -142,9 +154,9 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     const uint32_t lane_off = (uint32_t)(rbase * SW::P);
     const uint64_t row_bytes = (uint64_t)Cin * 2;
     const int nkb_log2 = __ffs(nkb) - 1;                // Cin / CIN_BLK is a power of two
-    // pair p OWNS ring slot p (stages <= 4 pairs): it fills the global stages g = p, p + stages, ...
-    // so it meets the generations of its slot in order and the 1-bit mbarrier parity is never
-    // ambiguous; with a 3-slot ring the fourth pair only passes through the slices
+    // pair p OWNS ring slot p: it fills the global stages g = p, p + stages, ... so it meets the
+    // generations of its slot in order and the 1-bit mbarrier parity is never ambiguous (a pair
+    // without a slot - ring shortened by U3D_TN_STAGES - only passes through the slices)
     const int slot = pair;
     int g = pair < stages ? pair : 0x7fffffff;
     uint32_t eph = 1u;   // parity to wait for on empty[slot]; flips on every visit
@@ -168,16 +180,19 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         const int cnt = n_units - u0 < kG ? n_units - u0 : kG;
         mbar_wait(&S.empty[slot], eph);
         eph ^= 1u;
-        if (half == 0 && lane == 0) mbar_expect_tx(&S.full[slot], (uint32_t)cnt * w_bytes);
+        if (half == 0 && lane == 0) mbar_expect_tx(&S.full[slot], (uint32_t)(cnt * n_rep) * w_bytes);
 #pragma unroll
         for (int j = 0; j < kG; ++j) {
           if (j < cnt) {
             const int u = u0 + j;
             const int ki = u >> nkb_log2, kb = u & (nkb - 1);
             const int k = __ffs(__ballot_sync(0xffffffffu, my_bit && my_rank == ki)) - 1;
-            if (half == 0 && lane == 0)
-              bulk_g2s(st_s + (uint32_t)j * w_unit,
-                       (const uint8_t*)wpk + ((size_t)k * nkb + kb) * w_bytes, w_bytes, &S.full[slot]);
+            if (half == 0 && lane == 0) {
+              const uint8_t* wsrc = (const uint8_t*)wpk + ((size_t)k * nkb + kb) * w_bytes;
+              for (int r = 0; r < n_rep; ++r)
+                bulk_g2s(st_s + (uint32_t)j * w_unit + (uint32_t)(r * rep_span * SW::P), wsrc, w_bytes,
+                         &S.full[slot]);
+            }
             const uint8_t* src_base =
                 reinterpret_cast<const uint8_t*>(in) + (size_t)(kb * CIN_BLK + chunk * 8) * 2;
             int idx[kPasses];
@@ -269,8 +284,10 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     // ======================= epilogue: TMEM -> registers -> global =======================
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int h = warp >> 2;           // column (= row of the tile) half
-    const int c = q * 32 + lane;       // output channel of this lane
-    const bool warp_live = q * 32 < Cout;
+    const int c = (q * 32 + lane) % rep_span;   // output channel of this lane
+    const int rho = (q * 32) / rep_span;        // which replica this quarter holds
+    const int ncol = 128 / n_rep;               // columns of the half this warp drains: 128 / 64 / 32
+    const int col_lo = h * 128 + rho * ncol;    // first column (tile row) of this warp
     const bool lane_live = c < Cout;
     const bool odd = lane & 1;
     const int cb = c & ~1;             // channel pair this lane stores
@@ -279,7 +296,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int ab = t & 1;
-      const int row0 = tile * kTile + h * 128 + (odd ? 1 : 0);   // + col + 2p
+      const int row0 = tile * kTile + col_lo + (odd ? 1 : 0);   // + col + 2p
       uint32_t res[16];
       auto load_res = [&](int col) {
 #pragma unroll
@@ -290,35 +307,33 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
                        : 0u;
         }
       };
-      if (warp_live) load_res(0);
+      load_res(0);
       mbar_wait_relaxed(&S.acc_full[ab], (uint32_t)(t >> 1) & 1u, 2000u);
       tc_fence_after();
-      if (warp_live) {
-        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * kTile + h * 128);
+      const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * kTile + col_lo);
 #pragma unroll 1
-        for (int col = 0; col < 128; col += 32) {
-          uint32_t v[32];
-          tmem_ld32(lane_base + (uint32_t)col, v);   // warp-collective
-          tmem_ld_wait();
-          uint32_t cur[16];
+      for (int col = 0; col < ncol; col += 32) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + (uint32_t)col, v);   // warp-collective
+        tmem_ld_wait();
+        uint32_t cur[16];
 #pragma unroll
-          for (int p = 0; p < 16; ++p) cur[p] = res[p];
-          if (col + 32 < 128) load_res(col + 32);     // prefetch the next chunk's residuals
+        for (int p = 0; p < 16; ++p) cur[p] = res[p];
+        if (col + 32 < ncol) load_res(col + 32);     // prefetch the next chunk's residuals
 #pragma unroll
-          for (int p = 0; p < 16; ++p) {
-            const float fe = __uint_as_float(v[2 * p]) * sc + sh;        // row col+2p
-            const float fo = __uint_as_float(v[2 * p + 1]) * sc + sh;    // row col+2p+1
-            const float recv = __shfl_xor_sync(0xffffffffu, odd ? fe : fo, 1);
-            float lo = odd ? recv : fe;     // channel cb
-            float hi = odd ? fo : recv;     // channel cb+1
-            const int o = row0 + col + 2 * p;
-            if (lane_live && o < n_out) {
-              const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cur[p]));
-              lo += r.x;
-              hi += r.y;
-              if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-              *reinterpret_cast<__nv_bfloat162*>(out + (size_t)o * Cout + cb) = __floats2bfloat162_rn(lo, hi);
-            }
+        for (int p = 0; p < 16; ++p) {
+          const float fe = __uint_as_float(v[2 * p]) * sc + sh;        // row col+2p
+          const float fo = __uint_as_float(v[2 * p + 1]) * sc + sh;    // row col+2p+1
+          const float recv = __shfl_xor_sync(0xffffffffu, odd ? fe : fo, 1);
+          float lo = odd ? recv : fe;     // channel cb
+          float hi = odd ? fo : recv;     // channel cb+1
+          const int o = row0 + col + 2 * p;
+          if (lane_live && o < n_out) {
+            const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cur[p]));
+            lo += r.x;
+            hi += r.y;
+            if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            *reinterpret_cast<__nv_bfloat162*>(out + (size_t)o * Cout + cb) = __floats2bfloat162_rn(lo, hi);
           }
         }
       }
@@ -358,8 +373,7 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint
   const int blk = Cin % 64 == 0 ? 64 : Cin;
   const uint32_t P = 2 * blk;
   const uint32_t kg = 64 / blk;
-  const uint32_t w_unit = ((uint32_t)Cout * P + 1023u) & ~1023u;
-  const uint32_t stage_bytes = kg * w_unit + kg * kTile * P;
+  const uint32_t stage_bytes = kg * 128u * P + kg * kTile * P;   // 16 KB weights (replicated) + 32 KB rows
   const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
   int stages = (int)((227u * 1024u - header) / stage_bytes);
   if (const char* e = getenv("U3D_TN_STAGES")) stages = atoi(e);

@@ -395,6 +395,33 @@ def add_layernorm(a, b, c, gamma, beta, eps, relu=False):
     return out
 
 
+@_timed(lambda r, xs, *a, **k: dict(bytes=(len(xs) + 1) * r.numel() * r.element_size()))
+def bias_act_sum(xs, biases, relus):
+    """out = sum_i act_i(xs[i] + biases[i]) for up to three same-shape (..., C) tensors (contiguous,
+    channels last); biases[i] is an f32 (C,) tensor or None, relus[i] a bool."""
+    lib = _lib.load()
+    assert 1 <= len(xs) <= 3 and len(biases) == len(xs) == len(relus)
+    x0 = xs[0]
+    _req(x0, None, "x0")
+    for t in xs[1:]:
+        _req(t, x0.dtype, "x")
+        assert t.shape == x0.shape
+    C = x0.shape[-1]
+    bs = []
+    for b in biases:
+        if b is not None:
+            _req(b, torch.float32, "bias")
+            assert b.numel() == C
+        bs.append(b)
+    xs = list(xs) + [None] * (3 - len(xs))
+    bs = bs + [None] * (3 - len(bs))
+    mask = sum(1 << i for i, r in enumerate(relus) if r)
+    out = torch.empty_like(x0)
+    _lib.check(lib.u3d_bias_act_sum(_p(xs[0]), _p(xs[1]), _p(xs[2]), _p(bs[0]), _p(bs[1]), _p(bs[2]), mask,
+                                    x0.numel() // C, C, _DT[x0.dtype], _p(out), _stream()))
+    return out
+
+
 @_timed(lambda r, q, k_, v, n_seq, seq_len, heads: dict(n_seq=n_seq, seq_len=seq_len, heads=heads,
                                                        esize=q.element_size()))
 def mha_core(q, k, v, n_seq, seq_len, heads):

@@ -14,6 +14,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .. import ops
 from ..compat import BACKBONES, NECKS
 
 
@@ -44,6 +45,7 @@ class _FoldedConv:
         self.transposed = transposed
         self.stride, self.padding = conv.stride, conv.padding
         self.b = b.to(dtype).contiguous()
+        self.b32 = b.float().contiguous()
         k = conv.kernel_size
         self.as2d = bool(as2d and k[0] == 1 and conv.stride[0] == 1 and conv.padding[0] == 0)
         if self.as2d:
@@ -57,6 +59,23 @@ class _FoldedConv:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 return self._run(x)
         return self._run(x)
+
+    def raw(self, x):
+        """Transposed conv WITHOUT its bias / ReLU epilogue (both are applied by the fused level merge,
+        ops.bias_act_sum): one cuDNN dgrad launch instead of dgrad + bias-add + clamp."""
+        assert self.transposed
+        if self.w.dtype == torch.float32:
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                return self._raw(x)
+        return self._raw(x)
+
+    def _raw(self, x):
+        if self.as2d:
+            B, C, D, H, W = x.shape
+            x2 = x.permute(0, 2, 1, 3, 4).reshape(B * D, C, H, W)
+            y = F.conv_transpose2d(x2, self.w, None, stride=self.stride[1:])
+            return y.reshape(B, D, y.shape[1], y.shape[2], y.shape[3]).permute(0, 2, 1, 3, 4)
+        return F.conv_transpose3d(x, self.w, None, stride=self.stride)
 
     def _run(self, x):
         # conv + bias + ReLU as ONE cuDNN fused op (torch.cudnn_convolution_relu) where it exists
@@ -230,13 +249,27 @@ class SECOND3DFPN(_PlanMixin, nn.Module):
         p = self._plan
         if p is None or p["dtype"] != self.compute_dtype or p["as2d"] != self.conv2d_trick:
             p = self.prepare()
-        ups = [d(xi.to(self.compute_dtype).contiguous(memory_format=torch.channels_last_3d))
-               for d, xi in zip(p["deblocks"], x)]
-        # sum in the tensors' own memory order (NDHWC): the add is then one vectorised kernel
-        out = ups[0].permute(0, 2, 3, 4, 1)
-        for u in ups[1:]:
-            out = out + u.permute(0, 2, 3, 4, 1)
-        out = out.permute(0, 4, 1, 2, 3)
+        xs = [xi.to(self.compute_dtype).contiguous(memory_format=torch.channels_last_3d) for xi in x]
+        if xs[0].is_cuda and len(xs) <= 3 and self.out_channels[0] % 8 == 0:
+            # level merge as ONE libu3d kernel over NDHWC rows: sum_i act_i(up_i + bias_i); the transposed
+            # convs run bare (cuDNN dgrad only), their folded-BN shift and ReLU happen in the merge
+            ups, biases, relus = [], [], []
+            for d, xi in zip(p["deblocks"], xs):
+                if d.transposed:
+                    ups.append(d.raw(xi).permute(0, 2, 3, 4, 1).contiguous())
+                    biases.append(d.b32)
+                    relus.append(True)
+                else:
+                    ups.append(d(xi).permute(0, 2, 3, 4, 1).contiguous())
+                    biases.append(None)
+                    relus.append(False)
+            out = ops.bias_act_sum(ups, biases, relus).permute(0, 4, 1, 2, 3)
+        else:
+            ups = [d(xi) for d, xi in zip(p["deblocks"], xs)]
+            out = ups[0].permute(0, 2, 3, 4, 1)
+            for u in ups[1:]:
+                out = out + u.permute(0, 2, 3, 4, 1)
+            out = out.permute(0, 4, 1, 2, 3)
         for conv in p["extra"]:
             out = conv(out)
         return out
