@@ -174,7 +174,10 @@ int u3d_spconv_fwd(const void* in, const int32_t* nbr, int nbr_stride, const int
  *   u3d_spconv_packed_bytes: size of the packed buffer, 0 if the shape is unsupported
  *     (supported: Cin in {16, 32, 64, 128, ... multiples of 64 up to 512}; Cout a power of two in
  *      [16, 512]; K <= 27)
- *   u3d_spconv_pack_weights: w (K,Cin,Cout) bf16 row-major -> packed
+ *   u3d_spconv_pack_weights: w (K,Cin,Cout) bf16 row-major -> packed: [K][Cin/blk] images of
+ *     (Cout x blk) for the rows-on-M kernel, followed (Cout < 128) by [K][Cin/blk] images of 128 rows
+ *     with the tile replicated every 32/64 rows for the rows-on-N kernel (spconv_tn.cu, taken for
+ *     Cout <= 128 with a rulebook: weights are the A operand, 256 gathered rows the N dimension)
  *   u3d_spconv_fwd_packed: in/out/residual bf16, 16-byte aligned; other arguments as u3d_spconv_fwd.
  *     nbr must be 16-byte aligned with nbr_stride a multiple of 4 and >= 128*ceil(out_cap/128)
  *     (whole 512-byte rulebook rows are bulk-copied into shared memory);

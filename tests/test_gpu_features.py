@@ -187,10 +187,12 @@ def test_sine_embed_golden(golden):
     np.testing.assert_allclose(out.cpu().numpy().reshape(golden["sine_out"].shape), golden["sine_out"], atol=2e-5)
 
 
+@pytest.mark.parametrize("qsplit", ["0", "1"])   # tcgen05 kernel: 0 = one CTA loops over the query blocks, 1 = CTA per block
 @pytest.mark.parametrize("seq_len,n_seq", [(300, 8), (900, 2), (5, 4), (64, 3), (129, 1)])
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
-def test_mha_core(seq_len, n_seq, dtype, tol):
+def test_mha_core(seq_len, n_seq, dtype, tol, qsplit, monkeypatch):
     from uni3detr_b200 import ops
+    monkeypatch.setenv("U3D_MHA_QSPLIT", qsplit)
     g = torch.Generator().manual_seed(seq_len)
     heads, E = 8, 256
     qk = torch.randn(n_seq * seq_len, 2 * E, generator=g).to(dtype)

@@ -4,7 +4,9 @@
 // every decoder layer (config uni3detr_sunrgbd.py:79-83): per (sequence, head),
 // seq_len in {300, 900} keys, head_dim 32.
 //
-// One CTA (128 threads) per (128-query block, head, sequence):
+// One CTA (128 threads) per (head, sequence); it stages all K rows and V^T ONCE and then loops over
+// the 128-query blocks of the sequence (U3D_MHA_QSPLIT=1: one CTA per query block as in the first
+// version, K / V^T staged once per block):
 //   Q block, all K rows and V^T live in shared memory in the UMMA K-major swizzled layouts
 //   (Q, K: 64-byte rows, SWIZZLE_64B; V^T and P: 64-key blocks of 128-byte rows, SWIZZLE_128B);
 //   per key block of <= 256 keys:
@@ -15,6 +17,7 @@
 //     online-softmax merge of O_blk into 32 fp32 registers per row
 //   out = O / l, one 64-byte bf16 row per thread.
 // TMEM: 256 columns per CTA, so two CTAs share an SM.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace u3d {
@@ -47,14 +50,14 @@ __host__ __device__ inline Layout make_layout(int keys_pad64) {
 __global__ void __launch_bounds__(kThreads)
 k_mha_tc(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
          const __nv_bfloat16* __restrict__ v, int ldq, int ldk, int ldv, int seq_len, int heads,
-         __nv_bfloat16* __restrict__ out) {
+         int qblocks_per_cta, __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int head = blockIdx.y, seq = blockIdx.z;
-  const int q0 = blockIdx.x * kQB;
+  const int qb_first = blockIdx.x * qblocks_per_cta;
   const size_t row0 = (size_t)seq * seq_len;
   const int keys_pad64 = (seq_len + 63) & ~63;
   const Layout L = make_layout(keys_pad64);
@@ -78,13 +81,6 @@ k_mha_tc(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ 
     for (int i = tid; i < n16; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  for (int e = tid; e < kQB * 4; e += kThreads) {          // Q block: 128 rows x 4 chunks
-    const int r = e >> 2, c = e & 3;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (q0 + r < seq_len)
-      val = __ldg(reinterpret_cast<const uint4*>(q + (row0 + q0 + r) * ldq + head * kHd + c * 8));
-    *reinterpret_cast<uint4*>(sm + L.q + SwQK::offset(r, c)) = val;
-  }
   for (int e = tid; e < seq_len * 4; e += kThreads) {      // K rows and V^T columns
     const int r = e >> 2, c = e & 3;
     const uint4 kv = __ldg(reinterpret_cast<const uint4*>(k + (row0 + r) * ldk + head * kHd + c * 8));
@@ -98,7 +94,6 @@ k_mha_tc(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ 
       *reinterpret_cast<__nv_bfloat16*>(sm + L.vt + blk * 4096 + SwP::offset(d, col >> 3) + (col & 7) * 2) = ve[j];
     }
   }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -106,18 +101,33 @@ k_mha_tc(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ 
   const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
   const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kQB >> 4) << 24);
   const float sl2 = 0.17677669529663687f * 1.4426950408889634f;   // 1/sqrt(32) * log2(e)
+  uint32_t phase = 0;
+
+  for (int qb = qb_first; qb < qb_first + qblocks_per_cta && qb * kQB < seq_len; ++qb) {
+  const int q0 = qb * kQB;
+  // Q block: 128 rows x 4 chunks (the MMAs that read the previous block's Q have completed: their
+  // commit was waited for before the last __syncthreads of the previous iteration)
+  for (int e = tid; e < kQB * 4; e += kThreads) {
+    const int r = e >> 2, c = e & 3;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (q0 + r < seq_len)
+      val = __ldg(reinterpret_cast<const uint4*>(q + (row0 + q0 + r) * ldq + head * kHd + c * 8));
+    *reinterpret_cast<uint4*>(sm + L.q + SwQK::offset(r, c)) = val;
+  }
+  fence_proxy_async();            // Q (and, first time, K / V^T) stores -> visible to the tensor core
+  __syncthreads();
 
   float o[kHd];
 #pragma unroll
   for (int d = 0; d < kHd; ++d) o[d] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;
-  uint32_t phase = 0;
 
   for (int kb0 = 0; kb0 < seq_len; kb0 += kKB) {
     const int nk = seq_len - kb0 < kKB ? seq_len - kb0 : kKB;
     const int nk16 = (nk + 15) & ~15;
     // ---- S = Q K^T
     if (tid == 0) {
+      tc_fence_after();
       const uint32_t idesc = idesc_base | ((uint32_t)(nk16 >> 3) << 17);
       const uint64_t a_desc = SwQK::desc(sm_u + L.q);
       const uint64_t b_desc = SwQK::desc(sm_u + L.k + (uint32_t)kb0 * 64);
@@ -205,6 +215,7 @@ k_mha_tc(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ 
 #pragma unroll
     for (int c = 0; c < 4; ++c) op[c] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
   }
+  }   // query-block loop
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -229,9 +240,15 @@ int mha_core_tc(const void* q, const void* k, const void* v, int ldq, int ldk, i
   const size_t smem = make_layout((seq_len + 63) & ~63).total + 1024;
   static int cur_smem = 0;
   U3D_CUDA(ensure_dynamic_smem(k_mha_tc, smem, &cur_smem));
-  dim3 grid(cdiv(seq_len, kQB), heads, n_seq);
+  // one CTA per (head, sequence) looping over the query blocks (K / V^T staged once), unless the
+  // launch would leave SMs idle (few sequences) or U3D_MHA_QSPLIT=1 asks for one CTA per query block
+  const int n_qb = cdiv(seq_len, kQB);
+  bool split = heads * n_seq < 2 * kNumSMs;
+  if (const char* e = getenv("U3D_MHA_QSPLIT")) split = atoi(e) != 0;
+  const int per_cta = split ? 1 : n_qb;
+  dim3 grid(cdiv(n_qb, per_cta), heads, n_seq);
   k_mha_tc<<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
-                                          (const __nv_bfloat16*)v, ldq, ldk, ldv, seq_len, heads,
+                                          (const __nv_bfloat16*)v, ldq, ldk, ldv, seq_len, heads, per_cta,
                                           (__nv_bfloat16*)out);
   U3D_LAUNCH_CHECK();
   return U3D_OK;

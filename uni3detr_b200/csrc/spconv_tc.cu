@@ -325,13 +325,18 @@ k_spconv_tc(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   }
 }
 
-// (K,Cin,Cout) row-major bf16 -> [K][Cin/CIN_BLK] images of (Cout x CIN_BLK), K-major, swizzled
+// (K,Cin,Cout) row-major bf16 -> [K][Cin/CIN_BLK] images of (Cout x CIN_BLK), K-major, swizzled;
+// for Cout < 128 a second set of 128-row images follows in which the tile is replicated every
+// 32 (Cout <= 32) / 64 rows (the A operand of the rows-on-N kernel, spconv_tn.cu; rows between a
+// tile and the next replica stay zero).
 template <int CIN_BLK>
 __global__ void __launch_bounds__(256)
 k_pack_w(const __nv_bfloat16* __restrict__ w, int K, int Cin, int Cout, __nv_bfloat16* __restrict__ out) {
   using SW = Swz<CIN_BLK>;
   const int nkb = Cin / CIN_BLK;
   const size_t total = (size_t)K * Cin * Cout;
+  const int rep_span = Cout <= 32 ? 32 : 64;
+  uint8_t* rep = reinterpret_cast<uint8_t*>(out) + total * 2;    // second image set (Cout < 128 only)
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total;
        e += (size_t)gridDim.x * blockDim.x) {
     const int n = (int)(e % Cout);
@@ -340,7 +345,13 @@ k_pack_w(const __nv_bfloat16* __restrict__ w, int K, int Cin, int Cout, __nv_bfl
     const int kb = c / CIN_BLK, cc = c % CIN_BLK;
     const size_t img = ((size_t)k * nkb + kb) * ((size_t)Cout * SW::P);
     const uint32_t off = SW::offset(n, cc / 8) + (uint32_t)(cc % 8) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + img + off) = w[e];
+    const __nv_bfloat16 val = w[e];
+    *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(out) + img + off) = val;
+    if (Cout < 128) {
+      const size_t img2 = ((size_t)k * nkb + kb) * ((size_t)128 * SW::P);
+      for (int row = n; row < 128; row += rep_span)
+        *reinterpret_cast<__nv_bfloat16*>(rep + img2 + SW::offset(row, cc / 8) + (uint32_t)(cc % 8) * 2) = val;
+    }
   }
 }
 
@@ -433,7 +444,8 @@ using namespace u3d;
 
 extern "C" size_t u3d_spconv_packed_bytes(int K, int Cin, int Cout) {
   if (!spconv_tc_supported(Cin, Cout, U3D_BF16) || K < 1) return 0;
-  return (size_t)K * Cin * Cout * sizeof(__nv_bfloat16);
+  // rows-on-M images (Cout rows each) + for Cout < 128 the replicated 128-row images of the rows-on-N kernel
+  return (size_t)K * Cin * ((size_t)Cout + (Cout < 128 ? 128 : 0)) * sizeof(__nv_bfloat16);
 }
 
 extern "C" int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, void* packed,
@@ -446,6 +458,8 @@ extern "C" int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, 
   int grid = (int)((total + 255) / 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   const int blk = tc::cin_blk_for(Cin);
+  if (Cout < 128)   // rows of the replicated images that no weight lands on (Cout = 16) must read as zero
+    U3D_CUDA(cudaMemsetAsync((uint8_t*)packed + total * 2, 0, (size_t)K * Cin * 128 * 2, st));
   if (blk == 64) tc::k_pack_w<64><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, K, Cin, Cout, (__nv_bfloat16*)packed);
   else if (blk == 32) tc::k_pack_w<32><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, K, Cin, Cout, (__nv_bfloat16*)packed);
   else tc::k_pack_w<16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, K, Cin, Cout, (__nv_bfloat16*)packed);

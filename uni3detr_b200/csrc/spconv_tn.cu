@@ -28,8 +28,8 @@
 //                rulebook entries arrive with a few 16-byte shared loads up front, followed by
 //                back-to-back 16-byte cp.async gathers (zero fill for missing neighbours) into the
 //                K-major swizzled B tile, published with cp.async.mbarrier.arrive.noinc; the first
-//                warp of the pair also bulk-copies the stage's weight images (the packed format of
-//                u3d_spconv_pack_weights, unchanged) once per replica.
+//                warp of the pair also bulk-copies the stage's 128-row weight images (second image
+//                set of u3d_spconv_pack_weights), one cp.async.bulk per (offset, Cin block).
 // Measured (profiles/): first version (one rulebook load per pass, one weight copy) 0.47 ms on the
 // 64->64 layers at batch 32 vs 0.64 ms rows-on-M; batched rulebook loads 0.33 ms; the replicated
 // image removes the epilogue bound of the 16- and 32-channel layers.
@@ -98,14 +98,16 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkb = Cin / CIN_BLK;
-  const uint32_t w_bytes = (uint32_t)Cout * SW::P;                        // one packed weight image
-  // The A tile always spans the 128 TMEM lanes. For Cout < 128 the image is REPLICATED (n_rep bulk
-  // copies of the same source) every rep_span rows, so every TMEM lane quarter holds a copy of the
-  // channels and all eight epilogue warps drain a tile (with one copy only the warps of the first
-  // quarter(s) can, and a 16/32-channel layer becomes epilogue-bound).
+  // The A tile always spans the 128 TMEM lanes. For Cout < 128 the packed weights carry a second
+  // set of images in which the (Cout x CIN_BLK) tile is REPLICATED every rep_span rows (written by
+  // u3d_spconv_pack_weights), so every TMEM lane quarter holds a copy of the channels and all eight
+  // epilogue warps drain a tile (with one copy only the warps of the first quarter(s) can, and a
+  // 16/32-channel layer becomes epilogue-bound). One bulk copy per (offset, Cin block) either way.
   const int rep_span = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);           // rows between replicas
   const int n_rep = 128 / rep_span;                                         // 4 / 2 / 1
   constexpr uint32_t w_unit = 128u * SW::P;                                 // 4 / 8 / 16 KB
+  const uint8_t* wimg = reinterpret_cast<const uint8_t*>(wpk) +
+                        (Cout < 128 ? (size_t)K * Cin * Cout * 2 : (size_t)0);   // 128-row images
   constexpr uint32_t w_region = kG * w_unit;                                // 16 KB for every CIN_BLK
   const uint32_t stage_bytes = w_region + kXBytes;
   const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;                   // 1024-aligned
@@ -180,19 +182,16 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         const int cnt = n_units - u0 < kG ? n_units - u0 : kG;
         mbar_wait(&S.empty[slot], eph);
         eph ^= 1u;
-        if (half == 0 && lane == 0) mbar_expect_tx(&S.full[slot], (uint32_t)(cnt * n_rep) * w_bytes);
+        if (half == 0 && lane == 0) mbar_expect_tx(&S.full[slot], (uint32_t)cnt * w_unit);
 #pragma unroll
         for (int j = 0; j < kG; ++j) {
           if (j < cnt) {
             const int u = u0 + j;
             const int ki = u >> nkb_log2, kb = u & (nkb - 1);
             const int k = __ffs(__ballot_sync(0xffffffffu, my_bit && my_rank == ki)) - 1;
-            if (half == 0 && lane == 0) {
-              const uint8_t* wsrc = (const uint8_t*)wpk + ((size_t)k * nkb + kb) * w_bytes;
-              for (int r = 0; r < n_rep; ++r)
-                bulk_g2s(st_s + (uint32_t)j * w_unit + (uint32_t)(r * rep_span * SW::P), wsrc, w_bytes,
-                         &S.full[slot]);
-            }
+            if (half == 0 && lane == 0)
+              bulk_g2s(st_s + (uint32_t)j * w_unit, wimg + ((size_t)k * nkb + kb) * w_unit, w_unit,
+                       &S.full[slot]);
             const uint8_t* src_base =
                 reinterpret_cast<const uint8_t*>(in) + (size_t)(kb * CIN_BLK + chunk * 8) * 2;
             int idx[kPasses];
