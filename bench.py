@@ -216,7 +216,10 @@ def roofline_pass(step_fn, peaks, reps=3):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(top["kernel"], {}).get("dram_bytes_per_launch")
+            tj = json.load(f).get(top["kernel"], {})
+        traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("tensor_pipe_active_pct") is not None:   # same committed ncu capture
+            roof["tensor_pipe_active_pct_ncu"] = tj["tensor_pipe_active_pct"]
     roof.update({"traffic": traffic, "kernel": top["kernel"], "avg_launch_ms": top["avg_launch_ms"],
                  "algorithmic_bytes_per_launch": top["bytes_per_launch"],
                  "algorithmic_flops_per_launch": top["flops_per_launch"],
@@ -326,7 +329,10 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     # ---- rank 0 only: roofline of the dominant libu3d kernel + CPU baseline
-    roof, kernels, ours_ms = roofline_pass(lambda: eager_step(dev_pts), peaks)
+    if args.no_roofline:      # profiler runs: skip the per-op timing pass (it launches profile-only kernels)
+        roof, kernels, ours_ms = None, [], None
+    else:
+        roof, kernels, ours_ms = roofline_pass(lambda: eager_step(dev_pts), peaks)
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -360,6 +366,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-scenes", type=int, default=2, help="bounded CPU-baseline sample (scenes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-op roofline pass (ncu runs)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--postprocess", action="store_true",
                     help="also run get_bboxes' device post-processing (per-class NMS) inside the step")

@@ -151,6 +151,23 @@ k_to_dense(const T* __restrict__ feats, const int32_t* __restrict__ coors,
   }
 }
 
+// NDHWC with 16-byte aligned rows: one 16-byte vector per thread (a row is C*sizeof(T)/16 of them)
+__global__ void __launch_bounds__(256)
+k_to_dense_ndhwc_vec(const uint4* __restrict__ feats, const int32_t* __restrict__ coors,
+                     const int32_t* __restrict__ n_rows_p, int D, int H, int W, int vec_per_row,
+                     uint4* __restrict__ out) {
+  const int n = *n_rows_p;
+  const long long total = (long long)n * vec_per_row;
+  const long long spatial = (long long)D * H * W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / vec_per_row), v = (int)(e - (long long)r * vec_per_row);
+    const int4 q = __ldg(reinterpret_cast<const int4*>(coors) + r);
+    const long long cell = ((long long)q.y * H + q.z) * W + q.w;
+    out[((long long)q.x * spatial + cell) * vec_per_row + v] = __ldg(&feats[e]);
+  }
+}
+
 }  // namespace u3d
 
 using namespace u3d;
@@ -186,7 +203,16 @@ extern "C" int u3d_sparse_to_dense(const void* feats, const int32_t* coors, cons
   int grid = (int)((total + 255) / 256);
   if (grid < 1) grid = 1;
   if (grid > kNumSMs * 16) grid = kNumSMs * 16;
-  if (dtype == U3D_F32)
+  const size_t row_bytes = (size_t)C * dtype_size(dtype);
+  if (channels_last && row_bytes % 16 == 0 && (((uintptr_t)feats | (uintptr_t)out) & 15) == 0) {
+    const int vec_per_row = (int)(row_bytes / 16);
+    long long tv = (long long)cap * vec_per_row;
+    int gv = (int)((tv + 255) / 256);
+    if (gv < 1) gv = 1;
+    if (gv > kNumSMs * 16) gv = kNumSMs * 16;
+    k_to_dense_ndhwc_vec<<<gv, 256, 0, st>>>((const uint4*)feats, coors, n_rows, D, H, W, vec_per_row,
+                                             (uint4*)out);
+  } else if (dtype == U3D_F32)
     k_to_dense<float><<<grid, 256, 0, st>>>((const float*)feats, coors, n_rows, D, H, W, C,
                                             channels_last, (float*)out);
   else
