@@ -140,6 +140,23 @@ int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, int in_cap,
                       uint32_t* tile_mask /* ceil(out_cap/128) words or NULL */, void* stream);
 
 /*
+ * Tile scheduling for u3d_spconv_fwd_packed (no counterpart in the reference: spconv multiplies pair
+ * lists; this library multiplies whole 256-row tiles per active kernel offset): bucket the output rows
+ * by a 12-bit signature of their neighbour mask so that the rows of a tile share their active offsets.
+ *   nbr (K, nbr_stride): natural-order table from u3d_rulebook_subm / _down; n_out DEVICE int32
+ *   scratch: u3d_tile_sort_scratch_ints(cap) int32
+ *   slot_row (out, >= 256*ceil(cap/256) ints): output row computed in slot s (permutation of [0,n_out))
+ *   nbr_sorted (out, (K, sorted_stride), sorted_stride >= 256*ceil(cap/256), multiple of 4):
+ *     nbr_sorted[k][s] = nbr[k][slot_row[s]]
+ *   tile_mask_sorted (out, ceil(cap/128) uint32): active offsets per 128 slots
+ * The order of the rows inside a bucket is not deterministic (atomics); conv results do not depend on it.
+ */
+size_t u3d_tile_sort_scratch_ints(int cap);
+int u3d_rulebook_sort_tiles(const int32_t* nbr, int nbr_stride, const int32_t* n_out, int cap, int K,
+                            int32_t* scratch, int32_t* slot_row, int32_t* nbr_sorted, int sorted_stride,
+                            uint32_t* tile_mask_sorted, void* stream);
+
+/*
  * Convert a neighbour table to the (in,out) pair lists of spconv 1.x
  * (`indice_pairs (2,K,N)`, `indice_num (K)`), pairs ordered by output row.
  * One CTA per kernel offset. pairs_in/pairs_out: (K, pair_stride) int32; -1 padded.
@@ -182,11 +199,14 @@ int u3d_spconv_fwd(const void* in, const int32_t* nbr, int nbr_stride, const int
  *     nbr must be 16-byte aligned with nbr_stride a multiple of 4 and >= 128*ceil(out_cap/128)
  *     (whole 512-byte rulebook rows are bulk-copied into shared memory);
  *     tile_mask from u3d_rulebook_* (NULL = treat every offset as active).
+ *     slot_row (NULL = natural order): nbr / tile_mask are a SORTED rulebook from
+ *     u3d_rulebook_sort_tiles and slot s computes output row slot_row[s] (rows-on-N kernel only:
+ *     Cout <= 128); nbr_stride and slot_row must then be padded to whole 256-slot tiles.
  */
 size_t u3d_spconv_packed_bytes(int K, int Cin, int Cout);
 int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, void* packed, void* stream);
 int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr_stride,
-                          const uint32_t* tile_mask, const int32_t* n_out,
+                          const uint32_t* tile_mask, const int32_t* slot_row, const int32_t* n_out,
                           int out_cap, int K, const void* w_packed, const float* scale,
                           const float* shift, const void* residual, int relu, void* out, int Cin,
                           int Cout, void* stream);

@@ -16,8 +16,6 @@ echo "bench exit: $?" >> gpurun_out/bench.err
 cut -c1-300 gpurun_out/bench.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 cut -c1-400 gpurun_out/bench_ref.json
-timeout 300 python bench.py --steps 10 --warmup 3 --batch 8 --no-cpu-baseline > gpurun_out/bench_b8.json 2> gpurun_out/bench_b8.err
-cut -c1-200 gpurun_out/bench_b8.json
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
   --log-file gpurun_out/launches.csv python bench.py --no-graph --batch 32 --steps 1 --warmup 1 --no-cpu-baseline --no-roofline > gpurun_out/bench_ncu.log 2>&1
 echo "ncu list exit: $?" >> gpurun_out/bench_ncu.log

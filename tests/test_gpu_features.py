@@ -361,11 +361,59 @@ def test_spconv_tc_many_tiles_per_cta(cin, cout):
     res = torch.randn(n, cout, generator=torch.Generator().manual_seed(2)).to(DEV, torch.bfloat16)
     ref = ops.spconv_fwd(xb, nbr, n_rows, n, wb, scale.to(DEV), shift.to(DEV), residual=res, relu=True, impl=1)
     wp = ops.spconv_pack_weights(wb)
+    ys = {}
     for kern in TC_KERNELS:
         with tc_kernel(kern):
             y = ops.spconv_fwd_packed(xb, nbr, n_rows, n, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV),
                                       residual=res, relu=True)
         assert relerr(y, ref) < 1e-2, (kern, relerr(y, ref))
+        ys[kern] = y
+    # sorted tiles (csrc/tilesort.cu): a scheduling permutation only - every row must come out IDENTICAL to
+    # the natural-order run of the same kernel (value equality: the sign of an exact zero may differ)
+    srt = ops.rulebook_sort_tiles(nbr, n_rows, n)
+    with tc_kernel("0"):
+        y = ops.spconv_fwd_packed(xb, srt, n_rows, n, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV),
+                                  residual=res, relu=True)
+    assert bool((y.float() == ys["0"].float()).all())
+
+
+def _tile_key(mask):
+    key = np.zeros_like(mask)
+    for line in range(9):
+        key |= (((mask >> (3 * line)) & 7) != 0).astype(mask.dtype) << line
+    for c in range(3):
+        key |= ((mask & (0x1249249 << c)) != 0).astype(mask.dtype) << (9 + c)
+    return key
+
+
+@pytest.mark.parametrize("n,cap,dims,B", [(5000, 5077, (8, 24, 24), 2), (300, 300, (6, 10, 10), 1), (1, 130, (4, 4, 4), 1),
+                                          (60_000, 60_000, (24, 64, 64), 2)])
+def test_rulebook_sort_tiles(n, cap, dims, B):
+    """Tile scheduling: slot_row is a permutation of the live rows ordered by the 12-bit neighbour signature,
+    the sorted table is the natural table gathered through it, tile masks are the OR over 128 slots.
+    Integer work: exact."""
+    from uni3detr_b200 import ops
+    coors = rand_coors(n, dims, B, n + 1)
+    c = torch.cat([T(coors), torch.zeros(cap - n, 4, dtype=torch.int32)]).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, cap, B, dims)
+    nbr = ops.rulebook_subm(c, n_rows, cap, vm)
+    srt = ops.rulebook_sort_tiles(nbr, n_rows, cap)
+    nat = nbr[:, :n].cpu().numpy()
+    np.testing.assert_array_equal(nat, G.subm_rulebook(coors, dims))          # natural table untouched
+    slot_row = srt.slot_row[:n].cpu().numpy()
+    np.testing.assert_array_equal(np.sort(slot_row), np.arange(n))            # permutation of the live rows
+    mask = ((nat >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+    key = _tile_key(mask)[slot_row]
+    assert bool((np.diff(key) >= 0).all())                                     # bucketed by signature
+    got = srt[:, :n].cpu().numpy()
+    np.testing.assert_array_equal(got, nat[:, slot_row])
+    nt = (n + 127) // 128
+    act = np.zeros((27, nt * 128), bool)
+    act[:, :n] = got >= 0
+    want = (act.reshape(27, nt, 128).any(2).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+    tm = srt.tile_mask[:nt].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    np.testing.assert_array_equal(tm, want)
 
 
 def _random_boxes(n, n_cls, seed):

@@ -1,0 +1,214 @@
+"""Hand-computed known answers for the third-party half of the path.
+
+The reference ships no tests and the arithmetic of these ops lives in packages that cannot be
+installed here (mmcv `Voxelization` / `DynamicScatter` / `furthest_point_sample`, spconv
+`get_indice_pairs` / `indice_conv`), so the oracle for them is "parity unpinned". These cases are
+small enough to work out on paper from the published semantics; every expected
+array below is a literal written by hand, not produced by any implementation. They are checked twice:
+against the CPU oracle (`-m "not gpu"`) and against the CUDA library through the C ABI (`-m gpu`).
+
+Case V (voxelization): pc_range [0,0,0,2,2,2], voxel 1 -> a 2x2x2 grid; seven points (x,y,z,f):
+  p0 (0.5,0.5,0.5,10) cell x0y0z0   p1 (1.5,0.5,0.5,20) x1y0z0   p2 (0.2,0.7,0.1,30) x0y0z0
+  p3 (2.5,0.5,0.5,40) out of range  p4 (0.9,0.1,0.9,50) x0y0z0   p5 (0.5,1.5,1.5,60) x0y1z1
+  p6 (1.0,0.0,0.0,70) x1y0z0 (a coordinate ON a cell boundary belongs to the upper cell)
+Case R (rulebooks): four voxels of a 3x3x3 grid, r0 (z1,y1,x1), r1 (1,1,2), r2 (0,1,1), r3 (2,2,2);
+  offset index k = (kz*3+ky)*3+kx, neighbour = coordinate + (kz-1, ky-1, kx-1).
+Case D (strided conv, k 3, stride 2, pad 1 on a 4x4x4 grid): inputs i0 (0,0,0), i1 (1,1,1), i2 (3,3,3),
+  i3 (0,0,1); output o covers inputs 2o-1+k per axis, so i1 reaches all eight outputs.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as G
+from oracle import model as M
+
+DEV = "cuda"
+
+V_POINTS = np.array([[0.5, 0.5, 0.5, 10], [1.5, 0.5, 0.5, 20], [0.2, 0.7, 0.1, 30], [2.5, 0.5, 0.5, 40],
+                     [0.9, 0.1, 0.9, 50], [0.5, 1.5, 1.5, 60], [1.0, 0.0, 0.0, 70]], np.float32)
+V_RANGE, V_SIZE, V_DIMS = [0, 0, 0, 2, 2, 2], [1, 1, 1], (2, 2, 2)
+# hard voxelization, max 2 points per voxel, first-appearance order, coordinates as (z,y,x)
+V_HARD_COORS = [[0, 0, 0], [0, 0, 1], [1, 1, 0]]
+V_HARD_NUM = [2, 2, 1]                                   # p4 is the third point of voxel 0: dropped
+V_HARD_VOXELS = [[[0.5, 0.5, 0.5, 10], [0.2, 0.7, 0.1, 30]],
+                 [[1.5, 0.5, 0.5, 20], [1.0, 0.0, 0.0, 70]],
+                 [[0.5, 1.5, 1.5, 60], [0, 0, 0, 0]]]
+V_HARD_MEAN = [[0.35, 0.6, 0.3, 20], [1.25, 0.25, 0.25, 45], [0.5, 1.5, 1.5, 60]]
+# dynamic voxelization: per-point (z,y,x) (-1 when out of range), voxels sorted by (z,y,x), mean of ALL points
+V_DYN_POINT_COORS = [[0, 0, 0], [0, 0, 1], [0, 0, 0], [-1, -1, -1], [0, 0, 0], [1, 1, 0], [0, 0, 1]]
+V_DYN_COORS = [[0, 0, 0, 0], [0, 0, 0, 1], [0, 1, 1, 0]]
+V_DYN_MEAN = [[1.6 / 3, 1.3 / 3, 0.5, 30], [1.25, 0.25, 0.25, 45], [0.5, 1.5, 1.5, 60]]
+
+R_COORS = np.array([[0, 1, 1, 1], [0, 1, 1, 2], [0, 0, 1, 1], [0, 2, 2, 2]], np.int32)
+R_DIMS = (3, 3, 3)
+R_PAIRS = {(13, 0): 0, (14, 0): 1, (4, 0): 2, (26, 0): 3,      # (offset k, output row) -> input row
+           (13, 1): 1, (12, 1): 0, (3, 1): 2, (25, 1): 3,
+           (13, 2): 2, (22, 2): 0, (23, 2): 1,
+           (13, 3): 3, (0, 3): 0, (1, 3): 1}
+# 1-channel conv on case R: x = [1,2,3,4], w[k] = k+1  ->  out[o] = sum_k x[nbr[k][o]] * (k+1)
+R_CONV_OUT = [1 * 14 + 2 * 15 + 3 * 5 + 4 * 27, 2 * 14 + 1 * 13 + 3 * 4 + 4 * 26, 3 * 14 + 1 * 23 + 2 * 24,
+              4 * 14 + 1 * 1 + 2 * 2]                     # 167, 157, 113, 61
+R_CONV_BN_RELU = [234.0, 214.0, 126.0, 22.0]              # relu(out * 2 - 100)
+
+D_COORS = np.array([[0, 0, 0, 0], [0, 1, 1, 1], [0, 3, 3, 3], [0, 0, 0, 1]], np.int32)
+D_DIMS, D_STRIDE, D_PAD = (4, 4, 4), (2, 2, 2), (1, 1, 1)
+D_OUT_COORS = [[0, z, y, x] for z in (0, 1) for y in (0, 1) for x in (0, 1)]   # ascending linear index
+D_PAIRS = {(13, 0): 0, (26, 7): 2, (14, 0): 3, (12, 1): 3,
+           (26, 0): 1, (24, 1): 1, (20, 2): 1, (18, 3): 1, (8, 4): 1, (6, 5): 1, (2, 6): 1, (0, 7): 1}
+
+F_LINE = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [10, 0, 0], [4, 0, 0]], np.float32)
+F_LINE_IDX = [0, 3, 4, 2]          # start at 0; farthest 10; then 4 (16 vs 4, 1); then 2 (4 vs 1)
+F_TIE = np.array([[0, 0, 0], [2, 0, 0], [-2, 0, 0], [0, 1, 0]], np.float32)
+F_TIE_IDX = [0, 1, 2]              # rows 1 and 2 tie at distance 4: the lowest index first
+
+
+def table_from_pairs(pairs, n_out):
+    t = np.full((27, n_out), -1, np.int32)
+    for (k, o), i in pairs.items():
+        t[k, o] = i
+    return t
+
+
+# ------------------------------------------------------------------ oracle (CPU) ----
+def test_oracle_hard_voxelize_known_answer():
+    vox, coors, num = G.hard_voxelize(V_POINTS, V_RANGE, V_SIZE, 2, 3)
+    np.testing.assert_array_equal(coors, V_HARD_COORS)
+    np.testing.assert_array_equal(num, V_HARD_NUM)
+    np.testing.assert_array_equal(vox, np.array(V_HARD_VOXELS, np.float32))
+    np.testing.assert_allclose(G.hard_simple_vfe(vox, num, 4), V_HARD_MEAN, atol=1e-6)
+    # max_voxels = 2: the third voxel is never created, p6 still joins voxel 1
+    vox2, coors2, num2 = G.hard_voxelize(V_POINTS, V_RANGE, V_SIZE, 2, 2)
+    np.testing.assert_array_equal(coors2, V_HARD_COORS[:2])
+    np.testing.assert_array_equal(num2, V_HARD_NUM[:2])
+
+
+def test_oracle_dynamic_voxelize_known_answer():
+    pc = G.dynamic_voxelize(V_POINTS, V_RANGE, V_SIZE)
+    np.testing.assert_array_equal(pc, V_DYN_POINT_COORS)
+    cb = np.concatenate([np.zeros((len(pc), 1), np.int32), pc], 1)
+    feats, coors = G.dynamic_scatter_mean(V_POINTS, cb)
+    np.testing.assert_array_equal(coors, V_DYN_COORS)
+    np.testing.assert_allclose(feats, V_DYN_MEAN, atol=1e-6)
+
+
+def test_oracle_rulebooks_known_answer():
+    np.testing.assert_array_equal(G.subm_rulebook(R_COORS, R_DIMS), table_from_pairs(R_PAIRS, 4))
+    oc, nbr, od = G.down_rulebook(D_COORS, D_DIMS, D_STRIDE, D_PAD)
+    assert tuple(od) == (2, 2, 2)
+    np.testing.assert_array_equal(oc, D_OUT_COORS)
+    np.testing.assert_array_equal(nbr, table_from_pairs(D_PAIRS, 8))
+
+
+def test_oracle_sparse_conv_known_answer():
+    x = torch.tensor([[1.0], [2.0], [3.0], [4.0]])
+    w = torch.arange(1, 28, dtype=torch.float32).reshape(3, 3, 3, 1, 1)
+    y = M.sparse_conv(x, table_from_pairs(R_PAIRS, 4), w, 4)
+    np.testing.assert_array_equal(y.reshape(-1).numpy(), R_CONV_OUT)
+
+
+def test_oracle_fps_known_answer():
+    np.testing.assert_array_equal(G.furthest_point_sample(F_LINE, 4), F_LINE_IDX)
+    np.testing.assert_array_equal(G.furthest_point_sample(F_TIE, 3), F_TIE_IDX)
+
+
+# ------------------------------------------------------------------ product (GPU) ----
+def _dev_points(p):
+    pts = torch.from_numpy(p).to(DEV)
+    off = torch.tensor([0, len(p)], dtype=torch.int32, device=DEV)
+    return pts, off
+
+
+@pytest.mark.gpu
+def test_gpu_hard_voxelize_known_answer():
+    from uni3detr_b200 import ops
+    pts, off = _dev_points(V_POINTS)
+    v = ops.voxelize_hard(pts, off, 1, V_RANGE, V_SIZE, V_DIMS, 2, 3, want_voxels=True)
+    assert int(v.scene_rows[-1]) == 3
+    np.testing.assert_array_equal(v.coors[:3, 1:].cpu().numpy(), V_HARD_COORS)
+    np.testing.assert_array_equal(v.num_points[:3].cpu().numpy(), V_HARD_NUM)
+    np.testing.assert_array_equal(v.voxels[:3].cpu().numpy(), np.array(V_HARD_VOXELS, np.float32))
+    np.testing.assert_allclose(v.feats[:3].cpu().numpy(), V_HARD_MEAN, atol=1e-6)
+    v2 = ops.voxelize_hard(pts, off, 1, V_RANGE, V_SIZE, V_DIMS, 2, 2)
+    assert int(v2.scene_rows[-1]) == 2
+    np.testing.assert_array_equal(v2.coors[:2, 1:].cpu().numpy(), V_HARD_COORS[:2])
+    np.testing.assert_array_equal(v2.num_points[:2].cpu().numpy(), V_HARD_NUM[:2])
+
+
+@pytest.mark.gpu
+def test_gpu_dynamic_voxelize_known_answer():
+    from uni3detr_b200 import ops
+    pts, off = _dev_points(V_POINTS)
+    v = ops.voxelize_dynamic(pts, off, 1, V_RANGE, V_SIZE, V_DIMS)
+    assert int(v.scene_rows[-1]) == 3
+    np.testing.assert_array_equal(v.pt_coors[:7, 1:].cpu().numpy(), V_DYN_POINT_COORS)
+    np.testing.assert_array_equal(v.coors[:3].cpu().numpy(), V_DYN_COORS)
+    np.testing.assert_allclose(v.feats[:3].cpu().numpy(), V_DYN_MEAN, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_rulebooks_known_answer():
+    from uni3detr_b200 import ops
+    c = torch.from_numpy(R_COORS).to(DEV)
+    n = torch.tensor([4], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n, 4, 1, R_DIMS)
+    nbr = ops.rulebook_subm(c, n, 4, vm)
+    np.testing.assert_array_equal(nbr[:, :4].cpu().numpy(), table_from_pairs(R_PAIRS, 4))
+    c = torch.from_numpy(D_COORS).to(DEV)
+    vm = ops.voxmap_build(c, n, 4, 1, D_DIMS)
+    oc, n_out, ovm, dn, ocap = ops.rulebook_down(c, n, 4, vm, D_STRIDE, D_PAD)
+    assert int(n_out) == 8 and tuple(ovm.dims) == (2, 2, 2)
+    np.testing.assert_array_equal(oc[:8].cpu().numpy(), D_OUT_COORS)
+    np.testing.assert_array_equal(dn[:, :8].cpu().numpy(), table_from_pairs(D_PAIRS, 8))
+    pairs, num = ops.rulebook_pairs(dn, n_out)            # spconv-1.x view of the same rulebook
+    num = num.cpu().numpy()
+    assert num.sum() == len(D_PAIRS)
+    for k in range(27):
+        got = {(k, int(o)): int(i) for i, o in zip(pairs[0, k, :num[k]].cpu(), pairs[1, k, :num[k]].cpu())}
+        assert got == {ko: i for ko, i in D_PAIRS.items() if ko[0] == k}
+
+
+@pytest.mark.gpu
+def test_gpu_sparse_conv_known_answer():
+    """fp32 SIMT kernel on the 1-channel case, then the tcgen05 kernels on the same rulebook with the
+    single channel embedded in 16 (bf16 represents these small integers exactly)."""
+    from uni3detr_b200 import ops
+    c = torch.from_numpy(R_COORS).to(DEV)
+    n = torch.tensor([4], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n, 4, 1, R_DIMS)
+    nbr = ops.rulebook_subm(c, n, 4, vm)
+    x = torch.tensor([[1.0], [2.0], [3.0], [4.0]], device=DEV)
+    w = torch.arange(1, 28, dtype=torch.float32, device=DEV).reshape(27, 1, 1)
+    y = ops.spconv_fwd(x, nbr, n, 4, w)
+    np.testing.assert_array_equal(y.reshape(-1).cpu().numpy(), R_CONV_OUT)
+    y = ops.spconv_fwd(x, nbr, n, 4, w, torch.tensor([2.0], device=DEV), torch.tensor([-100.0], device=DEV), relu=True)
+    np.testing.assert_array_equal(y.reshape(-1).cpu().numpy(), R_CONV_BN_RELU)
+    x16 = torch.zeros(4, 16, device=DEV, dtype=torch.bfloat16)
+    x16[:, 3] = x[:, 0].bfloat16()
+    w16 = torch.zeros(27, 16, 16, device=DEV, dtype=torch.bfloat16)
+    w16[:, 3, 5] = w[:, 0, 0].bfloat16()
+    wp = ops.spconv_pack_weights(w16)
+    import os
+    for kern in ("0", "1"):
+        prev = os.environ.get("U3D_TC_KERNEL")
+        os.environ["U3D_TC_KERNEL"] = kern
+        try:
+            y16 = ops.spconv_fwd_packed(x16, nbr, n, 4, wp, 27, 16, 16)
+        finally:
+            if prev is None:
+                os.environ.pop("U3D_TC_KERNEL", None)
+            else:
+                os.environ["U3D_TC_KERNEL"] = prev
+        got = y16.float().cpu().numpy()
+        np.testing.assert_array_equal(got[:, 5], R_CONV_OUT)
+        assert not got[:, [i for i in range(16) if i != 5]].any()
+
+
+@pytest.mark.gpu
+def test_gpu_fps_known_answer():
+    from uni3detr_b200 import ops
+    for pts_np, want in ((F_LINE, F_LINE_IDX), (F_TIE, F_TIE_IDX)):
+        pts = torch.from_numpy(pts_np).to(DEV)
+        seg = torch.tensor([0, len(pts_np)], dtype=torch.int32, device=DEV)
+        idx, _ = ops.fps(pts, 3, 3, pts, 3, seg, 1, len(pts_np), len(want))
+        np.testing.assert_array_equal(idx[0].cpu().numpy(), want)

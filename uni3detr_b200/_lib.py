@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libu3d_b200.so")
-_SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_tn.cu",
+_SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_tn.cu", "tilesort.cu",
             "fps.cu", "decoder.cu", "mha_tc.cu", "nms.cu"]
 _HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"),
             os.path.join(_HERE, "..", "include", "u3d.h")]
@@ -84,8 +84,10 @@ SIGNATURES = {
                               _i32, _i32, _i32, _vp]),
     "u3d_spconv_packed_bytes": (_sz, [_i32, _i32, _i32]),
     "u3d_spconv_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
-    "u3d_spconv_fwd_packed": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
+    "u3d_spconv_fwd_packed": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
                                      _i32, _vp, _i32, _i32, _vp]),
+    "u3d_tile_sort_scratch_ints": (_sz, [_i32]),
+    "u3d_rulebook_sort_tiles": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "u3d_sparse_to_dense": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                    _vp, _vp]),
     "u3d_fps": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

@@ -140,12 +140,14 @@ static inline size_t dtype_size(int dtype) { return dtype == U3D_BF16 ? 2 : 4; }
 int voxmap_scan(uint2* map, size_t words, int32_t* scratch, int32_t* total_out, cudaStream_t st);
 
 int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
-                  const uint32_t* tile_mask, const int32_t* n_out, int out_cap, int K, const void* w,
+                  const uint32_t* tile_mask, const int32_t* slot_row, const int32_t* n_out, int out_cap,
+                  int K, const void* w,
                   const float* scale, const float* shift, const void* residual, int relu, void* out,
                   int Cin, int Cout, cudaStream_t st);
 bool spconv_tc_supported(int Cin, int Cout, int dtype);
 int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride,
-                  const uint32_t* tile_mask, const int32_t* n_out, int out_cap, int K, const void* w,
+                  const uint32_t* tile_mask, const int32_t* slot_row, const int32_t* n_out, int out_cap,
+                  int K, const void* w,
                   const float* scale, const float* shift, const void* residual, int relu, void* out,
                   int Cin, int Cout, cudaStream_t st);
 bool spconv_tn_supported(int Cin, int Cout, const int32_t* nbr);

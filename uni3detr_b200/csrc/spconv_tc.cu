@@ -367,7 +367,8 @@ bool spconv_tc_supported(int Cin, int Cout, int dtype) {
 }
 
 int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
-                  const uint32_t* tile_mask, const int32_t* n_out, int out_cap, int K, const void* wpk,
+                  const uint32_t* tile_mask, const int32_t* slot_row, const int32_t* n_out, int out_cap,
+                  int K, const void* wpk,
                   const float* scale, const float* shift, const void* residual, int relu, void* out,
                   int Cin, int Cout, cudaStream_t st) {
   using namespace tc;
@@ -376,9 +377,11 @@ int spconv_fwd_tc(const void* in, const int32_t* nbr, int nbr_stride,
   {
     const char* e = getenv("U3D_TC_KERNEL");
     if (!(e && atoi(e) == 1) && spconv_tn_supported(Cin, Cout, nbr))
-      return spconv_fwd_tn(in, nbr, nbr_stride, tile_mask, n_out, out_cap, K, wpk, scale, shift, residual,
-                           relu, out, Cin, Cout, st);
+      return spconv_fwd_tn(in, nbr, nbr_stride, tile_mask, slot_row, n_out, out_cap, K, wpk, scale, shift,
+                           residual, relu, out, Cin, Cout, st);
   }
+  U3D_CHECK_ARG(slot_row == nullptr, "spconv tc: sorted tiles (slot_row) need the rows-on-N kernel "
+                "(Cout <= 128, U3D_TC_KERNEL != 1); pass the natural-order rulebook (Cin=%d Cout=%d)", Cin, Cout);
   U3D_CHECK_ARG(K >= 1 && K <= kMaxK, "spconv tc: K=%d unsupported", K);
   U3D_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)wpk | (uintptr_t)residual) & 15) == 0,
                 "spconv tc: buffers must be 16-byte aligned");
@@ -468,8 +471,8 @@ extern "C" int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, 
 }
 
 extern "C" int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr_stride,
-                                     const uint32_t* tile_mask, const int32_t* n_out, int out_cap,
-                                     int K, const void* w_packed,
+                                     const uint32_t* tile_mask, const int32_t* slot_row,
+                                     const int32_t* n_out, int out_cap, int K, const void* w_packed,
                                      const float* scale, const float* shift, const void* residual,
                                      int relu, void* out, int Cin, int Cout, void* stream) {
   U3D_CHECK_ARG(in && n_out && w_packed && out, "u3d_spconv_fwd_packed: null buffer");
@@ -477,6 +480,6 @@ extern "C" int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr
   U3D_CHECK_ARG(spconv_tc_supported(Cin, Cout, U3D_BF16),
                 "u3d_spconv_fwd_packed: needs Cin in {16,32,64k<=512}, Cout a power of two in [16,512] "
                 "(Cin=%d Cout=%d)", Cin, Cout);
-  return spconv_fwd_tc(in, nbr, nbr_stride, tile_mask, n_out, out_cap, K, w_packed, scale, shift,
+  return spconv_fwd_tc(in, nbr, nbr_stride, tile_mask, slot_row, n_out, out_cap, K, w_packed, scale, shift,
                        residual, relu, out, Cin, Cout, (cudaStream_t)stream);
 }

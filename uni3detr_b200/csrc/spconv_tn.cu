@@ -62,6 +62,7 @@ struct Smem {
   uint64_t slice_full[kSliceBufs];
   uint64_t slice_empty[kSliceBufs];
   uint32_t tmem_base;
+  alignas(128) int srow[2][kTile];   // output row of every slot of the tile in accumulator buffer ab (sorted tiles)
   alignas(128) int nbr[kSliceBufs][kMaxK][kTile];
 };
 
@@ -76,7 +77,8 @@ __device__ __forceinline__ uint32_t mask_of_tile(const uint32_t* __restrict__ ti
 template <int CIN_BLK>
 __global__ void __launch_bounds__(kThreads, 1)
 k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
-            const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ n_out_p, int K,
+            const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ slot_row,
+            const int32_t* __restrict__ n_out_p, int K,
             const __nv_bfloat16* __restrict__ wpk, const float* __restrict__ scale,
             const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
             __nv_bfloat16* __restrict__ out, int Cin, int Cout, int stages) {
@@ -119,7 +121,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       mbar_init(&S.empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&S.acc_full[b], 1);
+      mbar_init(&S.acc_full[b], slot_row ? 2 : 1);   // tcgen05.commit (+ the tile's slot->row list)
       mbar_init(&S.acc_empty[b], kEpiThreads);
     }
     for (int b = 0; b < kSliceBufs; ++b) {
@@ -255,6 +257,10 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         const int n_st = (n_units + kG - 1) / kG;
         mbar_wait(&S.acc_empty[ab], ((uint32_t)(t >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        if (slot_row) {   // sorted tiles: the epilogue of this tile needs slot -> output row (same lifetime as ab)
+          mbar_expect_tx(&S.acc_full[ab], (uint32_t)(kTile * 4));
+          bulk_g2s(smem_u32(&S.srow[ab][0]), slot_row + (size_t)tile * kTile, kTile * 4, &S.acc_full[ab]);
+        }
         const uint32_t d_tmem = tmem + (uint32_t)(ab * kTile);
         for (int st = 0; st < n_st; ++st) {
           const int cnt = n_units - st * kG < kG ? n_units - st * kG : kG;
@@ -295,20 +301,25 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     int t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int ab = t & 1;
-      const int row0 = tile * kTile + col_lo + (odd ? 1 : 0);   // + col + 2p
+      const int row0 = tile * kTile + col_lo + (odd ? 1 : 0);   // slot of this lane: + col + 2p
+      const int* srow = slot_row ? &S.srow[ab][col_lo + (odd ? 1 : 0)] : nullptr;
       uint32_t res[16];
       auto load_res = [&](int col) {
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
-          const int o = row0 + col + 2 * p;
-          res[p] = (residual && lane_live && o < n_out)
-                       ? __ldg(reinterpret_cast<const uint32_t*>(residual + (size_t)o * Cout + cb))
-                       : 0u;
+          const int slot = row0 + col + 2 * p;
+          if (residual && lane_live && slot < n_out) {
+            const int o = srow ? srow[col + 2 * p] : slot;
+            res[p] = __ldg(reinterpret_cast<const uint32_t*>(residual + (size_t)o * Cout + cb));
+          } else {
+            res[p] = 0u;
+          }
         }
       };
-      load_res(0);
+      if (!srow) load_res(0);          // natural order: residual addresses do not depend on the slot list
       mbar_wait_relaxed(&S.acc_full[ab], (uint32_t)(t >> 1) & 1u, 2000u);
       tc_fence_after();
+      if (srow) load_res(0);
       const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * kTile + col_lo);
 #pragma unroll 1
       for (int col = 0; col < ncol; col += 32) {
@@ -326,8 +337,9 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
           const float recv = __shfl_xor_sync(0xffffffffu, odd ? fe : fo, 1);
           float lo = odd ? recv : fe;     // channel cb
           float hi = odd ? fo : recv;     // channel cb+1
-          const int o = row0 + col + 2 * p;
-          if (lane_live && o < n_out) {
+          const int slot = row0 + col + 2 * p;
+          if (lane_live && slot < n_out) {
+            const int o = srow ? srow[col + 2 * p] : slot;
             const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cur[p]));
             lo += r.x;
             hi += r.y;
@@ -357,7 +369,8 @@ bool spconv_tn_supported(int Cin, int Cout, const int32_t* nbr) {
 }
 
 int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint32_t* tile_mask,
-                  const int32_t* n_out, int out_cap, int K, const void* wpk, const float* scale,
+                  const int32_t* slot_row, const int32_t* n_out, int out_cap, int K, const void* wpk,
+                  const float* scale,
                   const float* shift, const void* residual, int relu, void* out, int Cin, int Cout,
                   cudaStream_t st) {
   using namespace tn;
@@ -366,6 +379,9 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint
                 "spconv tn: buffers must be 16-byte aligned");
   const int tiles = cdiv(out_cap, kTile);
   if (tiles < 1) return U3D_OK;
+  U3D_CHECK_ARG(slot_row == nullptr || ((((uintptr_t)slot_row) & 15) == 0 && nbr_stride >= kTile * tiles),
+                "spconv tn: slot_row must be 16-byte aligned and, like the sorted rulebook, padded to whole "
+                "256-slot tiles (stride=%d, out_cap=%d)", nbr_stride, out_cap);
   U3D_CHECK_ARG((((uintptr_t)nbr) & 15) == 0 && nbr_stride % 4 == 0 && nbr_stride >= 128 * cdiv(out_cap, 128),
                 "spconv tn: the rulebook must be 16-byte aligned with a row stride that is a multiple of 4 "
                 "and >= 128*ceil(out_cap/128) (stride=%d, out_cap=%d)", nbr_stride, out_cap);
@@ -386,8 +402,9 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint
     static int cur_smem = 0;                                                                        \
     U3D_CUDA(ensure_dynamic_smem(k_spconv_tn<BLK>, smem, &cur_smem));                               \
     k_spconv_tn<BLK><<<grid, kThreads, smem, st>>>(                                                 \
-        (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, n_out, K, (const __nv_bfloat16*)wpk,  \
-        scale, shift, (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out, Cin, Cout, stages); \
+        (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, slot_row, n_out, K,                   \
+        (const __nv_bfloat16*)wpk, scale, shift, (const __nv_bfloat16*)residual, relu,              \
+        (__nv_bfloat16*)out, Cin, Cout, stages);                                                    \
   } while (0)
   if (blk == 64) U3D_TN_LAUNCH(64);
   else if (blk == 32) U3D_TN_LAUNCH(32);

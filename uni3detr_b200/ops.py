@@ -206,6 +206,7 @@ class Rulebook(torch.Tensor):
     """Neighbour table (27, cap) int32 that also carries the per-128-row tile masks
     (`.tile_mask`, uint32 as int32) the tensor-core conv uses to skip empty kernel offsets."""
     tile_mask = None
+    slot_row = None    # sorted rulebooks (rulebook_sort_tiles): output row computed in slot s
     __torch_function__ = torch._C._disabled_torch_function_impl   # ops on it yield plain tensors
 
     @staticmethod
@@ -261,6 +262,26 @@ def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=No
                                      _p(n_out), out_cap, _p(nbr), nbr.stride(0), _p(nbr.tile_mask),
                                      _stream()))
     return out_coors, n_out, VoxelMap(out_vm, None, vmap.B, out_dims), nbr, out_cap
+
+
+@_timed(lambda r, nbr, n_out, cap: dict(n_out=int(n_out)))
+def rulebook_sort_tiles(nbr, n_out, cap):
+    """Tile scheduling for the tensor-core conv: returns a SORTED Rulebook (27, cap) whose slots group
+    rows with similar neighbour masks (`.slot_row[s]` = output row of slot s, `.tile_mask` per 128
+    slots); see csrc/tilesort.cu. Inputs: the natural-order table and its device row count."""
+    lib = _lib.load()
+    K = nbr.shape[0]
+    cap = max(int(cap), 1)
+    dev = nbr.device
+    pad = (cap + 255) // 256 * 256
+    srt = torch.empty((K, pad), dtype=torch.int32, device=dev)[:, :cap].as_subclass(Rulebook)
+    srt.tile_mask = torch.empty(pad // 128, dtype=torch.int32, device=dev)
+    srt.slot_row = torch.empty(pad, dtype=torch.int32, device=dev)
+    scratch = torch.empty(lib.u3d_tile_sort_scratch_ints(cap), dtype=torch.int32, device=dev)
+    _lib.check(lib.u3d_rulebook_sort_tiles(_p(nbr), nbr.stride(0), _p(n_out), cap, K, _p(scratch),
+                                           _p(srt.slot_row), _p(srt), srt.stride(0), _p(srt.tile_mask),
+                                           _stream()))
+    return srt
 
 
 def rulebook_pairs(nbr, n_out):
@@ -324,7 +345,8 @@ def spconv_fwd_packed(x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, scale=None
         out = torch.empty((out_cap, Cout), dtype=torch.bfloat16, device=x.device)
     stride = nbr.stride(0) if nbr is not None else 0
     tile_mask = getattr(nbr, "tile_mask", None) if nbr is not None else None
-    _lib.check(lib.u3d_spconv_fwd_packed(_p(x), _p(nbr), stride, _p(tile_mask), _p(n_out),
+    slot_row = getattr(nbr, "slot_row", None) if nbr is not None else None
+    _lib.check(lib.u3d_spconv_fwd_packed(_p(x), _p(nbr), stride, _p(tile_mask), _p(slot_row), _p(n_out),
                                          out_cap, K, _p(w_packed),
                                          _p(scale), _p(shift), _p(residual), int(bool(relu)), _p(out),
                                          Cin, Cout, _stream()))

@@ -14,6 +14,8 @@ SURVEY.md Appendix B; weights in the spconv-1.x layout (kz,ky,kx,Cin,Cout), the 
 """
 import math
 
+import os
+
 import torch
 from torch import nn
 
@@ -246,21 +248,29 @@ class SparseEncoderHD(nn.Module):
         if plan["steps"][0]["cin"] > x.shape[1]:
             x = torch.nn.functional.pad(x, (0, plan["steps"][0]["cin"] - x.shape[1]))
         dims = tuple(self.sparse_shape)
-        level = dict(coors=coors, n=n_rows, cap=cap, vmap=vmap, nbr=None, dims=dims)
+        level = dict(coors=coors, n=n_rows, cap=cap, vmap=vmap, nbr=None, nbr_sorted=None, dims=dims)
         saved = None
+        # tile scheduling (csrc/tilesort.cu): the rows-on-N tensor-core kernel takes rulebooks whose
+        # 256-slot tiles group rows with similar neighbour masks. U3D_SORT_TILES=0 keeps the natural order.
+        sort_tiles = (os.environ.get("U3D_SORT_TILES", "1") != "0" and os.environ.get("U3D_TC_KERNEL") != "1")
         for st in plan["steps"]:
+            sortable = sort_tiles and st["packed"] is not None and st["k"] == 27 and st["cout"] <= 128
             if st["k"] == 1:
                 nbr, out_level = None, level
             elif st["subm"]:
                 if level["nbr"] is None:
                     level["nbr"] = ops.rulebook_subm(level["coors"], level["n"], level["cap"],
                                                      level["vmap"])
-                nbr, out_level = level["nbr"], level
+                if sortable and level["nbr_sorted"] is None:
+                    level["nbr_sorted"] = ops.rulebook_sort_tiles(level["nbr"], level["n"], level["cap"])
+                nbr, out_level = (level["nbr_sorted"] if sortable else level["nbr"]), level
             else:
                 oc, on, ovm, nbr, ocap = ops.rulebook_down(level["coors"], level["n"],
                                                            level["cap"], level["vmap"],
                                                            st["stride"], st["pad"])
-                out_level = dict(coors=oc, n=on, cap=ocap, vmap=ovm, nbr=None, dims=ovm.dims)
+                if sortable:
+                    nbr = ops.rulebook_sort_tiles(nbr, on, ocap)
+                out_level = dict(coors=oc, n=on, cap=ocap, vmap=ovm, nbr=None, nbr_sorted=None, dims=ovm.dims)
             if st["save"]:
                 saved = x
             res = saved if st["add"] else None
