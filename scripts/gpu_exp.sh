@@ -1,14 +1,9 @@
 #!/bin/bash
-# Experiment pass: parity tests of the changed kernels (tile sort, known answers, model), bench A/B.
+# Experiment pass: which rulebooks to tile-sort (policy A/B of validated code paths).
 set -u
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests -m gpu -q --timeout 300 -x --no-header -k "spconv or sort_tiles or known_answer or dense or forward" 2>&1 | tail -40 > gpurun_out/pytest_spconv.log
-rc=${PIPESTATUS[0]}
-echo "pytest exit: $rc" >> gpurun_out/pytest_spconv.log
-tail -6 gpurun_out/pytest_spconv.log
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
-echo "bench exit: $?" >> gpurun_out/bench.err
-cut -c1-300 gpurun_out/bench.json
-U3D_SORT_TILES=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_nosort.json 2> gpurun_out/bench_nosort.err
-cut -c1-300 gpurun_out/bench_nosort.json
-tail -3 gpurun_out/bench.err
+for cfg in "32 1" "32 0" "16 1"; do
+  set -- $cfg
+  U3D_SORT_MAX_CIN=$1 U3D_SORT_DOWN=$2 timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/bench_sort_$1_$2.json 2> gpurun_out/bench_sort_$1_$2.err
+  echo "cin<=$1 down=$2: $(cut -c1-120 gpurun_out/bench_sort_$1_$2.json)"
+done
