@@ -19,7 +19,7 @@ cut -c1-400 gpurun_out/bench_ref.json
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
   --log-file gpurun_out/launches.csv python bench.py --no-graph --batch 32 --steps 1 --warmup 1 --no-cpu-baseline --no-roofline > gpurun_out/bench_ncu.log 2>&1
 echo "ncu list exit: $?" >> gpurun_out/bench_ncu.log
-timeout 400 ncu --clock-control none -k 'regex:^k_' -c 200 --csv --log-file gpurun_out/ncu_kernels.csv \
+timeout 400 ncu --clock-control none -k 'regex:k_' -c 220 --csv --log-file gpurun_out/ncu_kernels.csv \
   --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__grid_size,launch__registers_per_thread \
   python bench.py --no-graph --batch 32 --steps 1 --warmup 1 --no-cpu-baseline --no-roofline > gpurun_out/ncu_kernels.log 2>&1
 echo "ncu kernels exit: $?" >> gpurun_out/ncu_kernels.log

@@ -254,11 +254,14 @@ class SparseEncoderHD(nn.Module):
         # 256-slot tiles group rows with similar neighbour masks. It pays where tile padding dominates
         # (thin layers: 6-35 % useful slots in natural order) and loses on the 64/128-channel levels at
         # batch 32, whose feature matrices no longer fit L2 once the gathers lose their spatial order
-        # (measured: 64->64 0.348 -> 0.404 ms, 32->32 0.328 -> 0.211 ms, 16->16 0.131 -> 0.075 ms).
-        # U3D_SORT_TILES=0 keeps the natural order everywhere; U3D_SORT_MAX_CIN / U3D_SORT_DOWN tune it.
+        # (measured per launch: 64->64 0.348 -> 0.404 ms, 32->32 0.328 -> 0.211 ms, 16->16 0.131 -> 0.075 ms;
+        # a sort costs ~0.1-0.2 ms, so it is spent on the SubM levels whose table serves 4-5 convs, not on
+        # the single-use strided tables: 1889 scenes/s vs 1885 with them, 1866 for Cin <= 16 only, 1860 for
+        # everything, 1844 unsorted). U3D_SORT_TILES=0 keeps the natural order everywhere;
+        # U3D_SORT_MAX_CIN / U3D_SORT_DOWN tune the policy.
         sort_tiles = (os.environ.get("U3D_SORT_TILES", "1") != "0" and os.environ.get("U3D_TC_KERNEL") != "1")
         sort_max_cin = int(os.environ.get("U3D_SORT_MAX_CIN", "32"))
-        sort_down = os.environ.get("U3D_SORT_DOWN", "1") != "0"
+        sort_down = os.environ.get("U3D_SORT_DOWN", "0") != "0"
         for st in plan["steps"]:
             sortable = (sort_tiles and st["packed"] is not None and st["k"] == 27 and st["cout"] <= 128
                         and st["cin"] <= sort_max_cin and (st["subm"] or sort_down))
