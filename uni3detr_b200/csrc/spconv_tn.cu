@@ -30,6 +30,10 @@
 //                K-major swizzled B tile, published with cp.async.mbarrier.arrive.noinc; the first
 //                warp of the pair also bulk-copies the stage's 128-row weight images (second image
 //                set of u3d_spconv_pack_weights), one cp.async.bulk per (offset, Cin block).
+// Sorted tiles (tilesort.cu): with a `slot_row` list the rulebook is in slot order, the MMA thread
+// bulk-copies the tile's 256 slot -> row entries next to the accumulator buffer (they complete on
+// acc_full together with the tcgen05.commit) and the epilogue reads the residual of / writes row
+// slot_row[s]; inputs keep their natural row numbers.
 // Measured (profiles/): first version (one rulebook load per pass, one weight copy) 0.47 ms on the
 // 64->64 layers at batch 32 vs 0.64 ms rows-on-M; batched rulebook loads 0.33 ms; the replicated
 // image removes the epilogue bound of the 16- and 32-channel layers.
