@@ -364,7 +364,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="scenes per step per GPU")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-scenes", type=int, default=2, help="bounded CPU-baseline sample (scenes)")
+    ap.add_argument("--cpu-scenes", type=int, default=10, help="bounded CPU-baseline sample (scenes, ~1.1 s each on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-op roofline pass (ncu runs)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
