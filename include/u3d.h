@@ -252,6 +252,24 @@ int u3d_coors_to_float(const int32_t* coors, int rows, float* out, void* stream)
 int u3d_sine_embed(const float* ref, int rows, void* out, int dtype, void* stream);
 
 /*
+ * Input pre-stage (EXPERIMENTAL in round 1: written after the GPU budget was spent, not yet run on
+ * hardware, not on the benchmarked path). The point-cloud part of the reference's test pipeline
+ * (projects/configs/uni3detr/uni3detr_sunrgbd.py:175-191: LoadPointsFromFile(load_dim, use_dim,
+ * shift_height) -> PointsRangeFilter -> PointSample) on the device, producing the (points, offsets)
+ * pair u3d_voxelize_* consume.
+ *   raw (Ntot, load_dim) f32, scenes concatenated; raw_off (B+1) int32 DEVICE offsets
+ *   use_dim: n_use HOST column indices (first three = x, y, z); shift_height: insert
+ *     z - np.percentile(z, 0.99) (per scene, linear interpolation) as 4th column
+ *   pc_range: 6 HOST floats or NULL; a point is kept iff lo < (x,y,z) < hi (strict, mmdet3d in_range_3d)
+ *   floor_z (B) f32, kept (B) int32, out_off (B+1) int32: DEVICE outputs; out (Ntot, n_use+shift_height) f32
+ * u3d_points_gather: out[i] = in[choices[i]] (PointSample with host-drawn indices).
+ */
+int u3d_points_prepare(const float* raw, const int32_t* raw_off, int B, int load_dim,
+                       const int32_t* use_dim, int n_use, int shift_height, const float* pc_range,
+                       float* floor_z, int32_t* kept, float* out, int32_t* out_off, void* stream);
+int u3d_points_gather(const float* in, int C, const int32_t* choices, int n, float* out, void* stream);
+
+/*
  * Fused level merge of SECOND3DFPN: out = sum_i act_i(x_i + bias_i), i < 3, one pass over NDHWC rows.
  * Replaces the `ups[0] + ups[1] + ups[2]` sum of necks/second3d_fpn.py:125-126 together with the
  * BatchNorm3d(eval) shift and ReLU of the ConvTranspose3d branches (:56-72), which then run without

@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libu3d_b200.so")
-_SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_tn.cu", "tilesort.cu",
+_SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_tn.cu", "tilesort.cu", "points.cu",
             "fps.cu", "decoder.cu", "mha_tc.cu", "nms.cu"]
 _HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"),
             os.path.join(_HERE, "..", "include", "u3d.h")]
@@ -94,6 +94,8 @@ SIGNATURES = {
     "u3d_coors_to_float": (_i32, [_vp, _i32, _vp, _vp]),
     "u3d_sine_embed": (_i32, [_vp, _i32, _vp, _i32, _vp]),
     "u3d_add_layernorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "u3d_points_prepare": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "u3d_points_gather": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "u3d_bias_act_sum": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, ctypes.c_longlong, _i32, _i32, _vp, _vp]),
     "u3d_mha_core": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
     "u3d_nms3d_mask_words": (_sz, [_i32]),

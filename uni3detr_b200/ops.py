@@ -493,3 +493,40 @@ def nms3d_bev(boxes, labels, valid, iou_threshold):
 def launch_count():
     """Kernels launched by libu3d_b200 in this process so far."""
     return int(_lib.load().u3d_launch_count())
+
+
+# ---------------------------------------------------------------- input pre-stage (experimental) ----
+def points_prepare(raw, raw_off, B, use_dim, shift_height=False, pc_range=None):
+    """EXPERIMENTAL (not yet run on hardware, see csrc/points.cu). LoadPointsFromFile column select
+    (+ shift_height) and PointsRangeFilter on the device. raw (Ntot, load_dim) f32, raw_off (B+1) int32.
+    Returns (points (Ntot, C) with the kept rows packed scene by scene, out_off (B+1) int32, floor_z (B))."""
+    lib = _lib.load()
+    _req(raw, torch.float32, "raw")
+    _req(raw_off, torch.int32, "raw_off")
+    Ntot, load_dim = raw.shape
+    use, usep = _iarr([int(u) for u in use_dim])
+    C = len(use_dim) + (1 if shift_height else 0)
+    dev = raw.device
+    floor_z = torch.empty(B, dtype=torch.float32, device=dev)
+    kept = torch.empty(B, dtype=torch.int32, device=dev)
+    out = torch.empty((max(Ntot, 1), C), dtype=torch.float32, device=dev)
+    out_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    if pc_range is not None:
+        pr, prp = _farr(pc_range)
+    else:
+        pr, prp = None, None
+    _lib.check(lib.u3d_points_prepare(_p(raw), _p(raw_off), B, load_dim, usep, len(use_dim),
+                                      int(bool(shift_height)), prp, _p(floor_z), _p(kept), _p(out),
+                                      _p(out_off), _stream()))
+    return out, out_off, floor_z
+
+
+def points_gather(points, choices):
+    """EXPERIMENTAL. PointSample with host-drawn indices: points[choices] on the device."""
+    lib = _lib.load()
+    _req(points, torch.float32, "points")
+    _req(choices, torch.int32, "choices")
+    n, C = choices.numel(), points.shape[1]
+    out = torch.empty((n, C), dtype=torch.float32, device=points.device)
+    _lib.check(lib.u3d_points_gather(_p(points), C, _p(choices), n, _p(out), _stream()))
+    return out
