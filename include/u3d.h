@@ -152,6 +152,15 @@ int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, int in_cap,
  * The order of the rows inside a bucket is not deterministic (atomics); conv results do not depend on it.
  */
 size_t u3d_tile_sort_scratch_ints(int cap);
+/* EXPERIMENTAL (round 1: not yet run on hardware; U3D_SORT_GROUP): the same with the signature buckets kept
+ * inside groups of `scenes_per_group` consecutive scenes (coors: (cap,4) [b,z,y,x] of the output rows,
+ * scene-major; n_groups = ceil(B / scenes_per_group)), so that a tile's gathers stay within a few scenes. */
+size_t u3d_tile_sort_grouped_scratch_ints(int cap, int n_groups);
+int u3d_rulebook_sort_tiles_grouped(const int32_t* nbr, int nbr_stride, const int32_t* coors,
+                                    const int32_t* n_out, int cap, int K, int n_groups,
+                                    int scenes_per_group, int32_t* scratch, int32_t* slot_row,
+                                    int32_t* nbr_sorted, int sorted_stride, uint32_t* tile_mask_sorted,
+                                    void* stream);
 int u3d_rulebook_sort_tiles(const int32_t* nbr, int nbr_stride, const int32_t* n_out, int cap, int K,
                             int32_t* scratch, int32_t* slot_row, int32_t* nbr_sorted, int sorted_stride,
                             uint32_t* tile_mask_sorted, void* stream);

@@ -509,3 +509,28 @@ def test_bias_act_sum(dtype, tol):
     assert relerr(y, ref) < tol
     y1 = ops.bias_act_sum([xs[0].to(DEV)], [bs[1].to(DEV)], [True])          # single operand
     assert relerr(y1, F.relu(xs[0].float() + bs[1])) < tol
+
+
+@pytest.mark.skipif(__import__("os").environ.get("U3D_EXPERIMENTAL") != "1",
+                    reason="grouped tile sort has not run on hardware yet: set U3D_EXPERIMENTAL=1")
+@pytest.mark.parametrize("B,per_group", [(4, 1), (5, 2), (3, 8)])
+def test_rulebook_sort_tiles_grouped(B, per_group):
+    """EXPERIMENTAL: signature buckets kept inside groups of consecutive scenes: slot_row permutes every
+    group's row range onto itself, keys are sorted inside a group, table / masks as in the global variant."""
+    from uni3detr_b200 import ops
+    dims, n = (8, 24, 24), 9000
+    coors = rand_coors(n, dims, B, 77)
+    c = T(coors).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, n, B, dims)
+    nbr = ops.rulebook_subm(c, n_rows, n, vm)
+    srt = ops.rulebook_sort_tiles(nbr, n_rows, n, c, B, per_group)
+    nat = nbr[:, :n].cpu().numpy()
+    slot_row = srt.slot_row[:n].cpu().numpy()
+    np.testing.assert_array_equal(np.sort(slot_row), np.arange(n))
+    grp = coors[:, 0] // per_group
+    np.testing.assert_array_equal(grp[slot_row], grp)                  # a group's rows stay in its range
+    mask = ((nat >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+    key = grp[slot_row].astype(np.int64) * 4096 + _tile_key(mask)[slot_row]
+    assert bool((np.diff(key) >= 0).all())
+    np.testing.assert_array_equal(srt[:, :n].cpu().numpy(), nat[:, slot_row])

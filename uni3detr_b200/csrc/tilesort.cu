@@ -151,6 +151,101 @@ k_nbr_permute(const int32_t* __restrict__ nbr, int nbr_stride, const int32_t* __
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Grouped variant (EXPERIMENTAL in round 1: written after the GPU budget was spent, not yet run on
+// hardware; reached only through u3d_rulebook_sort_tiles_grouped / U3D_SORT_GROUP): bucket by
+// signature INSIDE groups of consecutive scenes, so that the gathers of a tile stay within a few
+// scenes' feature rows (L2 resident on the wide levels at batch 32, where the global order loses:
+// 64->64 0.348 -> 0.404 ms). CPU estimate of the useful slot fraction on 8 scenes, stage 2:
+// natural 0.65, per-scene buckets 0.88, global 0.92 (scripts/tile_padding_stats.py).
+// Rows are scene-major at every level, so a group is a contiguous row segment seg[g]..seg[g+1].
+
+// seg[g] = first row whose batch index is >= g * scenes_per_group (binary search), seg[G] = n
+__global__ void k_seg_bounds(const int32_t* __restrict__ coors, const int32_t* __restrict__ n_p, int G,
+                             int scenes_per_group, int32_t* __restrict__ seg) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > G) return;
+  const int n = *n_p;
+  const int want = g * scenes_per_group;
+  int lo = 0, hi = n;                       // first row with batch >= want
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(&coors[(size_t)mid * 4]) < want) lo = mid + 1; else hi = mid;
+  }
+  seg[g] = g == G ? n : lo;
+}
+
+__device__ __forceinline__ void seg_block_range(const int32_t* __restrict__ seg, int& start, int& end) {
+  const int s0 = seg[blockIdx.y], s1 = seg[blockIdx.y + 1];
+  const int n = s1 - s0;
+  int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  per = (per + kSortThreads - 1) / kSortThreads * kSortThreads;
+  const long long s = (long long)blockIdx.x * per;
+  start = s0 + (s < n ? (int)s : n);
+  end = s0 + (s + per < n ? (int)(s + per) : n);
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+k_key_hist_seg(const int32_t* __restrict__ row_key, const int32_t* __restrict__ seg, int32_t* __restrict__ hist) {
+  __shared__ int s_hist[kKeyBins];
+  for (int b = threadIdx.x; b < kKeyBins; b += kSortThreads) s_hist[b] = 0;
+  __syncthreads();
+  int start, end;
+  seg_block_range(seg, start, end);
+  block_histogram(row_key, start, end, s_hist);
+  __syncthreads();
+  int32_t* h = hist + (size_t)blockIdx.y * kKeyBins;
+  for (int b = threadIdx.x; b < kKeyBins; b += kSortThreads)
+    if (s_hist[b]) atomicAdd(&h[b], s_hist[b]);
+}
+
+// exclusive scan over the concatenated (group-major) histograms: G * 4096 bins, one block
+__global__ void __launch_bounds__(1024)
+k_key_scan_seg(const int32_t* __restrict__ hist, int total_bins, int32_t* __restrict__ cursor) {
+  __shared__ int smem[33];
+  const int per = (total_bins + 1023) / 1024;
+  const int b0 = threadIdx.x * per;
+  int sum = 0;
+  for (int i = 0; i < per; ++i)
+    if (b0 + i < total_bins) sum += hist[b0 + i];
+  int total;
+  int ex = block_exclusive_scan(sum, smem, total);
+  for (int i = 0; i < per; ++i)
+    if (b0 + i < total_bins) { cursor[b0 + i] = ex; ex += hist[b0 + i]; }
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+k_key_scatter_seg(const int32_t* __restrict__ row_key, const int32_t* __restrict__ seg,
+                  int32_t* __restrict__ cursor, int32_t* __restrict__ slot_row) {
+  __shared__ int s_cnt[kKeyBins];
+  __shared__ int s_base[kKeyBins];
+  for (int b = threadIdx.x; b < kKeyBins; b += kSortThreads) s_cnt[b] = 0;
+  __syncthreads();
+  int start, end;
+  seg_block_range(seg, start, end);
+  block_histogram(row_key, start, end, s_cnt);
+  __syncthreads();
+  int32_t* cur = cursor + (size_t)blockIdx.y * kKeyBins;
+  for (int b = threadIdx.x; b < kKeyBins; b += kSortThreads) {
+    const int c = s_cnt[b];
+    if (c) s_base[b] = atomicAdd(&cur[b], c);
+    s_cnt[b] = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int base = start; base < end; base += kSortThreads) {
+    const int r = base + threadIdx.x;
+    const bool valid = r < end;
+    const int key = valid ? __ldg(&row_key[r]) : (kKeyBins + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int leader = __ffs(peers) - 1;
+    int first = 0;
+    if (valid && lane == leader) first = atomicAdd(&s_cnt[key], __popc(peers));
+    first = __shfl_sync(0xffffffffu, first, leader);
+    if (valid) slot_row[s_base[key] + first + __popc(peers & ((1u << lane) - 1u))] = r;
+  }
+}
+
 }  // namespace u3d
 
 using namespace u3d;
@@ -186,6 +281,53 @@ extern "C" int u3d_rulebook_sort_tiles(const int32_t* nbr, int nbr_stride, const
   k_key_scan<<<1, 1024, 0, st>>>(hist, cursor);
   U3D_LAUNCH_CHECK();
   k_key_scatter<<<gs, kSortThreads, 0, st>>>(row_key, n_out, cursor, slot_row);
+  U3D_LAUNCH_CHECK();
+  k_nbr_permute<<<g, 256, 0, st>>>(nbr, nbr_stride, slot_row, n_out, K, nbr_sorted, sorted_stride,
+                                   tile_mask_sorted);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+extern "C" size_t u3d_tile_sort_grouped_scratch_ints(int cap, int n_groups) {
+  return (size_t)(cap > 0 ? cap : 1) + (size_t)(n_groups + 1) + 2 * (size_t)kKeyBins * (size_t)(n_groups > 0 ? n_groups : 1);
+}
+
+// EXPERIMENTAL (see the grouped kernels above): u3d_rulebook_sort_tiles with the signature buckets kept
+// inside groups of `scenes_per_group` consecutive scenes. coors: (cap,4) int32 [b,z,y,x] of the OUTPUT rows
+// (scene-major); n_groups = ceil(B / scenes_per_group).
+extern "C" int u3d_rulebook_sort_tiles_grouped(const int32_t* nbr, int nbr_stride, const int32_t* coors,
+                                               const int32_t* n_out, int cap, int K, int n_groups,
+                                               int scenes_per_group, int32_t* scratch, int32_t* slot_row,
+                                               int32_t* nbr_sorted, int sorted_stride,
+                                               uint32_t* tile_mask_sorted, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  U3D_CHECK_ARG(nbr && coors && n_out && scratch && slot_row && nbr_sorted && tile_mask_sorted,
+                "u3d_rulebook_sort_tiles_grouped: null buffer");
+  U3D_CHECK_ARG(K >= 1 && K <= 27 && cap >= 0 && nbr_stride >= cap && sorted_stride >= cap && n_groups >= 1 &&
+                    n_groups <= 1024 && scenes_per_group >= 1,
+                "u3d_rulebook_sort_tiles_grouped: bad shape (K=%d cap=%d groups=%d)", K, cap, n_groups);
+  if (cap == 0) return U3D_OK;
+  int32_t* row_key = scratch;
+  int32_t* seg = scratch + cap;
+  int32_t* hist = seg + (n_groups + 1);
+  int32_t* cursor = hist + (size_t)kKeyBins * n_groups;
+  U3D_CUDA(cudaMemsetAsync(hist, 0, 2 * (size_t)kKeyBins * n_groups * sizeof(int32_t), st));
+  U3D_CUDA(cudaMemsetAsync(tile_mask_sorted, 0, (size_t)cdiv(cap, 128) * sizeof(uint32_t), st));
+  int g = cdiv(cap, 256);
+  if (g > kNumSMs * 8) g = kNumSMs * 8;
+  k_row_key<<<g, 256, 0, st>>>(nbr, nbr_stride, n_out, K, row_key);
+  U3D_LAUNCH_CHECK();
+  k_seg_bounds<<<cdiv(n_groups + 1, 128), 128, 0, st>>>(coors, n_out, n_groups, scenes_per_group, seg);
+  U3D_LAUNCH_CHECK();
+  int per_group = cdiv(cdiv(cap, n_groups), 8 * kSortThreads);   // >= 2048 rows per block at full capacity
+  if (per_group < 1) per_group = 1;
+  if (per_group * n_groups > kNumSMs * 8) per_group = cdiv(kNumSMs * 8, n_groups);
+  dim3 gs(per_group, n_groups);
+  k_key_hist_seg<<<gs, kSortThreads, 0, st>>>(row_key, seg, hist);
+  U3D_LAUNCH_CHECK();
+  k_key_scan_seg<<<1, 1024, 0, st>>>(hist, kKeyBins * n_groups, cursor);
+  U3D_LAUNCH_CHECK();
+  k_key_scatter_seg<<<gs, kSortThreads, 0, st>>>(row_key, seg, cursor, slot_row);
   U3D_LAUNCH_CHECK();
   k_nbr_permute<<<g, 256, 0, st>>>(nbr, nbr_stride, slot_row, n_out, K, nbr_sorted, sorted_stride,
                                    tile_mask_sorted);

@@ -264,11 +264,13 @@ def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=No
     return out_coors, n_out, VoxelMap(out_vm, None, vmap.B, out_dims), nbr, out_cap
 
 
-@_timed(lambda r, nbr, n_out, cap: dict(n_out=int(n_out)))
-def rulebook_sort_tiles(nbr, n_out, cap):
+@_timed(lambda r, nbr, n_out, cap, *a, **k: dict(n_out=int(n_out)))
+def rulebook_sort_tiles(nbr, n_out, cap, coors=None, n_scenes=0, scenes_per_group=0):
     """Tile scheduling for the tensor-core conv: returns a SORTED Rulebook (27, cap) whose slots group
     rows with similar neighbour masks (`.slot_row[s]` = output row of slot s, `.tile_mask` per 128
-    slots); see csrc/tilesort.cu. Inputs: the natural-order table and its device row count."""
+    slots); see csrc/tilesort.cu. Inputs: the natural-order table and its device row count.
+    EXPERIMENTAL: with `coors` (the output rows' (cap,4) coordinates), `n_scenes` and
+    `scenes_per_group` > 0 the buckets stay inside groups of consecutive scenes."""
     lib = _lib.load()
     K = nbr.shape[0]
     cap = max(int(cap), 1)
@@ -277,6 +279,14 @@ def rulebook_sort_tiles(nbr, n_out, cap):
     srt = torch.empty((K, pad), dtype=torch.int32, device=dev)[:, :cap].as_subclass(Rulebook)
     srt.tile_mask = torch.empty(pad // 128, dtype=torch.int32, device=dev)
     srt.slot_row = torch.empty(pad, dtype=torch.int32, device=dev)
+    if scenes_per_group and coors is not None and n_scenes > 0:
+        G = (int(n_scenes) + int(scenes_per_group) - 1) // int(scenes_per_group)
+        _req(coors, torch.int32, "coors")
+        scratch = torch.empty(lib.u3d_tile_sort_grouped_scratch_ints(cap, G), dtype=torch.int32, device=dev)
+        _lib.check(lib.u3d_rulebook_sort_tiles_grouped(_p(nbr), nbr.stride(0), _p(coors), _p(n_out), cap, K, G,
+                                                       int(scenes_per_group), _p(scratch), _p(srt.slot_row),
+                                                       _p(srt), srt.stride(0), _p(srt.tile_mask), _stream()))
+        return srt
     scratch = torch.empty(lib.u3d_tile_sort_scratch_ints(cap), dtype=torch.int32, device=dev)
     _lib.check(lib.u3d_rulebook_sort_tiles(_p(nbr), nbr.stride(0), _p(n_out), cap, K, _p(scratch),
                                            _p(srt.slot_row), _p(srt), srt.stride(0), _p(srt.tile_mask),

@@ -262,6 +262,8 @@ class SparseEncoderHD(nn.Module):
         sort_tiles = (os.environ.get("U3D_SORT_TILES", "1") != "0" and os.environ.get("U3D_TC_KERNEL") != "1")
         sort_max_cin = int(os.environ.get("U3D_SORT_MAX_CIN", "32"))
         sort_down = os.environ.get("U3D_SORT_DOWN", "0") != "0"
+        # EXPERIMENTAL (not yet run on hardware): U3D_SORT_GROUP=g keeps the buckets inside groups of g scenes
+        sort_group = int(os.environ.get("U3D_SORT_GROUP", "0"))
         for st in plan["steps"]:
             sortable = (sort_tiles and st["packed"] is not None and st["k"] == 27 and st["cout"] <= 128
                         and st["cin"] <= sort_max_cin and (st["subm"] or sort_down))
@@ -272,14 +274,15 @@ class SparseEncoderHD(nn.Module):
                     level["nbr"] = ops.rulebook_subm(level["coors"], level["n"], level["cap"],
                                                      level["vmap"])
                 if sortable and level["nbr_sorted"] is None:
-                    level["nbr_sorted"] = ops.rulebook_sort_tiles(level["nbr"], level["n"], level["cap"])
+                    level["nbr_sorted"] = ops.rulebook_sort_tiles(level["nbr"], level["n"], level["cap"],
+                                                                  level["coors"], B, sort_group)
                 nbr, out_level = (level["nbr_sorted"] if sortable else level["nbr"]), level
             else:
                 oc, on, ovm, nbr, ocap = ops.rulebook_down(level["coors"], level["n"],
                                                            level["cap"], level["vmap"],
                                                            st["stride"], st["pad"])
                 if sortable:
-                    nbr = ops.rulebook_sort_tiles(nbr, on, ocap)
+                    nbr = ops.rulebook_sort_tiles(nbr, on, ocap, oc, B, sort_group)
                 out_level = dict(coors=oc, n=on, cap=ocap, vmap=ovm, nbr=None, nbr_sorted=None, dims=ovm.dims)
             if st["save"]:
                 saved = x
