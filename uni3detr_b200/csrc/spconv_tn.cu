@@ -52,12 +52,14 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kMmaWarp = 8;
 constexpr int kSliceWarp = 9;
 constexpr int kProdWarp0 = 10;
-constexpr int kNumProd = 6;            // 3 pairs = 3 ring slots (a stage is always 48 KB)
-constexpr int kThreads = (kProdWarp0 + kNumProd) * 32;   // 512
-constexpr int kSliceBufs = 2;
+// producer warps: 6 = 3 pairs = 3 ring slots (a stage is always 48 KB; default), or 8 with the
+// single-buffered rulebook slices of the EXPERIMENTAL 4-stage variant (U3D_TN_SLICE_BUFS=1)
+constexpr int threads_of(int n_prod) { return (kProdWarp0 + n_prod) * 32; }   // 512 / 576
 constexpr int kMaxK = 27;
-constexpr int kMaxStages = 3;      // one ring slot per producer warp pair
 
+// kSliceBufs: rulebook-slice buffers, 2 (default) or 1 (EXPERIMENTAL: frees 28 KB -> a 4th stage);
+// kMaxStages: one ring slot per producer warp pair
+template <int kSliceBufs, int kMaxStages>
 struct Smem {
   uint64_t full[kMaxStages];    // 64 cp.async arrives (the stage's two warps) + 1 arrive.expect_tx
   uint64_t empty[kMaxStages];   // tcgen05.commit: the MMAs that read the stage have retired
@@ -78,8 +80,8 @@ __device__ __forceinline__ uint32_t mask_of_tile(const uint32_t* __restrict__ ti
   return m & all_mask;
 }
 
-template <int CIN_BLK>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CIN_BLK, int kSliceBufs, int kNumProd>
+__global__ void __launch_bounds__(threads_of(kNumProd), 1)
 k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
             const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ slot_row,
             const int32_t* __restrict__ n_out_p, int K,
@@ -94,8 +96,9 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   constexpr int kUnitX = kTile * SW::P;           // one 256-row feature sub-tile
   constexpr int kXBytes = kG * kUnitX;            // 32 KB for every CIN_BLK
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-  constexpr uint32_t kHeader = (uint32_t)((sizeof(Smem) + 1023) & ~(size_t)1023);
+  using SmemT = Smem<kSliceBufs, kNumProd / 2>;
+  SmemT& S = *reinterpret_cast<SmemT*>(smem_raw);
+  constexpr uint32_t kHeader = (uint32_t)((sizeof(SmemT) + 1023) & ~(size_t)1023);
 
   const int n_out = *n_out_p;
   const int n_tiles = (n_out + kTile - 1) / kTile;
@@ -393,27 +396,38 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint
   const uint32_t P = 2 * blk;
   const uint32_t kg = 64 / blk;
   const uint32_t stage_bytes = kg * 128u * P + kg * kTile * P;   // 16 KB weights (replicated) + 32 KB rows
-  const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
+  // Default: double-buffered rulebook slices, 6 producer warps, 3 stages. EXPERIMENTAL (not yet run on
+  // hardware): U3D_TN_SLICE_BUFS=1 single-buffers the slices, which frees 28 KB for a 4th stage filled by a
+  // 4th producer pair (576 threads).
+  bool deep = false;
+  if (const char* e = getenv("U3D_TN_SLICE_BUFS")) deep = atoi(e) == 1;
+  const int max_stages = deep ? 4 : 3;                        // one ring slot per producer pair
+  const size_t header = ((deep ? sizeof(Smem<1, 4>) : sizeof(Smem<2, 3>)) + 1023) & ~(size_t)1023;
   int stages = (int)((227u * 1024u - header) / stage_bytes);
   if (const char* e = getenv("U3D_TN_STAGES")) stages = atoi(e);
-  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > max_stages) stages = max_stages;
   U3D_CHECK_ARG(stages >= 2, "spconv tn: tile does not fit shared memory (Cin=%d Cout=%d)", Cin, Cout);
   const size_t smem = header + (size_t)stages * stage_bytes;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
 
-#define U3D_TN_LAUNCH(BLK)                                                                          \
+#define U3D_TN_LAUNCH2(BLK, SB, NP)                                                                 \
   do {                                                                                              \
     static int cur_smem = 0;                                                                        \
-    U3D_CUDA(ensure_dynamic_smem(k_spconv_tn<BLK>, smem, &cur_smem));                               \
-    k_spconv_tn<BLK><<<grid, kThreads, smem, st>>>(                                                 \
+    U3D_CUDA(ensure_dynamic_smem(k_spconv_tn<BLK, SB, NP>, smem, &cur_smem));                       \
+    k_spconv_tn<BLK, SB, NP><<<grid, threads_of(NP), smem, st>>>(                                   \
         (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, slot_row, n_out, K,                   \
         (const __nv_bfloat16*)wpk, scale, shift, (const __nv_bfloat16*)residual, relu,              \
         (__nv_bfloat16*)out, Cin, Cout, stages);                                                    \
+  } while (0)
+#define U3D_TN_LAUNCH(BLK)                                                                          \
+  do {                                                                                              \
+    if (deep) U3D_TN_LAUNCH2(BLK, 1, 8); else U3D_TN_LAUNCH2(BLK, 2, 6);                            \
   } while (0)
   if (blk == 64) U3D_TN_LAUNCH(64);
   else if (blk == 32) U3D_TN_LAUNCH(32);
   else U3D_TN_LAUNCH(16);
 #undef U3D_TN_LAUNCH
+#undef U3D_TN_LAUNCH2
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }
