@@ -534,3 +534,23 @@ def test_rulebook_sort_tiles_grouped(B, per_group):
     key = grp[slot_row].astype(np.int64) * 4096 + _tile_key(mask)[slot_row]
     assert bool((np.diff(key) >= 0).all())
     np.testing.assert_array_equal(srt[:, :n].cpu().numpy(), nat[:, slot_row])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("U3D_EXPERIMENTAL") != "1",
+                    reason="MN-major V attention variant has not run on hardware yet: set U3D_EXPERIMENTAL=1")
+@pytest.mark.parametrize("seq_len,n_seq", [(300, 8), (900, 2), (5, 4), (129, 1)])
+def test_mha_core_v_mn_major(seq_len, n_seq, monkeypatch):
+    """EXPERIMENTAL: U3D_MHA_VMN=1 stages V untransposed and uses an MN-major B operand for O = P V."""
+    from uni3detr_b200 import ops
+    monkeypatch.setenv("U3D_MHA_VMN", "1")
+    g = torch.Generator().manual_seed(seq_len)
+    heads, E = 8, 256
+    qk = torch.randn(n_seq * seq_len, 2 * E, generator=g).bfloat16()
+    v = torch.randn(n_seq * seq_len, E, generator=g).bfloat16()
+    out = ops.mha_core(qk.to(DEV)[:, :E], qk.to(DEV)[:, E:], v.to(DEV), n_seq, seq_len, heads)
+
+    def split(t):
+        return t.float().view(n_seq, seq_len, heads, 32).permute(0, 2, 1, 3)
+    ref = F.scaled_dot_product_attention(split(qk[:, :E]), split(qk[:, E:]), split(v))
+    ref = ref.permute(0, 2, 1, 3).reshape(n_seq * seq_len, E)
+    assert relerr(out, ref) < 1e-2

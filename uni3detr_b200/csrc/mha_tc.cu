@@ -47,6 +47,11 @@ __host__ __device__ inline Layout make_layout(int keys_pad64) {
   return L;
 }
 
+// kVT = true (default): V is staged TRANSPOSED (V^T[d][key], K-major B operand of O = P V).
+// kVT = false (EXPERIMENTAL, U3D_MHA_VMN=1, not yet run on hardware): V is staged as loaded ([key][d], 64-byte
+// rows, the layout of the K tile) and handed to the tensor core as an MN-major B operand (instruction
+// descriptor bit 16), which removes the 2-byte transposing shared stores.
+template <bool kVT>
 __global__ void __launch_bounds__(kThreads)
 k_mha_tc(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
          const __nv_bfloat16* __restrict__ v, int ldq, int ldk, int ldv, int seq_len, int heads,
@@ -86,12 +91,16 @@ k_mha_tc(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ 
     const uint4 kv = __ldg(reinterpret_cast<const uint4*>(k + (row0 + r) * ldk + head * kHd + c * 8));
     *reinterpret_cast<uint4*>(sm + L.k + SwQK::offset(r, c)) = kv;
     const uint4 vv = __ldg(reinterpret_cast<const uint4*>(v + (row0 + r) * ldv + head * kHd + c * 8));
-    const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-    const int blk = r >> 6, col = r & 63;
+    if (kVT) {
+      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+      const int blk = r >> 6, col = r & 63;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {                          // V^T[d][key]: row d = c*8+j, column = key
-      const int d = c * 8 + j;
-      *reinterpret_cast<__nv_bfloat16*>(sm + L.vt + blk * 4096 + SwP::offset(d, col >> 3) + (col & 7) * 2) = ve[j];
+      for (int j = 0; j < 8; ++j) {                          // V^T[d][key]: row d = c*8+j, column = key
+        const int d = c * 8 + j;
+        *reinterpret_cast<__nv_bfloat16*>(sm + L.vt + blk * 4096 + SwP::offset(d, col >> 3) + (col & 7) * 2) = ve[j];
+      }
+    } else {
+      *reinterpret_cast<uint4*>(sm + L.vt + SwQK::offset(r, c)) = vv;   // V[key][d], same layout as the K tile
     }
   }
   tc_fence_before();
@@ -180,11 +189,13 @@ k_mha_tc(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ 
     // ---- O_blk = P V  (accumulator reuses TMEM columns 0..31 of S)
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t idesc = idesc_base | ((uint32_t)(kHd >> 3) << 17);
+      const uint32_t idesc = idesc_base | ((uint32_t)(kHd >> 3) << 17) | (kVT ? 0u : (1u << 16));   // bit 16: B MN-major
       for (int ks = 0; ks < nk16 / 16; ++ks) {
         const int blk = ks >> 2, kk = ks & 3;
         const uint64_t a_desc = SwP::desc(sm_u + L.p + (uint32_t)blk * 16384) + (uint64_t)(kk * 2);
-        const uint64_t b_desc = SwP::desc(sm_u + L.vt + (uint32_t)((kb0 >> 6) + blk) * 4096) + (uint64_t)(kk * 2);
+        const uint64_t b_desc =
+            kVT ? SwP::desc(sm_u + L.vt + (uint32_t)((kb0 >> 6) + blk) * 4096) + (uint64_t)(kk * 2)
+                : SwQK::desc(sm_u + L.vt + (uint32_t)(kb0 + ks * 16) * 64);   // 16 keys x 64-byte rows per K step
         umma_bf16(tmem, a_desc, b_desc, idesc, ks > 0 ? 1u : 0u);
       }
       umma_commit(&s_bar);
@@ -238,8 +249,10 @@ int mha_core_tc(const void* q, const void* k, const void* v, int ldq, int ldk, i
                 int seq_len, int heads, void* out, cudaStream_t st) {
   using namespace mha;
   const size_t smem = make_layout((seq_len + 63) & ~63).total + 1024;
-  static int cur_smem = 0;
-  U3D_CUDA(ensure_dynamic_smem(k_mha_tc, smem, &cur_smem));
+  const bool vmn = getenv("U3D_MHA_VMN") != nullptr && atoi(getenv("U3D_MHA_VMN")) == 1;   // EXPERIMENTAL
+  static int cur_smem = 0, cur_smem_vmn = 0;
+  if (vmn) U3D_CUDA(ensure_dynamic_smem(k_mha_tc<false>, smem, &cur_smem_vmn));
+  else U3D_CUDA(ensure_dynamic_smem(k_mha_tc<true>, smem, &cur_smem));
   // one CTA per (head, sequence) looping over the query blocks (K / V^T staged once), unless the
   // launch would leave SMs idle (few sequences) or U3D_MHA_QSPLIT=1 asks for one CTA per query block
   const int n_qb = cdiv(seq_len, kQB);
@@ -247,9 +260,14 @@ int mha_core_tc(const void* q, const void* k, const void* v, int ldq, int ldk, i
   if (const char* e = getenv("U3D_MHA_QSPLIT")) split = atoi(e) != 0;
   const int per_cta = split ? 1 : n_qb;
   dim3 grid(cdiv(n_qb, per_cta), heads, n_seq);
-  k_mha_tc<<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
-                                          (const __nv_bfloat16*)v, ldq, ldk, ldv, seq_len, heads, per_cta,
-                                          (__nv_bfloat16*)out);
+  if (vmn)
+    k_mha_tc<false><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                   (const __nv_bfloat16*)v, ldq, ldk, ldv, seq_len, heads,
+                                                   per_cta, (__nv_bfloat16*)out);
+  else
+    k_mha_tc<true><<<grid, kThreads, smem, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k,
+                                                  (const __nv_bfloat16*)v, ldq, ldk, ldv, seq_len, heads,
+                                                  per_cta, (__nv_bfloat16*)out);
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }
