@@ -73,6 +73,60 @@ def test_prestage_reads_the_shipped_configs():
     assert pre.pc_range == PCR
 
 
+def _float_key(f):
+    u = np.float32(f).view(np.uint32)
+    return np.uint32(~u) if (u & np.uint32(0x80000000)) else np.uint32(u | np.uint32(0x80000000))
+
+
+def _key_float(k):
+    k = np.uint32(k)
+    return (np.uint32(k & np.uint32(0x7FFFFFFF)) if (k & np.uint32(0x80000000)) else np.uint32(~k)).view(np.float32)
+
+
+def _radix_select_percentile(z):
+    """Python model of k_points_stats (csrc/points.cu): 4 x 8-bit radix select of the lower order statistic
+    on order-preserving keys, the next one from the duplicate count / the smallest larger key, lerp in double."""
+    n = len(z)
+    keys = np.array([_float_key(v) for v in z], dtype=np.uint64)
+    q = 0.99 / 100.0
+    vi = n * q + (1.0 + q * (-1.0)) - 1.0
+    k_lo = max(0, min(int(np.floor(vi)), n - 1))
+    gamma = vi - np.floor(vi)
+    prefix, rank, less = 0, k_lo, 0
+    for p in (3, 2, 1, 0):
+        hi_mask = 0 if p == 3 else (0xFFFFFFFF << (8 * (p + 1))) & 0xFFFFFFFF
+        sel = (keys & hi_mask) == prefix
+        hist = np.bincount(((keys[sel] >> (8 * p)) & 255).astype(np.int64), minlength=256)
+        acc, b = 0, 0
+        while b < 256 and acc + hist[b] <= rank:
+            acc += hist[b]
+            b += 1
+        b = min(b, 255)
+        rank -= acc
+        less += acc
+        prefix |= b << (8 * p)
+    eq = int((keys == prefix).sum())
+    larger = keys[keys > prefix]
+    k_hi = min(k_lo + 1, n - 1)
+    a = _key_float(prefix)
+    bb = a if (k_hi < less + eq or len(larger) == 0) else _key_float(int(larger.min()))
+    return np.float32(float(a) + (float(bb) - float(a)) * gamma)
+
+
+def test_radix_select_percentile_algorithm_matches_numpy():
+    """The selection algorithm of the shift_height kernel, modelled in Python, vs np.percentile(z, 0.99):
+    within 1 ulp (the two order statistics are exact; only the interpolation arithmetic differs)."""
+    rng = np.random.default_rng(1)
+    for t in range(60):
+        n = int(rng.integers(1, 3000))
+        z = (rng.normal(size=n) * rng.uniform(0.01, 10)).astype(np.float32)
+        if n > 5 and t % 3 == 0:
+            z[: n // 2] = z[0]                      # duplicated order statistics
+        ref = np.float32(np.percentile(z, 0.99))
+        got = _radix_select_percentile(z)
+        assert abs(float(got) - float(ref)) <= 2 * float(np.spacing(np.float32(max(abs(ref), 1e-30)))), (n, got, ref)
+
+
 def _raw_scene(n, seed):
     rng = np.random.default_rng(seed)
     raw = np.zeros((n, 6), np.float32)
