@@ -182,6 +182,27 @@ def test_bench_reference_arm_emits_one_json_line():
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
 
 
+def test_bench_reference_arm_other_ranks_exit_silently():
+    """Under torchrun (N > 1) only rank 0 runs the CPU arm; the other ranks print nothing and exit 0."""
+    import sys
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout.strip() == ""
+
+
+def test_bench_without_cuda_fails_loudly():
+    """The GPU arm has no CPU fallback: without a CUDA device bench.py exits non-zero with a message."""
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
 def test_rulebook_buffer_layout():
     """Rulebook.alloc: row stride padded to whole 128-row tiles (the conv bulk-copies 512-byte rows)."""
     from uni3detr_b200 import ops
