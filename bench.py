@@ -150,6 +150,36 @@ def spconv_cost(info, n_in):
     return by, 2.0 * pairs * info["Cin"] * info["Cout"]
 
 
+def roofline_of(top, peaks):
+    """Roofline of one kernel record of the profile pass (pure arithmetic; tests/test_abi.py exercises it)."""
+    # every op of this pass is timed ALONE (a sync before each launch): the GPU is not under the sustained
+    # power-capped load of a long step, so the tensor denominator is the BURST cuBLAS figure of
+    # MEASURED_PEAKS.json (B200_PROFILING.md); the sustained figure is reported beside it
+    tf_peak = peaks["tf_burst"]
+    ridge = tf_peak * 1e12 / (peaks["hbm"] * 1e9)
+    intensity = top["flops_per_launch"] / max(top["bytes_per_launch"], 1.0)
+    if intensity > ridge:
+        roof = {"bound": "tensor", "achieved": top["tflops"], "peak": tf_peak, "unit": "TFLOP/s",
+                "frac": top["tflops"] / tf_peak, "frac_of_sustained_peak": top["tflops"] / peaks["tf_sustained"],
+                "sustained_peak": peaks["tf_sustained"]}
+    else:
+        roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": top["gbs"] / peaks["hbm"]}
+    traffic = None   # dram__bytes_read+write per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f).get(top["kernel"], {})
+        traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("tensor_pipe_active_pct") is not None:   # same committed ncu capture
+            roof["tensor_pipe_active_pct_ncu"] = tj["tensor_pipe_active_pct"]
+    roof.update({"traffic": traffic, "kernel": top["kernel"], "avg_launch_ms": top["avg_launch_ms"],
+                 "algorithmic_bytes_per_launch": top["bytes_per_launch"],
+                 "algorithmic_flops_per_launch": top["flops_per_launch"],
+                 "peak_source": peaks["source"] + " (burst cuBLAS bf16 for a kernel timed alone / copy bandwidth)", "rule": RIDGE_NOTE})
+    return roof
+
+
 def roofline_pass(step_fn, peaks, reps=3):
     """Per-op device times (CUDA events on the launching stream) of the libu3d kernels inside the
     step, then the roofline of the dominant one."""
@@ -204,26 +234,7 @@ def roofline_pass(step_fn, peaks, reps=3):
                         "bytes_per_launch": a["bytes"] / a["calls"], "flops_per_launch": a["flops"] / a["calls"]})
     kernels.sort(key=lambda k: -k["ms_per_step"])
     top = kernels[0]
-    ridge = peaks["tf_sustained"] * 1e12 / (peaks["hbm"] * 1e9)
-    intensity = top["flops_per_launch"] / max(top["bytes_per_launch"], 1.0)
-    if intensity > ridge:
-        roof = {"bound": "tensor", "achieved": top["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": top["tflops"] / peaks["tf_sustained"]}
-    else:
-        roof = {"bound": "hbm", "achieved": top["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": top["gbs"] / peaks["hbm"]}
-    traffic = None   # dram__bytes_read+write per launch from the committed ncu --set full capture
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f).get(top["kernel"], {})
-        traffic = tj.get("dram_bytes_per_launch")
-        if tj.get("tensor_pipe_active_pct") is not None:   # same committed ncu capture
-            roof["tensor_pipe_active_pct_ncu"] = tj["tensor_pipe_active_pct"]
-    roof.update({"traffic": traffic, "kernel": top["kernel"], "avg_launch_ms": top["avg_launch_ms"],
-                 "algorithmic_bytes_per_launch": top["bytes_per_launch"],
-                 "algorithmic_flops_per_launch": top["flops_per_launch"],
-                 "peak_source": peaks["source"] + " (sustained bf16 / copy bandwidth)", "rule": RIDGE_NOTE})
+    roof = roofline_of(top, peaks)
     ours_ms = sum(k["ms_per_step"] for k in kernels)
     return roof, kernels[:12], ours_ms
 

@@ -203,6 +203,30 @@ def test_bench_without_cuda_fails_loudly():
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
 
 
+def test_bench_roofline_arithmetic():
+    """bench.roofline_of: bound by FLOP/byte vs the measured ridge, fraction against the burst cuBLAS peak for a
+    kernel timed alone (sustained figure beside it), HBM fraction against the copy peak. Run in a subprocess:
+    importing bench.py re-routes the process' stdout."""
+    import json
+    import sys
+    code = (
+        "import importlib.util, json, sys\n"
+        "spec = importlib.util.spec_from_file_location('bench_mod', %r)\n"
+        "b = importlib.util.module_from_spec(spec); sys.argv = ['bench.py']; spec.loader.exec_module(b)\n"
+        "peaks = dict(hbm=6000.0, tf_burst=1600.0, tf_sustained=1400.0, source='measured')\n"
+        "conv = dict(kernel='spconv_tc[27x64->64]', tflops=400.0, gbs=1100.0, avg_launch_ms=0.3,\n"
+        "            bytes_per_launch=350e6, flops_per_launch=126e9)\n"
+        "thin = dict(kernel='spconv_tc[27x16->16]', tflops=7.0, gbs=650.0, avg_launch_ms=0.07,\n"
+        "            bytes_per_launch=48e6, flops_per_launch=0.55e9)\n"
+        "b.emit([b.roofline_of(conv, peaks), b.roofline_of(thin, peaks)])\n") % os.path.join(ROOT, "bench.py")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    conv, thin = json.loads(r.stdout.strip().splitlines()[-1])
+    assert conv["bound"] == "tensor" and conv["peak"] == 1600.0 and abs(conv["frac"] - 0.25) < 1e-9
+    assert abs(conv["frac_of_sustained_peak"] - 400.0 / 1400.0) < 1e-9 and conv["unit"] == "TFLOP/s"
+    assert thin["bound"] == "hbm" and thin["peak"] == 6000.0 and abs(thin["frac"] - 650.0 / 6000.0) < 1e-9
+
+
 def test_rulebook_buffer_layout():
     """Rulebook.alloc: row stride padded to whole 128-row tiles (the conv bulk-copies 512-byte rows)."""
     from uni3detr_b200 import ops
