@@ -286,8 +286,8 @@ class Uni3DETRHead(nn.Module):
         if pp is None:
             return boxes, scores, labels, keep
         if pp["type"] != "nms":
-            raise NotImplementedError(f"post_processing type {pp['type']!r}: soft_nms / box_merging are "
-                                      "CPU post-processing outside the device path (SURVEY.md 2.1 rows 5,12)")
+            raise NotImplementedError(f"post_processing type {pp['type']!r}: box_merging runs host-side through "
+                                      "get_bboxes (like the reference); soft_nms is not built (SURVEY.md 2.1 rows 5,12)")
         # class-major, score-descending order inside a class (the reference's output order);
         # rows the coder dropped sort to the end
         B, M = scores.shape
@@ -317,10 +317,54 @@ class Uni3DETRHead(nn.Module):
         return boxes, scores, labels, keep
 
     @torch.no_grad()
+    def _get_bboxes_box_merging(self, preds_dicts, img_metas):
+        """post_processing type 'box_merging' (uni3detr_kitti_3classes.py:115-117; uni3detr_head.py:881-914):
+        device-resident decode + bottom-centre shift, then - exactly like the reference, which calls
+        `.cpu().numpy()` here - the greedy median merge on the host (plugin/box_merging.py), the per-class
+        `score_thr` list and `num_thr`."""
+        from . import box_merging as BM
+        pp = self.post_processing
+        boxes, scores, labels, keep = self.bbox_coder.decode_fixed(preds_dicts)
+        boxes = boxes.clone()
+        boxes[..., 2] = boxes[..., 2] - boxes[..., 5] * 0.5
+        if boxes.shape[-1] != 7:
+            raise NotImplementedError("box_merging: the reference's corner routine takes 7-value boxes only")
+        dev = boxes.device
+        ret = []
+        for i in range(boxes.shape[0]):
+            k = keep[i]
+            cl, bx, sc, _ = BM.nms_boxes_3d_merge_only(labels[i][k].cpu().numpy(), boxes[i][k].float().cpu().numpy(),
+                                                       scores[i][k].float().cpu().numpy(), overlapped_thres=0.1)
+            if "score_thr" in pp:
+                thr = pp["score_thr"]
+                if isinstance(thr, (list, tuple)):
+                    assert len(thr) == self.num_classes
+                    ind = np.zeros(len(sc), bool)
+                    for j in range(self.num_classes):
+                        ind |= (cl == j) & (sc > thr[j])
+                else:
+                    ind = sc > thr
+                cl, bx, sc = cl[ind], bx[ind], sc[ind]
+            if "num_thr" in pp:
+                ind = np.argsort(-sc)[: pp["num_thr"]]
+                cl, bx, sc = cl[ind], bx[ind], sc[ind]
+            bboxes = torch.from_numpy(np.ascontiguousarray(bx)).to(dev)
+            meta = img_metas[i] if img_metas is not None and i < len(img_metas) else {}
+            box_type = meta.get("box_type_3d") if isinstance(meta, dict) else None
+            if box_type is not None:
+                bboxes = box_type(bboxes, bboxes.shape[-1])
+            ret.append([bboxes, torch.from_numpy(np.ascontiguousarray(sc)).to(dev),
+                        torch.from_numpy(np.ascontiguousarray(cl)).to(dev)])
+        return ret
+
+    @torch.no_grad()
     def get_bboxes(self, preds_dicts, img_metas, rescale=False):
         """Reference API (uni3detr_head.py:827-918): list over scenes of [bboxes, scores, labels].
         post_processing None / 'nms' run on the device (:meth:`postprocess_fixed`); the only host
         round trip is the final compaction to exact-size tensors."""
+        pp = self.post_processing
+        if pp is not None and pp["type"] == "box_merging":
+            return self._get_bboxes_box_merging(preds_dicts, img_metas)
         boxes, scores, labels, keep = self.postprocess_fixed(preds_dicts)
         ret = []
         for i in range(boxes.shape[0]):
