@@ -5,10 +5,12 @@ hot path: `LoadPointsFromFile`, `PointsRangeFilter`, `Po
 projects/configs/uni3detr/uni3detr_sunrgbd.py:175-191 (and uni3detr_scannet_large.py, which loads 6 dims
 and uses 3).
 
-PARITY STATUS: **unpinned by the reference**. The transforms are mmdet3d v1.0.0rc5 classes
-(mmdet3d/datasets/pipelines/loading.py, transforms_3d.py), not vendored and not installable here; they
-are restated from the published source. The one numerically delicate step, `np.percentile(z, 0.99)`
-behind `shift_height`, is numpy's own function and is called as such.
+PARITY STATUS: `LoadPointsFromFile` and `PointsRangeFilter` are **unpinned by the reference** (mmdet3d
+v1.0.0rc5 classes, mmdet3d/datasets/pipelines/loading.py, transforms_3d.py: not vendored, not installable
+here; restated from the published source; `np.percentile(z, 0.99)` behind `shift_height` is numpy's own
+function and is called as such). `PointSample` is **pinned**: the reference carries a first-party copy of the
+class (projects/mmdet3d_plugin/models/detectors/uni3detr.py:50-111) and tests/golden/make_golden_pipeline.py
+stores its choices under fixed legacy numpy seeds (tests/test_prestage.py).
 """
 import numpy as np
 
@@ -40,7 +42,9 @@ def range_filter(points, pc_range):
 
 
 def sample_choices(n_points, num_samples, rng):
-    """PointSample._points_random_sampling: replace only when there are fewer points than samples."""
+    """PointSample._points_random_sampling (uni3detr.py:67-111 / mmdet3d transforms_3d.py) with
+    sample_range=None: replace only when there are fewer points than samples. `rng`: a numpy Generator or a
+    legacy RandomState (the reference draws from the global legacy stream, np.random.choice)."""
     replace = n_points < num_samples
     return rng.choice(n_points, num_samples, replace=replace)
 

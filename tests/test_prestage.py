@@ -53,6 +53,16 @@ def test_oracle_point_sample_semantics():
     np.testing.assert_array_equal(P.point_sample(pts, [4, 0, 4]), pts[[4, 0, 4]])
 
 
+def test_oracle_point_sample_matches_the_reference_class():
+    """Golden choices drawn by the reference's own PointSample class (first-party copy in uni3detr.py:50-111)
+    under legacy numpy seeds == the oracle's restatement fed with the same legacy stream."""
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_point_sample.npz")))
+    for ci in range(4):
+        n, num, seed = int(g[f"c{ci}_n"]), int(g[f"c{ci}_num"]), int(g[f"c{ci}_seed"])
+        got = P.sample_choices(n, num, np.random.RandomState(seed))
+        np.testing.assert_array_equal(got, g[f"c{ci}_choices"])
+
+
 def test_prestage_parses_the_reference_pipeline():
     from uni3detr_b200.prestage import PointsPreStage
     pre = PointsPreStage(SUNRGBD_TEST_PIPELINE)

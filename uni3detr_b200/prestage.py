@@ -42,7 +42,9 @@ class PointsPreStage:
                 raise NotImplementedError("PointsPreStage: multi-sweep loading is a next row (SURVEY.md 8f)")
         if self.load_dim is None:
             raise ValueError("PointsPreStage: the pipeline has no LoadPointsFromFile entry")
-        self.rng = np.random.default_rng(seed)
+        # the reference draws PointSample's indices from numpy's global legacy stream: a RandomState seeded the
+        # same way reproduces its choices (tests/golden/golden_point_sample.npz)
+        self.rng = np.random.RandomState(seed)
 
     @property
     def channels(self):
