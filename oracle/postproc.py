@@ -6,8 +6,11 @@ projects/mmdet3d_plugin/models/dense_heads/uni3detr_head.py:827-918 for
 post_processing.type == 'nms' (per-class mmcv nms3d at :847-871, score_thr :895-908, num_thr :910-914).
 
 PARITY STATUS: the first-party control flow (bottom-centre shift, per-class loop, class-major output
-order, thresholds) is restated line by line; mmcv.ops.nms3d itself (iou3d_nms3d_forward) is third-party
-and not vendored - **unpinned by the reference**. It is restated from its published algorithm: sort by
+order, score_thr scalar / per-class list, num_thr) is **pinned**: tests/golden/make_golden_getbboxes.py runs
+the reference's OWN get_bboxes + NMSFreeCoder.decode (golden_get_bboxes.npz) and
+tests/test_oracle_golden.py::test_get_bboxes_nms_control_flow checks get_bboxes_nms against it.
+mmcv.ops.nms3d itself (iou3d_nms3d_forward) is third-party and not vendored - **unpinned by the reference**
+(the golden run uses this file's nms3d in its place). It is restated from its published algorithm: sort by
 score (descending), rotated-rectangle BEV IoU over (x, y, dx, dy, heading), greedy suppression of boxes
 with IoU > threshold. The IoU here is the exact polygon-intersection area (float64 clipping), checked
 against closed-form cases in tests/test_oracle.py.

@@ -4,6 +4,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from conftest import GOLDEN
@@ -174,3 +175,26 @@ def test_encoder_layer_construction(model_cfgs):
                 assert c["conv_type"] == "SparseConv3d" and M._t3(c["k"]) == (1, 1, 1)
             else:
                 assert c["conv_type"] == "SubMConv3d"
+
+
+GB_CASES = [dict(type="nms", nms_thr=0.5), dict(type="nms", nms_thr=0.3, score_thr=0.2),
+            dict(type="nms", nms_thr=0.5, score_thr=[0.1, 0.3, 0.2, 0.25], num_thr=15),
+            dict(type="nms", nms_thr=0.2, num_thr=20)]
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_get_bboxes_nms_control_flow(case):
+    """uni3detr_head.py:826-918 executed from the reference's own file (tests/golden/make_golden_getbboxes.py;
+    mmcv nms3d stubbed by the oracle's) vs oracle/postproc.py get_bboxes_nms: bottom-centre shift, per-class
+    loop, class-major order, score_thr (scalar / per-class list), num_thr."""
+    from oracle import postproc as PP
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_get_bboxes.npz")))
+    pp = GB_CASES[case]
+    pc = [-3.2, -0.2, -2.0, 3.2, 6.2, 0.56]
+    outs = {k: T(g[f"c{case}_{k}"]) for k in ("all_cls_scores", "all_bbox_preds", "all_iou_preds")}
+    dec = M.nms_free_decode(outs, dict(num_classes=4, alpha=0.2, post_center_range=pc, max_num=40))
+    for i, d in enumerate(dec):
+        b, s, l = PP.get_bboxes_nms({k: v.numpy() for k, v in d.items()}, 4, pp)
+        np.testing.assert_array_equal(l, g[f"c{case}_s{i}_labels"])
+        np.testing.assert_allclose(s, g[f"c{case}_s{i}_scores"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(b, g[f"c{case}_s{i}_bboxes"], rtol=0, atol=1e-5)
