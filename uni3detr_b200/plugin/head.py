@@ -286,8 +286,8 @@ class Uni3DETRHead(nn.Module):
         if pp is None:
             return boxes, scores, labels, keep
         if pp["type"] != "nms":
-            raise NotImplementedError(f"post_processing type {pp['type']!r}: box_merging runs host-side through "
-                                      "get_bboxes (like the reference); soft_nms is not built (SURVEY.md 2.1 rows 5,12)")
+            raise NotImplementedError(f"post_processing type {pp['type']!r}: box_merging / soft_nms are greedy "
+                                      "sequential loops that run host-side through get_bboxes (like the reference)")
         # class-major, score-descending order inside a class (the reference's output order);
         # rows the coder dropped sort to the end
         B, M = scores.shape
@@ -317,12 +317,16 @@ class Uni3DETRHead(nn.Module):
         return boxes, scores, labels, keep
 
     @torch.no_grad()
-    def _get_bboxes_box_merging(self, preds_dicts, img_metas):
-        """post_processing type 'box_merging' (uni3detr_kitti_3classes.py:115-117; uni3detr_head.py:881-914):
-        device-resident decode + bottom-centre shift, then - exactly like the reference, which calls
-        `.cpu().numpy()` here - the greedy median merge on the host (plugin/box_merging.py), the per-class
-        `score_thr` list and `num_thr`."""
+    def _get_bboxes_host(self, preds_dicts, img_metas):
+        """post_processing types whose core is a greedy, data-dependent sequential loop, run on the host:
+        'box_merging' (uni3detr_kitti_3classes.py:115-117; uni3detr_head.py:881-892) - exactly like the
+        reference, which calls `.cpu().numpy()` here - the same-class median merge of plugin/box_merging.py;
+        'soft_nms' (the commented alternative of every config; uni3detr_head.py:795-823, :862-867) - per class,
+        Gaussian score decay by 3-D IoU (plugin/soft_nms.py), class-major output like the 'nms' branch.
+        Device-resident decode + bottom-centre shift before, `score_thr` (scalar or per-class list) and
+        `num_thr` (:895-914) after."""
         from . import box_merging as BM
+        from . import soft_nms as SN
         pp = self.post_processing
         boxes, scores, labels, keep = self.bbox_coder.decode_fixed(preds_dicts)
         boxes = boxes.clone()
@@ -333,8 +337,23 @@ class Uni3DETRHead(nn.Module):
         ret = []
         for i in range(boxes.shape[0]):
             k = keep[i]
-            cl, bx, sc, _ = BM.nms_boxes_3d_merge_only(labels[i][k].cpu().numpy(), boxes[i][k].float().cpu().numpy(),
-                                                       scores[i][k].float().cpu().numpy(), overlapped_thres=0.1)
+            l_np, b_np = labels[i][k].cpu().numpy(), boxes[i][k].float().cpu().numpy()
+            s_np = scores[i][k].float().cpu().numpy()
+            if pp["type"] == "box_merging":
+                cl, bx, sc, _ = BM.nms_boxes_3d_merge_only(l_np, b_np, s_np, overlapped_thres=0.1)
+            else:
+                ob, os_, ol = [], [], []
+                for j in range(self.num_classes):
+                    ind = l_np == j
+                    if not ind.any():
+                        continue
+                    sel, soft = SN.soft_nms(b_np[ind][:, :7], s_np[ind], pp["gaussian_sigma"], pp["prune_threshold"])
+                    ob.append(b_np[ind][sel])
+                    os_.append(soft.astype(np.float32))
+                    ol.extend([j] * len(sel))
+                bx = np.concatenate(ob) if ob else np.zeros((0, b_np.shape[1]), np.float32)
+                sc = np.concatenate(os_) if os_ else np.zeros(0, np.float32)
+                cl = np.asarray(ol, np.int64)
             if "score_thr" in pp:
                 thr = pp["score_thr"]
                 if isinstance(thr, (list, tuple)):
@@ -363,8 +382,8 @@ class Uni3DETRHead(nn.Module):
         post_processing None / 'nms' run on the device (:meth:`postprocess_fixed`); the only host
         round trip is the final compaction to exact-size tensors."""
         pp = self.post_processing
-        if pp is not None and pp["type"] == "box_merging":
-            return self._get_bboxes_box_merging(preds_dicts, img_metas)
+        if pp is not None and pp["type"] in ("box_merging", "soft_nms"):
+            return self._get_bboxes_host(preds_dicts, img_metas)
         boxes, scores, labels, keep = self.postprocess_fixed(preds_dicts)
         ret = []
         for i in range(boxes.shape[0]):
