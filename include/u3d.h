@@ -50,6 +50,9 @@ extern "C" {
 
 const char* u3d_last_error(void);
 int u3d_version(void);
+/* "U3D_BUILD_ID=<16 hex>": hash of the sources the binary was built from; the Python loader
+ * (uni3detr_b200/_lib.py) refuses a library whose id differs from the sources beside it */
+const char* u3d_build_id(void);
 /* number of CUDA kernels this library has launched in this process (host-side counter) */
 unsigned long long u3d_launch_count(void);
 

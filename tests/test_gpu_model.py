@@ -17,6 +17,15 @@ def relerr(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+def close_frac(a, b, rtol, atol_rel):
+    """Elementwise companion of `relerr` (the max-norm hides per-element error on small activations):
+    fraction of elements with |a-b| <= atol + rtol*|b|, atol = atol_rel * rms(b)."""
+    a = a.detach().float().cpu()
+    b = torch.as_tensor(b).detach().float().cpu()
+    atol = atol_rel * float(b.pow(2).mean().sqrt())
+    return float(((a - b).abs() <= atol + rtol * b.abs()).float().mean())
+
+
 def build(workload):
     from uni3detr_b200 import synth
     model, cfg = synth.build_model(workload, seed=0)
@@ -68,8 +77,15 @@ def test_sunrgbd_full_forward_fp32_and_bf16():
     e_enc, e_neck = relerr(cap16["encoder"], inter["encoder"]), relerr(cap16["neck"], inter["neck"])
     errs = {k: relerr(outs16[k], ref_outs[k]) for k in outs16}
     print("bf16 relerr: encoder %.4f neck %.4f heads %s" % (e_enc, e_neck, errs))
-    assert e_enc < 1e-2 and e_neck < 2e-2
+    # north_star: 1e-2 bf16 for features (encoder, neck) and box regressions
+    assert e_enc < 1e-2 and e_neck < 1e-2
     assert errs["all_bbox_preds"] < 1e-2 and errs["all_cls_scores"] < 3e-2 and errs["all_iou_preds"] < 3e-2
+    # elementwise: |a-b| <= 1e-2*|b| + 1e-2*rms(b) nearly everywhere (not only in the max-norm)
+    fr = {"encoder": close_frac(cap16["encoder"], inter["encoder"], 1e-2, 1e-2),
+          "neck": close_frac(cap16["neck"], inter["neck"], 1e-2, 1e-2),
+          "bbox": close_frac(outs16["all_bbox_preds"], ref_outs["all_bbox_preds"], 1e-2, 1e-2)}
+    print("bf16 elementwise close fraction:", fr)
+    assert fr["encoder"] > 0.999 and fr["neck"] > 0.995 and fr["bbox"] > 0.99, fr
 
 
 @pytest.mark.parametrize("workload,npts", [("scannet_large", 6000), ("kitti", 6000), ("nuscenes", 8000)])
@@ -91,6 +107,52 @@ def test_other_configs_encoder_and_decoder_fp32(workload, npts):
     for k in ("all_cls_scores", "all_bbox_preds", "all_iou_preds"):
         assert tuple(outs[k].shape) == tuple(ref_outs[k].shape)
         assert relerr(outs[k], ref_outs[k]) < 1e-3, (k, relerr(outs[k], ref_outs[k]))
+
+
+FULL = {"scannet_large": (torch.float32,), "kitti": (torch.float32, torch.bfloat16), "nuscenes": (torch.float32,)}
+
+
+@pytest.mark.parametrize("workload", ["scannet_large", "kitti", "nuscenes"])
+def test_full_size_configs_vs_oracle(workload):
+    """BASELINE configs 3-5 at their STATED sizes (ScanNet-large 100k pts fp32, KITTI 20k pts L=9 in
+    fp32 AND bf16, nuScenes 200k pts 900 queries fp32), one scene:
+      * sparse half (voxelize -> VFE -> 21 sparse convs -> dense(), both FPS calls) against the oracle
+        at full size - coordinates / FPS picks exact, encoder 1e-3 fp32 / 1e-2 bf16;
+      * dense CNN (SECOND3D + SECOND3DFPN) on a 40x40 (H,W) crop of the product's own encoder volume
+        against the oracle's dense CNN on the same crop (the full volume is minutes of CPU);
+      * decoder + heads at full size against the oracle fed with the product's neck volume."""
+    from uni3detr_b200 import synth
+    model, cfg = build(workload)
+    nq = cfg["pts_bbox_head"]["num_query"]
+    scenes = [synth.make_scene(workload, 0)]
+    assert len(scenes[0]) == synth.WORKLOADS[workload]["n_points"]
+    rp = torch.rand(1, nq, 3, generator=torch.Generator().manual_seed(8))
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    _, ref_fps, inter = M.forward(sd, cfg, scenes, random_point=rp, stop_after="encoder")
+    for dtype in FULL[workload]:
+        tol = 1e-3 if dtype == torch.float32 else 1e-2
+        outs, fps, cap = run_product(model, scenes, rp, dtype)
+        check_geometry(cap, inter, fps, ref_fps)
+        e = relerr(cap["encoder"], inter["encoder"])
+        assert e < tol, (workload, dtype, "encoder", e)
+        assert close_frac(cap["encoder"], inter["encoder"], tol, tol) > 0.999
+        # dense CNN on a crop (the modules are fully convolutional in H, W)
+        enc = cap["encoder"]
+        h0, w0 = enc.shape[3] // 2 - 20, enc.shape[4] // 2 - 20
+        crop = enc[:, :, :, h0:h0 + 40, w0:w0 + 40]
+        neck = model.pts_neck(model.pts_backbone(crop.contiguous(memory_format=torch.channels_last_3d)))
+        ref_crop = crop.float().cpu().contiguous()
+        ref_neck = M.second3dfpn(sd, cfg["pts_neck"], M.second3d(sd, cfg["pts_backbone"], ref_crop))
+        e = relerr(neck, ref_neck)
+        assert e < tol, (workload, dtype, "neck", e)
+        # decoder + heads, full-size volume and query count
+        ref_outs = M.head_forward(sd, cfg["pts_bbox_head"], cap["neck"].float().cpu().contiguous(), ref_fps, rp)
+        for k in ("all_cls_scores", "all_bbox_preds", "all_iou_preds"):
+            assert tuple(outs[k].shape) == tuple(ref_outs[k].shape)
+            e = relerr(outs[k], ref_outs[k])
+            lim = tol if (dtype == torch.float32 or k == "all_bbox_preds") else 3e-2
+            print(workload, dtype, k, "relerr %.2e" % e)
+            assert e < lim, (workload, dtype, k, e)
 
 
 def test_reference_call_convention():

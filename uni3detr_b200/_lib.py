@@ -27,12 +27,33 @@ def so_path():
     return _SO
 
 
-def _stale():
+def source_hash():
+    """sha256 over every CUDA source, header and the compiler flags: the library's build id. It is
+    compiled into the .so (u3d_build_id()), so a binary is recognised as stale - or as built from a
+    different ABI - by content, not by file times (snapshots onto a GPU box do not keep mtimes)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in [os.path.join(_CSRC, s) for s in _SOURCES] + _HEADERS:
+        with open(d, "rb") as f:
+            h.update(os.path.basename(d).encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
+def _so_build_id():
+    """Build id of the library on disk, read from the file (no dlopen): the marker string
+    'U3D_BUILD_ID=<hash>' that csrc/voxmap.cu embeds."""
     if not os.path.exists(_SO):
-        return True
-    t = os.path.getmtime(_SO)
-    deps = [os.path.join(_CSRC, s) for s in _SOURCES] + _HEADERS
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+        return None
+    with open(_SO, "rb") as f:
+        blob = f.read()
+    i = blob.find(b"U3D_BUILD_ID=")
+    if i < 0:
+        return None
+    return blob[i + 13:i + 29].decode("ascii", "replace")
+
+
+def _stale():
+    return _so_build_id() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -49,7 +70,8 @@ def build(force=False, verbose=False):
                 return _SO
             nvcc = os.environ.get("NVCC", "nvcc")
             tmp = _SO + ".tmp.%d" % os.getpid()
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+            cmd = [nvcc] + NVCC_FLAGS + ["-DU3D_BUILD_ID_STR=\"%s\"" % source_hash()] + \
+                (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
                 [os.path.join(_CSRC, s) for s in _SOURCES]
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
@@ -68,6 +90,7 @@ _vp, _i32, _f32, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_s
 SIGNATURES = {
     "u3d_last_error": (ctypes.c_char_p, []),
     "u3d_version": (_i32, []),
+    "u3d_build_id": (ctypes.c_char_p, []),
     "u3d_launch_count": (ctypes.c_ulonglong, []),
     "u3d_voxmap_words": (_sz, [_i32] * 4),
     "u3d_scan_scratch_ints": (_sz, [_sz]),
@@ -115,14 +138,21 @@ def load():
         if _lib is not None:
             return _lib
         if _stale():
+            # no silent fallback and no stale binary: a library built from other sources may export the
+            # same names with different argument lists, so a failed rebuild is fatal even if an old
+            # .so is still on disk
             try:
                 build()
-            except Exception as e:  # no silent fallback: the CUDA library IS the product
-                if not os.path.exists(_SO):
-                    raise RuntimeError(
-                        "libu3d_b200.so is missing and could not be built; "
-                        "run `python -c 'import __graft_entry__ as g; g.build()'`") from e
+            except Exception as e:
+                raise RuntimeError(
+                    "libu3d_b200.so is missing or was built from different sources (build id "
+                    f"{_so_build_id()} != {source_hash()}) and could not be rebuilt; "
+                    "run `python -c 'import __graft_entry__ as g; g.build()'`") from e
         lib = ctypes.CDLL(_SO)
+        lib.u3d_build_id.restype = ctypes.c_char_p
+        bid = lib.u3d_build_id().decode()
+        if bid != "U3D_BUILD_ID=" + source_hash():
+            raise RuntimeError(f"libu3d_b200.so build id {bid} does not match the sources ({source_hash()})")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the header and library diverge
             fn.restype = res

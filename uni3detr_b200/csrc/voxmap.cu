@@ -116,7 +116,13 @@ int voxmap_scan(uint2* map, size_t words, int32_t* scratch, int32_t* total_out, 
 extern "C" {
 
 const char* u3d_last_error(void) { return u3d::g_err; }
-int u3d_version(void) { return 100; }
+int u3d_version(void) { return 200; }
+#ifndef U3D_BUILD_ID_STR
+#define U3D_BUILD_ID_STR "unversioned-----"
+#endif
+// sha256 prefix of the sources this binary was built from (uni3detr_b200/_lib.py source_hash());
+// the loader refuses a library whose id differs from the sources next to it
+const char* u3d_build_id(void) { return "U3D_BUILD_ID=" U3D_BUILD_ID_STR; }
 unsigned long long u3d_launch_count(void) { return u3d::g_launches.load(std::memory_order_relaxed); }
 
 size_t u3d_voxmap_words(int B, int D, int H, int W) {

@@ -56,8 +56,13 @@ class GraphedForward:
         """host_points: (Ntot,C) f32 (pinned for an async copy) -> static device buffer."""
         self.points.copy_(host_points, non_blocking=True)
 
-    def run(self, host_points=None):
+    def run(self, host_points=None, redraw_random_group=False):
+        """redraw_random_group=True refills the reference points of the random 4th query group in place
+        before the replay (the reference draws `torch.rand` on every forward, uni3detr_head.py:445-447);
+        the default keeps them fixed so repeated runs are reproducible."""
         if host_points is not None:
             self.load(host_points)
+        if redraw_random_group:
+            self.random_point.uniform_()
         self.graph.replay()
         return self.outputs

@@ -271,6 +271,15 @@ class Uni3DETRHead(nn.Module):
         raise NotImplementedError("Uni3DETRHead.loss (Hungarian matching + SoftFocal/IoU3D losses) "
                                   "is a 'next' row, SURVEY.md 8f rank 3")
 
+    def _score_thr(self, thr, like):
+        """Per-class score_thr list as a device tensor, cached per (device, dtype): building it inside a
+        step would be a pageable host-to-device copy (a sync, and illegal during graph capture)."""
+        key = (like.device, like.dtype, tuple(float(t) for t in thr))
+        cache = self.__dict__.setdefault("_thr_cache", {})
+        if key not in cache:
+            cache[key] = torch.tensor(key[2], dtype=like.dtype, device=like.device)
+        return cache[key]
+
     @torch.no_grad()
     def postprocess_fixed(self, preds_dicts):
         """Device-resident get_bboxes (uni3detr_head.py:827-918) for post_processing None / 'nms':
@@ -303,7 +312,7 @@ class Uni3DETRHead(nn.Module):
             thr = pp["score_thr"]
             if isinstance(thr, (list, tuple)):
                 assert len(thr) == self.num_classes
-                keep = keep & (scores > scores.new_tensor(thr)[labels.clamp(max=self.num_classes - 1)])
+                keep = keep & (scores > self._score_thr(thr, scores)[labels.clamp(max=self.num_classes - 1)])
             else:
                 keep = keep & (scores > thr)
         if "num_thr" in pp:
@@ -331,7 +340,7 @@ class Uni3DETRHead(nn.Module):
         boxes, scores, labels, keep = self.bbox_coder.decode_fixed(preds_dicts)
         boxes = boxes.clone()
         boxes[..., 2] = boxes[..., 2] - boxes[..., 5] * 0.5
-        if boxes.shape[-1] != 7:
+        if pp["type"] == "box_merging" and boxes.shape[-1] != 7:
             raise NotImplementedError("box_merging: the reference's corner routine takes 7-value boxes only")
         dev = boxes.device
         ret = []

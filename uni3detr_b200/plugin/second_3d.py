@@ -28,9 +28,11 @@ def _norm(norm_cfg, ch):
     return nn.BatchNorm3d(ch, eps=norm_cfg.get("eps", 1e-5), momentum=norm_cfg.get("momentum", 0.1))
 
 
-def _fold(conv_w, bn, transposed=False):
+def _fold(conv_w, bn, transposed=False, conv_bias=None):
     scale = bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)
     shift = bn.bias.float() - bn.running_mean.float() * scale
+    if conv_bias is not None:      # conv_cfg / upsample_cfg / extra_conv with bias=True
+        shift = shift + conv_bias.float() * scale
     w = conv_w.float()
     w = w * (scale.view(1, -1, 1, 1, 1) if transposed else scale.view(-1, 1, 1, 1, 1))
     return w, shift
@@ -41,7 +43,8 @@ class _FoldedConv:
 
     def __init__(self, conv, bn, dtype, as2d):
         transposed = isinstance(conv, nn.ConvTranspose3d)
-        w, b = _fold(conv.weight.detach(), bn, transposed)
+        w, b = _fold(conv.weight.detach(), bn, transposed,
+                     conv.bias.detach() if conv.bias is not None else None)
         self.transposed = transposed
         self.stride, self.padding = conv.stride, conv.padding
         self.b = b.to(dtype).contiguous()

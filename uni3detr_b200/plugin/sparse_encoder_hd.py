@@ -85,17 +85,36 @@ def make_sparse_convmodule(in_channels, out_channels, kernel_size, indice_key, s
 
 
 class SparseBasicBlock(nn.Module):
-    """mmdet3d.ops.SparseBasicBlock: conv1-norm1-relu-conv2-norm2-(+identity)-relu, SubM 3^3."""
+    """mmdet3d.ops.SparseBasicBlock: conv1-norm1-relu-conv2-norm2-(+identity)-relu, SubM 3^3.
+
+    Upstream inherits mmdet's ``BasicBlock``, which registers its norm layers under the names
+    ``build_norm_layer(..., postfix=i)`` returns - ``bn1`` / ``bn2`` for BN - and exposes ``norm1`` /
+    ``norm2`` only as properties, so reference checkpoints carry ``...bn1.weight`` etc. Same here;
+    state dicts written with the ``norm{1,2}.`` spelling are remapped on load."""
 
     def __init__(self, inplanes, planes, norm_cfg=None, conv_cfg=None):
         super().__init__()
         norm_cfg = norm_cfg or dict(type="BN1d", eps=1e-3, momentum=0.01)
         eps, mom = norm_cfg.get("eps", 1e-5), norm_cfg.get("momentum", 0.1)
         self.conv1 = SubMConv3d(inplanes, planes, 3, padding=1, bias=False)
-        self.norm1 = nn.BatchNorm1d(planes, eps=eps, momentum=mom)
+        self.bn1 = nn.BatchNorm1d(planes, eps=eps, momentum=mom)
         self.conv2 = SubMConv3d(planes, planes, 3, padding=1, bias=False)
-        self.norm2 = nn.BatchNorm1d(planes, eps=eps, momentum=mom)
+        self.bn2 = nn.BatchNorm1d(planes, eps=eps, momentum=mom)
         self.relu = nn.ReLU(inplace=True)
+
+    @property
+    def norm1(self):
+        return self.bn1
+
+    @property
+    def norm2(self):
+        return self.bn2
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for old, new in (("norm1.", "bn1."), ("norm2.", "bn2.")):
+            for key in [k for k in state_dict if k.startswith(prefix + old)]:
+                state_dict.setdefault(prefix + new + key[len(prefix + old):], state_dict.pop(key))
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
 
 def _fold_bn(bn, conv_bias=None):
