@@ -511,11 +511,9 @@ def test_bias_act_sum(dtype, tol):
     assert relerr(y1, F.relu(xs[0].float() + bs[1])) < tol
 
 
-@pytest.mark.skipif(__import__("os").environ.get("U3D_EXPERIMENTAL") != "1",
-                    reason="grouped tile sort has not run on hardware yet: set U3D_EXPERIMENTAL=1")
 @pytest.mark.parametrize("B,per_group", [(4, 1), (5, 2), (3, 8)])
 def test_rulebook_sort_tiles_grouped(B, per_group):
-    """EXPERIMENTAL: signature buckets kept inside groups of consecutive scenes: slot_row permutes every
+    """Signature buckets kept inside groups of consecutive scenes: slot_row permutes every
     group's row range onto itself, keys are sorted inside a group, table / masks as in the global variant."""
     from uni3detr_b200 import ops
     dims, n = (8, 24, 24), 9000
@@ -536,11 +534,9 @@ def test_rulebook_sort_tiles_grouped(B, per_group):
     np.testing.assert_array_equal(srt[:, :n].cpu().numpy(), nat[:, slot_row])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("U3D_EXPERIMENTAL") != "1",
-                    reason="MN-major V attention variant has not run on hardware yet: set U3D_EXPERIMENTAL=1")
 @pytest.mark.parametrize("seq_len,n_seq", [(300, 8), (900, 2), (5, 4), (129, 1)])
 def test_mha_core_v_mn_major(seq_len, n_seq, monkeypatch):
-    """EXPERIMENTAL: U3D_MHA_VMN=1 stages V untransposed and uses an MN-major B operand for O = P V."""
+    """U3D_MHA_VMN=1 stages V untransposed and uses an MN-major B operand for O = P V."""
     from uni3detr_b200 import ops
     monkeypatch.setenv("U3D_MHA_VMN", "1")
     g = torch.Generator().manual_seed(seq_len)

@@ -1,9 +1,8 @@
-"""Input pre-stage (EXPERIMENTAL in round 1).
+"""Input pre-stage (validated on hardware in round 2).
 
 CPU part: the oracle restatement of LoadPointsFromFile / PointsRangeFilter / PointSample against
 hand-computed cases and numpy, and the host-side parsing of the reference's `test_pipeline` dicts.
-GPU part: csrc/points.cu vs the oracle - gated behind U3D_EXPERIMENTAL=1 because the kernels were
-written after the round's GPU budget was spent and have not run on hardware yet."""
+GPU part: csrc/points.cu vs the oracle (bit-exact rows / offsets, 1e-6 floor height)."""
 import os
 
 import numpy as np
@@ -12,7 +11,6 @@ import torch
 
 from oracle import pipeline as P
 
-EXPERIMENTAL = os.environ.get("U3D_EXPERIMENTAL") == "1"
 PCR = [-3.2, -0.2, -2.0, 3.2, 6.2, 0.56]
 SUNRGBD_TEST_PIPELINE = [   # projects/configs/uni3detr/uni3detr_sunrgbd.py:175-191
     dict(type="LoadPointsFromFile", coord_type="DEPTH", shift_height=True, load_dim=6, use_dim=[0, 1, 2]),
@@ -148,7 +146,6 @@ def _raw_scene(n, seed):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not EXPERIMENTAL, reason="csrc/points.cu has not run on hardware yet: set U3D_EXPERIMENTAL=1")
 @pytest.mark.parametrize("sizes", [(20000, 1, 357), (101,), (2, 0, 5000)])
 def test_gpu_points_prepare_vs_oracle(sizes):
     from uni3detr_b200 import ops
@@ -169,7 +166,6 @@ def test_gpu_points_prepare_vs_oracle(sizes):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not EXPERIMENTAL, reason="csrc/points.cu has not run on hardware yet: set U3D_EXPERIMENTAL=1")
 def test_gpu_points_gather():
     from uni3detr_b200 import ops
     pts = torch.randn(1000, 4, device="cuda")
