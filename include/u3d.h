@@ -330,6 +330,41 @@ int u3d_cross_sample(const void* value, int B, int D, int H, int W, int C,
                      void* stream);
 
 /*
+ * Row-wise linear layer with a fused epilogue on tcgen05 (csrc/linear_tc.cu) - every nn.Linear of the
+ * decoder and the heads together with the elementwise kernels the reference runs around it:
+ *     out  = act2( LN( act1(A @ W^T + bias) * mul + res1 + res2 ) )      out2 = out + add2
+ * Replaces: MLP layers (utils/uni3detr_transformer.py:18-30), query_pos = query_scale(x) * ref_point_head(sine)
+ * (:179-186), nn.MultiheadAttention in/out projections + identity + LayerNorm and FFN + identity + LayerNorm of
+ * mmcv BaseTransformerLayer (config uni3detr_sunrgbd.py:76-100), UniCrossAtten.output_proj + residual +
+ * position encoder + LayerNorm (:356-360), the cls / reg / iou branches (dense_heads/uni3detr_head.py:365-400)
+ * and the reference-point refinement (:194-202 of the transformer).
+ *   a (rows, K) bf16, row stride lda elements (lda % 8 == 0), K % 64 == 0
+ *   w_packed: u3d_linear_pack_weights(W (N,K) bf16 = nn.Linear.weight); N <= 256 or N == 512
+ *   bias (N) f32 or NULL; gamma / beta (N) f32 (LayerNorm, N %% 32 == 0 and N <= 256)
+ *   mul, res1, res2, add2, out2: (rows, N) bf16 with row stride ldr; out: (rows, ldo) bf16, or f32 with
+ *   U3D_LIN_OUT_F32 (any N; narrow heads); U3D_LIN_REF: ref_out[r] = ref_in[r] + (v[r][0], v[r][1], v[r][4]).
+ */
+#define U3D_LIN_RELU1 1
+#define U3D_LIN_MUL 2
+#define U3D_LIN_RES1 4
+#define U3D_LIN_RES2 8
+#define U3D_LIN_LN 16
+#define U3D_LIN_RELU2 32
+#define U3D_LIN_OUT2 64
+#define U3D_LIN_OUT_F32 128
+#define U3D_LIN_REF 256
+size_t u3d_linear_packed_bytes(int N, int K);
+int u3d_linear_pack_weights(const void* w, int N, int K, void* packed, void* stream);
+int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed, int N, const float* bias,
+                  int flags, const void* mul, const void* res1, const void* res2, int ldr,
+                  const float* gamma, const float* beta, float eps, const void* add2, void* out2,
+                  void* out, int ldo, const float* ref_in, float* ref_out, void* stream);
+/* relu(LayerNorm(ref @ w^T + b)): Linear(3 -> C) + LN + ReLU, the first stage of UniCrossAtten.position_encoder
+ * (utils/uni3detr_transformer.py:253-260). ref (rows,3) f32, w (C,3) f32, b/gamma/beta (C) f32, C <= 256. */
+int u3d_pos3_ln_relu(const float* ref, const float* w, const float* b, const float* gamma, const float* beta,
+                     float eps, int rows, int C, void* out, int dtype, void* stream);
+
+/*
  * Per-class rotated-BEV-IoU NMS, batched over scenes.
  * Replaces: the per-class python loop over mmcv.ops.nms3d (iou3d_nms3d_forward) in
  * Uni3DETRHead.get_bboxes, models/dense_heads/uni3detr_head.py:847-871.

@@ -550,3 +550,108 @@ def test_mha_core_v_mn_major(seq_len, n_seq, monkeypatch):
     ref = F.scaled_dot_product_attention(split(qk[:, :E]), split(qk[:, E:]), split(v))
     ref = ref.permute(0, 2, 1, 3).reshape(n_seq * seq_len, E)
     assert relerr(out, ref) < 1e-2
+
+
+# ------------------------------------------------------------------ decoder GEMMs (tcgen05) ----
+def _lin_ref(a, W, b, relu=False, mul=None, res1=None, res2=None, ln=None, relu_out=False):
+    """fp32 torch reference of u3d_linear_tc on the same bf16 inputs."""
+    y = a.float() @ W.to(torch.bfloat16).float().t()
+    if b is not None:
+        y = y + b.float()
+    if relu:
+        y = torch.relu(y)
+    if mul is not None:
+        y = y * mul.float()
+    for r in (res1, res2):
+        if r is not None:
+            y = y + r.float()
+    if ln is not None:
+        y = torch.nn.functional.layer_norm(y, (y.shape[1],), ln[0].float(), ln[1].float(), ln[2])
+    if relu_out:
+        y = torch.relu(y)
+    return y
+
+
+@pytest.mark.parametrize("rows,K,N", [(300, 256, 256), (1000, 384, 256), (128 * 149 + 77, 256, 256),
+                                       (513, 512, 256), (700, 256, 512), (129, 64, 32)])
+def test_linear_tc_plain_and_relu(rows, K, N):
+    """out = relu?(A W^T + b): K in {64..512}, N in {32, 256, 512 (two passes)}, ragged last tile,
+    more tiles than SMs (persistent loop + both TMEM accumulators + ring wrap-around)."""
+    from uni3detr_b200 import ops
+    g = torch.Generator().manual_seed(rows + K + N)
+    a = (torch.randn(rows, K, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    lin = ops.PackedLinear(W, b)
+    for relu in (False, True):
+        out = ops.linear_tc(a, lin, relu=relu)
+        ref = _lin_ref(a, W, b, relu=relu)
+        assert out.dtype == torch.bfloat16 and tuple(out.shape) == (rows, N)
+        torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+    # strided A view (column slice of a wider matrix, as the packed QK projection is consumed)
+    wide = torch.zeros(rows, K + 64, dtype=torch.bfloat16, device=DEV)
+    wide[:, 64:] = a
+    out = ops.linear_tc(wide[:, 64:], lin)
+    torch.testing.assert_close(out.float(), _lin_ref(a, W, b), rtol=1e-2, atol=1e-2)
+
+
+def test_linear_tc_fused_epilogues():
+    """Every epilogue stage: multiplier, two residuals, LayerNorm (+ReLU), second output, no bias."""
+    from uni3detr_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    rows, K, N = 128 * 3 + 50, 256, 256
+    bf = lambda *s: (torch.randn(*s, generator=g) * 0.7).to(torch.bfloat16).to(DEV)
+    a, mul, r1, r2, add2 = bf(rows, K), bf(rows, N), bf(rows, N), bf(rows, N), bf(rows, N)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    gamma, beta = (1 + 0.2 * torch.randn(N, generator=g)).to(DEV), (0.3 * torch.randn(N, generator=g)).to(DEV)
+    lin = ops.PackedLinear(W, b, ln=(gamma, beta, 1e-5))
+    out = ops.linear_tc(a, lin, res1=r1, ln=True)                                  # out-proj + identity + LN
+    torch.testing.assert_close(out.float(), _lin_ref(a, W, b, res1=r1, ln=(gamma, beta, 1e-5)), rtol=1e-2, atol=2e-2)
+    out = ops.linear_tc(a, lin, res1=r1, res2=r2, ln=True)                         # cross-attn block
+    torch.testing.assert_close(out.float(), _lin_ref(a, W, b, res1=r1, res2=r2, ln=(gamma, beta, 1e-5)),
+                               rtol=1e-2, atol=2e-2)
+    out = ops.linear_tc(a, lin, ln=True, relu_out=True)                            # Linear-LN-ReLU (cls branch)
+    torch.testing.assert_close(out.float(), _lin_ref(a, W, b, ln=(gamma, beta, 1e-5), relu_out=True),
+                               rtol=1e-2, atol=2e-2)
+    out, out2 = ops.linear_tc(a, lin, mul=mul, add2=add2)                          # query_scale * qpos, x + qpos
+    ref = _lin_ref(a, W, b, mul=mul)
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(out2.float(), out.float() + add2.float(), rtol=1e-2, atol=2e-2)
+    lin0 = ops.PackedLinear(W, None)
+    torch.testing.assert_close(ops.linear_tc(a, lin0, relu=True).float(), _lin_ref(a, W, None, relu=True),
+                               rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("N", [1, 8, 10])
+def test_linear_tc_narrow_fp32_heads(N):
+    """Final cls (10) / reg (8) / iou (1) layers: fp32 output, N padded to 16 inside; the reg variant
+    also emits the refined reference points ref + (v0, v1, v4)."""
+    from uni3detr_b200 import ops
+    g = torch.Generator().manual_seed(20 + N)
+    rows, K = 1000, 256
+    a = (torch.randn(rows, K, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    lin = ops.PackedLinear(W, b)
+    ref = _lin_ref(a, W, b)
+    if N == 8:
+        r_in = torch.randn(rows, 3, generator=g).to(DEV)
+        out, r_out = ops.linear_tc(a, lin, out_f32=True, ref_in=r_in)
+        torch.testing.assert_close(r_out, r_in + torch.stack((out[:, 0], out[:, 1], out[:, 4]), 1), rtol=0, atol=1e-6)
+    else:
+        out = ops.linear_tc(a, lin, out_f32=True)
+    assert out.dtype == torch.float32 and tuple(out.shape) == (rows, N)
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3)
+
+
+def test_pos3_ln_relu():
+    from uni3detr_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    ref = torch.randn(777, 3, generator=g).to(DEV)
+    W, b = torch.randn(256, 3, generator=g).to(DEV), torch.randn(256, generator=g).to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(256, generator=g)).to(DEV), (0.1 * torch.randn(256, generator=g)).to(DEV)
+    want = torch.relu(torch.nn.functional.layer_norm(ref @ W.t() + b, (256,), gamma, beta, 1e-5))
+    torch.testing.assert_close(ops.pos3_ln_relu(ref, W, b, gamma, beta, 1e-5, torch.float32), want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ops.pos3_ln_relu(ref, W, b, gamma, beta, 1e-5, torch.bfloat16).float(), want,
+                               rtol=1e-2, atol=1e-2)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libu3d_b200.so")
 _SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_tn.cu", "tilesort.cu", "points.cu",
-            "fps.cu", "decoder.cu", "mha_tc.cu", "nms.cu"]
+            "fps.cu", "decoder.cu", "mha_tc.cu", "linear_tc.cu", "nms.cu"]
 _HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"),
             os.path.join(_HERE, "..", "include", "u3d.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -124,6 +124,11 @@ SIGNATURES = {
     "u3d_points_gather": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp]),
     "u3d_bias_act_sum": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, ctypes.c_longlong, _i32, _i32, _vp, _vp]),
     "u3d_mha_core": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "u3d_linear_packed_bytes": (_sz, [_i32, _i32]),
+    "u3d_linear_pack_weights": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "u3d_linear_tc": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _f32,
+                             _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "u3d_pos3_ln_relu": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _vp, _i32, _vp]),
     "u3d_nms3d_mask_words": (_sz, [_i32]),
     "u3d_nms3d_bev": (_i32, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp]),
     "u3d_cross_sample": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _i32,

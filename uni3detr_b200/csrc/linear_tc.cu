@@ -1,0 +1,532 @@
+// K7 — dense row-wise linear layer with a fused epilogue on tcgen05: the decoder / head GEMMs.
+//
+//   out = act2( LN( act1(A @ W^T + bias) * mul + res1 + res2 ) ),   out2 = out + add2
+//
+// Reference: every nn.Linear of the DETR decoder and the heads, together with the elementwise
+// work the reference runs as separate kernels around them -
+//   projects/mmdet3d_plugin/models/utils/uni3detr_transformer.py:18-30 (MLP), :179-186 (query_pos =
+//   query_scale(output) * ref_point_head(sine)), :329-360 (UniCrossAtten output_proj + residual +
+//   position encoder), mmcv BaseTransformerLayer (self-attn out-proj + identity + LN,
+//   FFN + identity + LN), projects/mmdet3d_plugin/models/dense_heads/uni3detr_head.py:365-411
+//   (cls / reg / iou branches: Linear-LN-ReLU / Linear-ReLU stacks).
+//
+// One persistent CTA per SM, 128-row tiles, the full output row (N <= 256 per pass) in one fp32
+// TMEM accumulator so that LayerNorm needs no cross-thread reduction:
+//   warp 0   producer (one lane): per 64-wide K chunk one TMA tensor load of the A box
+//            (128 rows x 64 bf16, hardware SWIZZLE_128B, rows beyond the matrix zero-filled) and one
+//            cp.async.bulk of the pre-swizzled (N x 64) weight image; 4-stage mbarrier ring.
+//   warp 1   MMA issue (one lane): K/16 x tcgen05.mma M=128, N<=256 per tile; accumulators
+//            double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps tile i+1.
+//   warps 2-5 epilogue: thread = output row (TMEM lane), tcgen05.ld 32 columns at a time; bias, ReLU,
+//            elementwise multiplier, up to two residual rows; LayerNorm statistics in fp32 over the
+//            row (the pre-norm row is parked back in TMEM with tcgen05.st), second sweep normalises;
+//            bf16 (or fp32 for the narrow final heads) stores, optional second output out + add2
+//            (the next GEMM's A operand, e.g. x + query_pos).
+// N > 256 (in_proj 512, FFN 512) runs as independent 256-column halves.
+#include <cuda.h>
+#include "tc_common.cuh"
+
+namespace u3d {
+namespace lin {
+
+using namespace tc;
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kABytes = kBM * kBK * 2;   // 16 KB per stage
+constexpr int kEpiThreads = 128;
+
+enum : int {
+  F_RELU1 = 1,      // ReLU right after the bias
+  F_MUL = 2,        // * mul[r][c]
+  F_RES1 = 4,
+  F_RES2 = 8,
+  F_LN = 16,
+  F_RELU2 = 32,     // ReLU on the final value
+  F_OUT2 = 64,      // out2 = out + add2
+  F_OUT_F32 = 128,  // fp32 output (narrow heads)
+  F_REF = 256,      // ref_out[r][0..2] = ref_in[r][0..2] + (v0, v1, v4): the decoder's reference refinement
+};
+
+struct Params {
+  int rows, K, n_pass, n_cols;   // n_pass = columns per pass (<= 256, multiple of 16); n_cols = real output columns
+  int n_passes;                  // 1 or 2 (N = n_passes * n_pass)
+  int ldo, ldr;                  // output / residual row strides in elements
+  int flags;
+  float eps;
+  const uint8_t* wpk;            // [pass][K/64] images of (n_pass x 64) bf16, K-major, SWIZZLE_128B
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  const __nv_bfloat16* mul;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  const __nv_bfloat16* add2;
+  __nv_bfloat16* out2;
+  void* out;
+  const float* ref_in;
+  float* ref_out;
+};
+
+struct Smem {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+  float bias[512];
+  float gamma[256];
+  float beta[256];
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 32 consecutive bf16 of a row (64 bytes, 16-byte aligned) added into f[32]
+__device__ __forceinline__ void add_row32(float* f, const __nv_bfloat16* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = __ldg(q + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      f[8 * i + 2 * j] += t.x;
+      f[8 * i + 2 * j + 1] += t.y;
+    }
+  }
+}
+__device__ __forceinline__ void mul_row32(float* f, const __nv_bfloat16* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = __ldg(q + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      f[8 * i + 2 * j] *= t.x;
+      f[8 * i + 2 * j + 1] *= t.y;
+    }
+  }
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16* p, const float* f) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    q[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr uint32_t kHeader = (uint32_t)((sizeof(Smem) + 1023) & ~(size_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (P.rows + kBM - 1) / kBM;
+  const int n_items = n_tiles * P.n_passes;
+  const int KC = P.K / kBK;
+  const uint32_t w_bytes = (uint32_t)P.n_pass * 128u;
+  const uint32_t stage_bytes = (uint32_t)kABytes + w_bytes;
+  const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.acc_full[b], 1);
+      mbar_init(&S.acc_empty[b], kEpiThreads);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // per-column constants of the epilogue -> shared memory (broadcast reads)
+  {
+    const int ntot = P.n_pass * P.n_passes;
+    for (int i = tid; i < ntot; i += kThreads) S.bias[i] = (P.bias && i < P.n_cols) ? __ldg(&P.bias[i]) : 0.f;
+    if (P.flags & F_LN)
+      for (int i = tid; i < P.n_pass; i += kThreads) {
+        S.gamma[i] = __ldg(&P.gamma[i]);
+        S.beta[i] = __ldg(&P.beta[i]);
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    // ======================= producer =======================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+      int slot = 0;
+      uint32_t eph = 1u;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / P.n_passes, pass = item - tile * P.n_passes;
+        const uint8_t* wsrc = P.wpk + (size_t)pass * KC * w_bytes;
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&S.empty[slot], eph);
+          const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
+          mbar_expect_tx(&S.full[slot], stage_bytes);
+          tma_load_2d(st_s, &tmap_a, kc * kBK, tile * kBM, &S.full[slot]);
+          bulk_g2s(st_s + kABytes, wsrc + (size_t)kc * w_bytes, w_bytes, &S.full[slot]);
+          if (++slot == kStages) { slot = 0; eph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      using SW = Swz<64>;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.n_pass >> 3) << 17) |
+                             ((uint32_t)(kBM >> 4) << 24);
+      int slot = 0, t = 0;
+      uint32_t fph = 0u;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
+        const int ab = t & 1;
+        mbar_wait(&S.acc_empty[ab], ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem + (uint32_t)(ab * 256);
+        for (int kc = 0; kc < KC; ++kc) {
+          mbar_wait(&S.full[slot], fph);
+          tc_fence_after();
+          const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
+          const uint64_t a_desc = SW::desc(st_s);
+          const uint64_t b_desc = SW::desc(st_s + kABytes);
+#pragma unroll
+          for (int kk = 0; kk < kBK / 16; ++kk)
+            umma_bf16(d_tmem, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                      (kc > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&S.empty[slot]);
+          if (++slot == kStages) { slot = 0; fph ^= 1u; }
+        }
+        umma_commit(&S.acc_full[ab]);
+      }
+      tc_fence_before();
+    }
+  } else {
+    // ======================= epilogue: thread = row =======================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int flags = P.flags;
+    const int N = P.n_pass;
+    int t = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
+      const int tile = item / P.n_passes, pass = item - tile * P.n_passes;
+      const int ab = t & 1;
+      const int r = tile * kBM + q * 32 + lane;
+      const bool row_ok = r < P.rows;
+      const int cbase = pass * N;                 // first output column of this pass
+      const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256);
+      mbar_wait_relaxed(&S.acc_full[ab], (uint32_t)(t >> 1) & 1u, 1000u);
+      tc_fence_after();
+      float sum = 0.f, sumsq = 0.f;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        if (N - c0 >= 32) {
+          tmem_ld32(lane_base + (uint32_t)c0, v);
+        } else {                                  // narrow heads: N = 16
+          tmem_ld16(lane_base + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0u;
+        }
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = __uint_as_float(v[j]) + S.bias[cbase + c0 + j];
+          if (flags & F_RELU1) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (row_ok && N - c0 >= 32) {
+          const size_t off = (size_t)r * P.ldr + cbase + c0;
+          if (flags & F_MUL) mul_row32(f, P.mul + off);
+          if (flags & F_RES1) add_row32(f, P.res1 + off);
+          if (flags & F_RES2) add_row32(f, P.res2 + off);
+        }
+        if (flags & F_LN) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            sum += f[j];
+            sumsq += f[j] * f[j];
+            v[j] = __float_as_uint(f[j]);
+          }
+          tmem_st32(lane_base + (uint32_t)c0, v);      // park the pre-norm row in the accumulator
+        } else if (row_ok) {
+          if (flags & F_RELU2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (flags & F_OUT_F32) {
+            float* o = reinterpret_cast<float*>(P.out) + (size_t)r * P.ldo;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + c0 + j < P.n_cols) o[cbase + c0 + j] = f[j];
+            if ((flags & F_REF) && c0 == 0) {
+              P.ref_out[(size_t)r * 3 + 0] = __ldg(&P.ref_in[(size_t)r * 3 + 0]) + f[0];
+              P.ref_out[(size_t)r * 3 + 1] = __ldg(&P.ref_in[(size_t)r * 3 + 1]) + f[1];
+              P.ref_out[(size_t)r * 3 + 2] = __ldg(&P.ref_in[(size_t)r * 3 + 2]) + f[4];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + (size_t)r * P.ldo + cbase + c0;
+            store_row32(o, f);
+            if (flags & F_OUT2) {
+              const size_t off = (size_t)r * P.ldr + cbase + c0;
+              add_row32(f, P.add2 + off);
+              store_row32(P.out2 + off, f);
+            }
+          }
+        }
+      }
+      if (flags & F_LN) {
+        tmem_st_wait();
+        const float mean = sum / (float)N;
+        const float var = fmaxf(sumsq / (float)N - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + P.eps);
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_base + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = (__uint_as_float(v[j]) - mean) * rstd * S.gamma[c0 + j] + S.beta[c0 + j];
+            if (flags & F_RELU2) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (row_ok) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + (size_t)r * P.ldo + c0;
+            store_row32(o, f);
+            if (flags & F_OUT2) {
+              const size_t off = (size_t)r * P.ldr + c0;
+              add_row32(f, P.add2 + off);
+              store_row32(P.out2 + off, f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&S.acc_empty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// Linear(3 -> C) + LayerNorm + ReLU: the first half of UniCrossAtten.position_encoder
+// (uni3detr_transformer.py:256-260). K = 3 is no GEMM: one warp per row, 8 channels per lane (C = 256).
+template <typename T>
+__global__ void k_pos3_ln_relu(const float* __restrict__ ref, const float* __restrict__ w,   // w (C,3)
+                               const float* __restrict__ b, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, float eps, int rows, int C, T* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float x = __ldg(&ref[(size_t)row * 3]), y = __ldg(&ref[(size_t)row * 3 + 1]), z = __ldg(&ref[(size_t)row * 3 + 2]);
+  float v[8];
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane * 8 + j;
+    v[j] = c < C ? __ldg(&w[c * 3]) * x + __ldg(&w[c * 3 + 1]) * y + __ldg(&w[c * 3 + 2]) * z + __ldg(&b[c]) : 0.f;
+    s += v[j];
+    ss += v[j] * v[j];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const float mean = s / (float)C;
+  const float rstd = rsqrtf(fmaxf(ss / (float)C - mean * mean, 0.f) + eps);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = lane * 8 + j;
+    if (c < C) out[(size_t)row * C + c] = from_f32<T>(fmaxf((v[j] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]), 0.f));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace lin
+}  // namespace u3d
+
+using namespace u3d;
+
+extern "C" {
+
+size_t u3d_linear_packed_bytes(int N, int K) {
+  if (N < 1 || K < 64 || K % 64 != 0) return 0;
+  const int n_pass = N > 256 ? 256 : (N + 15) / 16 * 16;
+  if (N > 256 && N % 256 != 0) return 0;
+  const int passes = N > 256 ? N / 256 : 1;
+  if (passes > 2) return 0;
+  return (size_t)passes * (K / 64) * n_pass * 128;
+}
+
+// packs W (N, K) bf16 row-major (nn.Linear.weight) into [pass][K/64] images of (n_pass x 64) bf16 in the
+// UMMA K-major SWIZZLE_128B layout (rows >= N zero)
+__global__ void k_linear_pack(const __nv_bfloat16* __restrict__ w, int N, int K, int n_pass, int passes,
+                              __nv_bfloat16* __restrict__ packed) {
+  const int KC = K / 64;
+  const long long total = (long long)passes * KC * n_pass * 8;   // 16-byte chunks
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i & 7);
+    long long t = i >> 3;
+    const int n = (int)(t % n_pass);
+    t /= n_pass;
+    const int kc = (int)(t % KC);
+    const int pass = (int)(t / KC);
+    const int row = pass * n_pass + n;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (row < N) val = *reinterpret_cast<const uint4*>(w + (size_t)row * K + kc * 64 + chunk * 8);
+    uint8_t* img = reinterpret_cast<uint8_t*>(packed) + ((size_t)pass * KC + kc) * n_pass * 128;
+    *reinterpret_cast<uint4*>(img + tc::Swz<64>::offset(n, chunk)) = val;
+  }
+}
+
+int u3d_linear_pack_weights(const void* w, int N, int K, void* packed, void* stream) {
+  const size_t bytes = u3d_linear_packed_bytes(N, K);
+  U3D_CHECK_ARG(bytes != 0, "linear pack: N=%d K=%d unsupported (K %% 64 == 0, N <= 256 or N == 512)", N, K);
+  U3D_CHECK_ARG((((uintptr_t)w | (uintptr_t)packed) & 15) == 0, "linear pack: buffers must be 16-byte aligned");
+  const int n_pass = N > 256 ? 256 : (N + 15) / 16 * 16;
+  const int passes = N > 256 ? N / 256 : 1;
+  const long long total = (long long)bytes / 16;
+  k_linear_pack<<<cdiv(total, 256) < 1024 ? cdiv(total, 256) : 1024, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)w, N, K, n_pass, passes, (__nv_bfloat16*)packed);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed, int N, const float* bias,
+                  int flags, const void* mul, const void* res1, const void* res2, int ldr,
+                  const float* gamma, const float* beta, float eps, const void* add2, void* out2,
+                  void* out, int ldo, const float* ref_in, float* ref_out, void* stream) {
+  using namespace lin;
+  U3D_CHECK_ARG(u3d_linear_packed_bytes(N, K) != 0, "linear: N=%d K=%d unsupported", N, K);
+  U3D_CHECK_ARG(rows >= 0 && lda >= K && lda % 8 == 0, "linear: lda=%d must be >= K=%d and a multiple of 8", lda, K);
+  if (rows == 0) return U3D_OK;
+  Params P;
+  P.rows = rows;
+  P.K = K;
+  P.n_passes = N > 256 ? N / 256 : 1;
+  P.n_pass = N > 256 ? 256 : (N + 15) / 16 * 16;
+  P.n_cols = N;
+  P.ldo = ldo;
+  P.ldr = ldr;
+  P.flags = flags;
+  P.eps = eps;
+  P.wpk = (const uint8_t*)w_packed;
+  P.bias = bias;
+  P.gamma = gamma;
+  P.beta = beta;
+  P.mul = (const __nv_bfloat16*)mul;
+  P.res1 = (const __nv_bfloat16*)res1;
+  P.res2 = (const __nv_bfloat16*)res2;
+  P.add2 = (const __nv_bfloat16*)add2;
+  P.out2 = (__nv_bfloat16*)out2;
+  P.out = out;
+  P.ref_in = ref_in;
+  P.ref_out = ref_out;
+  const bool f32 = (flags & F_OUT_F32) != 0;
+  U3D_CHECK_ARG(!(flags & F_LN) || (P.n_passes == 1 && P.n_pass == N && N % 32 == 0 && gamma && beta),
+                "linear: LayerNorm needs the whole row in one pass (N=%d <= 256, N %% 32 == 0)", N);
+  U3D_CHECK_ARG(f32 || (P.n_pass % 32 == 0 && ldo % 8 == 0), "linear: bf16 output needs N %% 32 == 0 and ldo %% 8 == 0");
+  U3D_CHECK_ARG(!(flags & (F_MUL | F_RES1 | F_RES2 | F_OUT2)) || (ldr % 8 == 0 && P.n_pass % 32 == 0),
+                "linear: residual / multiplier rows need ldr %% 8 == 0");
+  U3D_CHECK_ARG(!(flags & F_MUL) || mul, "linear: F_MUL without a multiplier");
+  U3D_CHECK_ARG(!(flags & F_RES1) || res1, "linear: F_RES1 without res1");
+  U3D_CHECK_ARG(!(flags & F_RES2) || res2, "linear: F_RES2 without res2");
+  U3D_CHECK_ARG(!(flags & F_OUT2) || (add2 && out2 && !f32), "linear: F_OUT2 needs add2, out2 and a bf16 output");
+  U3D_CHECK_ARG(!(flags & F_REF) || (f32 && ref_in && ref_out && N >= 5), "linear: F_REF needs an fp32 output with >= 5 columns");
+  U3D_CHECK_ARG((((uintptr_t)a | (uintptr_t)w_packed | (uintptr_t)out | (uintptr_t)mul | (uintptr_t)res1 |
+                  (uintptr_t)res2 | (uintptr_t)add2 | (uintptr_t)out2) & 15) == 0,
+                "linear: buffers must be 16-byte aligned");
+
+  EncodeTiledFn enc = encode_tiled_fn();
+  U3D_CHECK_ARG(enc != nullptr, "linear: cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)lda * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  U3D_CHECK_ARG(cr == CUDA_SUCCESS, "linear: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d lda=%d", (int)cr, rows, K, lda);
+
+  const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
+  const size_t smem = header + (size_t)kStages * (kABytes + (size_t)P.n_pass * 128) + 1024;
+  static int cur_smem = 0;
+  U3D_CUDA(ensure_dynamic_smem(k_linear_tc, smem, &cur_smem));
+  const int items = cdiv(rows, kBM) * P.n_passes;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  k_linear_tc<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap, P);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+int u3d_pos3_ln_relu(const float* ref, const float* w, const float* b, const float* gamma, const float* beta,
+                     float eps, int rows, int C, void* out, int dtype, void* stream) {
+  U3D_CHECK_ARG(C >= 1 && C <= 256, "pos3_ln_relu: C=%d must be <= 256", C);
+  if (rows <= 0) return U3D_OK;
+  const int wpb = 8;
+  if (dtype == U3D_BF16)
+    lin::k_pos3_ln_relu<__nv_bfloat16><<<cdiv(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        ref, w, b, gamma, beta, eps, rows, C, (__nv_bfloat16*)out);
+  else
+    lin::k_pos3_ln_relu<float><<<cdiv(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(ref, w, b, gamma, beta, eps,
+                                                                                       rows, C, (float*)out);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+}  // extern "C"

@@ -540,3 +540,96 @@ def points_gather(points, choices):
     out = torch.empty((n, C), dtype=torch.float32, device=points.device)
     _lib.check(lib.u3d_points_gather(_p(points), C, _p(choices), n, _p(out), _stream()))
     return out
+
+
+# ------------------------------------------------------------- decoder / head GEMMs (tcgen05) ----
+LIN_RELU1, LIN_MUL, LIN_RES1, LIN_RES2, LIN_LN, LIN_RELU2, LIN_OUT2, LIN_OUT_F32, LIN_REF = \
+    1, 2, 4, 8, 16, 32, 64, 128, 256
+
+
+def linear_supported(N, K):
+    return _lib.load().u3d_linear_packed_bytes(int(N), int(K)) != 0
+
+
+class PackedLinear:
+    """nn.Linear parameters in the layout u3d_linear_tc consumes: `w` the pre-swizzled bf16 weight
+    images, `bias` f32; `ln` = (gamma f32, beta f32, eps) of a LayerNorm fused behind it, or None."""
+    __slots__ = ("w", "bias", "N", "K", "ln")
+
+    def __init__(self, weight, bias=None, ln=None):
+        lib = _lib.load()
+        N, K = weight.shape
+        nbytes = lib.u3d_linear_packed_bytes(N, K)
+        if nbytes == 0:
+            raise _lib.U3DError(f"u3d_linear_tc does not support N={N} K={K}")
+        w = weight.detach().to(torch.bfloat16).contiguous()
+        _req(w, torch.bfloat16, "weight")
+        self.w = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+        _lib.check(lib.u3d_linear_pack_weights(_p(w), N, K, _p(self.w), _stream()))
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.N, self.K = N, K
+        self.ln = None if ln is None else (ln[0].detach().float().contiguous(), ln[1].detach().float().contiguous(),
+                                           float(ln[2]))
+
+
+@_timed(lambda r, a, lin, **k: dict(rows=a.shape[0], K=lin.K, N=lin.N))
+def linear_tc(a, lin, relu=False, mul=None, res1=None, res2=None, ln=False, relu_out=False, add2=None,
+              out_f32=False, ref_in=None):
+    """out = act2(LN(act1(a @ W^T + b) * mul + res1 + res2)); returns out, or (out, out + add2) with
+    `add2`, or (out f32, ref_in + (out[:,0], out[:,1], out[:,4])) with `ref_in`. a: (rows, K) bf16 2-D
+    view with unit column stride; mul / res1 / res2 / add2: (rows, N) bf16 sharing one row stride."""
+    lib = _lib.load()
+    if a.dtype != torch.bfloat16 or not a.is_cuda or a.dim() != 2 or a.stride(1) != 1:
+        raise _lib.U3DError("linear_tc: a must be a CUDA bf16 (rows, K) view with unit column stride")
+    rows, K = a.shape
+    assert K == lin.K
+    N = lin.N
+    flags = (LIN_RELU1 if relu else 0) | (LIN_RELU2 if relu_out else 0)
+    ldr = N
+    for t, f in ((mul, LIN_MUL), (res1, LIN_RES1), (res2, LIN_RES2), (add2, LIN_OUT2)):
+        if t is not None:
+            if t.dtype != torch.bfloat16 or t.stride(1) != 1 or t.shape != (rows, N):
+                raise _lib.U3DError("linear_tc: epilogue operands must be (rows, N) bf16 with unit column stride")
+            flags |= f
+            ldr = t.stride(0)
+    for t in (mul, res1, res2, add2):
+        if t is not None and t.stride(0) != ldr:
+            raise _lib.U3DError("linear_tc: epilogue operands must share one row stride")
+    g = b = None
+    eps = 0.0
+    if ln:
+        g, b, eps = lin.ln
+        flags |= LIN_LN
+    out2 = ref_out = None
+    if out_f32:
+        flags |= LIN_OUT_F32
+        out = torch.empty((rows, N), dtype=torch.float32, device=a.device)
+        if ref_in is not None:
+            _req(ref_in, torch.float32, "ref_in")
+            flags |= LIN_REF
+            ref_out = torch.empty_like(ref_in)
+    else:
+        out = torch.empty((rows, N), dtype=torch.bfloat16, device=a.device)
+        if add2 is not None:
+            out2 = torch.empty((rows, N), dtype=torch.bfloat16, device=a.device)
+            if ldr != N:
+                raise _lib.U3DError("linear_tc: add2 must be contiguous (out2 shares its row stride)")
+    _lib.check(lib.u3d_linear_tc(_p(a), a.stride(0), rows, K, _p(lin.w), N, _p(lin.bias), flags, _p(mul), _p(res1),
+                                 _p(res2), ldr, _p(g), _p(b), eps, _p(add2), _p(out2), _p(out), N, _p(ref_in),
+                                 _p(ref_out), _stream()))
+    if ref_out is not None:
+        return out, ref_out
+    if out2 is not None:
+        return out, out2
+    return out
+
+
+def pos3_ln_relu(ref, weight, bias, gamma, beta, eps, dtype=torch.bfloat16):
+    """relu(LayerNorm(ref @ weight^T + bias)) for Linear(3 -> C): ref (rows,3) f32; parameters f32."""
+    lib = _lib.load()
+    _req(ref, torch.float32, "ref")
+    rows, C = ref.shape[0], weight.shape[0]
+    out = torch.empty((rows, C), dtype=dtype, device=ref.device)
+    _lib.check(lib.u3d_pos3_ln_relu(_p(ref), _p(weight), _p(bias), _p(gamma), _p(beta), float(eps), rows, C,
+                                    _p(out), _DT[dtype], _stream()))
+    return out
