@@ -359,6 +359,12 @@ int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed,
                   int flags, const void* mul, const void* res1, const void* res2, int ldr,
                   const float* gamma, const float* beta, float eps, const void* add2, void* out2,
                   void* out, int ldo, const float* ref_in, float* ref_out, void* stream);
+/* Box assembly of Uni3DETRHead.forward (dense_heads/uni3detr_head.py:470-496): out = tmp with
+ * out[0] = sigmoid(tmp[0] + logit(ref.x)) * (pc[3]-pc[0]) + pc[0], likewise [1] (y) and [4] (z), where
+ * logit(.) = inverse_sigmoid(sigmoid(ref_logit), eps=1e-5) as in the reference's round trip.
+ * tmp, out (rows, code) f32; ref_logit (rows,3) f32; pc_range: 6 host floats. */
+int u3d_box_assemble(const float* tmp, const float* ref_logit, int rows, int code, const float* pc_range,
+                     float* out, void* stream);
 /* relu(LayerNorm(ref @ w^T + b)): Linear(3 -> C) + LN + ReLU, the first stage of UniCrossAtten.position_encoder
  * (utils/uni3detr_transformer.py:253-260). ref (rows,3) f32, w (C,3) f32, b/gamma/beta (C) f32, C <= 256. */
 int u3d_pos3_ln_relu(const float* ref, const float* w, const float* b, const float* gamma, const float* beta,

@@ -573,9 +573,9 @@ def _lin_ref(a, W, b, relu=False, mul=None, res1=None, res2=None, ln=None, relu_
 
 
 @pytest.mark.parametrize("rows,K,N", [(300, 256, 256), (1000, 384, 256), (128 * 149 + 77, 256, 256),
-                                       (513, 512, 256), (700, 256, 512), (129, 64, 32)])
+                                       (513, 512, 256), (700, 256, 512), (129, 64, 64), (2000, 128, 128)])
 def test_linear_tc_plain_and_relu(rows, K, N):
-    """out = relu?(A W^T + b): K in {64..512}, N in {32, 256, 512 (two passes)}, ragged last tile,
+    """out = relu?(A W^T + b): K in {64..512}, N in {64, 128, 256, 512 (two passes)}, ragged last tile,
     more tiles than SMs (persistent loop + both TMEM accumulators + ring wrap-around)."""
     from uni3detr_b200 import ops
     g = torch.Generator().manual_seed(rows + K + N)

@@ -33,10 +33,14 @@ using namespace tc;
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kStages = 4;
-constexpr int kThreads = 192;
-constexpr int kABytes = kBM * kBK * 2;   // 16 KB per stage
-constexpr int kEpiThreads = 128;
+constexpr int kStages = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kInWarp = 2 + kEpiWarps;            // warp 10: loader of the TMA-staged epilogue operand
+constexpr int kThreads = (kInWarp + 1) * 32;      // 352
+constexpr int kABytes = kBM * kBK * 2;            // 16 KB per stage
+constexpr int kSlab = 64;                         // output columns per staging slab (128-byte rows)
+constexpr int kSlabBytes = kBM * kSlab * 2;       // 16 KB
 
 enum : int {
   F_RELU1 = 1,      // ReLU right after the bias
@@ -48,6 +52,9 @@ enum : int {
   F_OUT2 = 64,      // out2 = out + add2
   F_OUT_F32 = 128,  // fp32 output (narrow heads)
   F_REF = 256,      // ref_out[r][0..2] = ref_in[r][0..2] + (v0, v1, v4): the decoder's reference refinement
+  F_DBG_NOSTORE = 1 << 20,   // profiling switches (scripts/bench_linear.py): no global epilogue traffic,
+  F_DBG_NOEPI = 1 << 21,     // epilogue releases the accumulator untouched,
+  F_DBG_LDTM = 1 << 22,      // epilogue only reads TMEM
 };
 
 struct Params {
@@ -55,17 +62,17 @@ struct Params {
   int n_passes;                  // 1 or 2 (N = n_passes * n_pass)
   int ldo, ldr;                  // output / residual row strides in elements
   int flags;
+  int in0_kind;                  // 0 none, 1 = multiplier, 2 = addend: the epilogue operand staged through TMA
   float eps;
   const uint8_t* wpk;            // [pass][K/64] images of (n_pass x 64) bf16, K-major, SWIZZLE_128B
   const float* bias;
   const float* gamma;
   const float* beta;
-  const __nv_bfloat16* mul;
+  const __nv_bfloat16* mul;      // operands NOT staged through TMA (thread = row loads); null if staged / absent
   const __nv_bfloat16* res1;
   const __nv_bfloat16* res2;
   const __nv_bfloat16* add2;
-  __nv_bfloat16* out2;
-  void* out;
+  void* out;                     // fp32 narrow path only (bf16 outputs leave through the tensor maps)
   const float* ref_in;
   float* ref_out;
 };
@@ -75,10 +82,13 @@ struct Smem {
   uint64_t empty[kStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t in_full[2];
+  uint64_t in_empty[2];
   uint32_t tmem_base;
-  float bias[512];
-  float gamma[256];
-  float beta[256];
+  alignas(16) float bias[512];
+  alignas(16) float gamma[256];
+  alignas(16) float beta[256];
+  float2 stat[2][kBM];
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -86,6 +96,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kEpiThreads) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
@@ -100,51 +124,40 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// 32 consecutive bf16 of a row (64 bytes, 16-byte aligned) added into f[32]
-__device__ __forceinline__ void add_row32(float* f, const __nv_bfloat16* p) {
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// 32 consecutive bf16 of a global row (64 bytes, 16-byte aligned) combined into f[32]
+template <bool kMul> __device__ __forceinline__ void apply_row32(float* f, const __nv_bfloat16* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const uint4 u = __ldg(q + i);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float t[8];
+    unpack8(__ldg(q + i), t);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-      f[8 * i + 2 * j] += t.x;
-      f[8 * i + 2 * j + 1] += t.y;
-    }
-  }
-}
-__device__ __forceinline__ void mul_row32(float* f, const __nv_bfloat16* p) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 u = __ldg(q + i);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
-      f[8 * i + 2 * j] *= t.x;
-      f[8 * i + 2 * j + 1] *= t.y;
-    }
-  }
-}
-__device__ __forceinline__ void store_row32(__nv_bfloat16* p, const float* f) {
-  uint4* q = reinterpret_cast<uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
-      w[j] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    q[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    for (int j = 0; j < 8; ++j) f[8 * i + j] = kMul ? f[8 * i + j] * t[j] : f[8 * i + j] + t[j];
   }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
+k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_in0,
+            const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+            const Params P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   constexpr uint32_t kHeader = (uint32_t)((sizeof(Smem) + 1023) & ~(size_t)1023);
@@ -155,6 +168,9 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
   const uint32_t w_bytes = (uint32_t)P.n_pass * 128u;
   const uint32_t stage_bytes = (uint32_t)kABytes + w_bytes;
   const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;
+  const uint32_t out_s = tiles_s + (uint32_t)kStages * stage_bytes;   // 2 output staging slabs
+  const uint32_t in_s = out_s + 2u * kSlabBytes;                      // 2 input staging slabs
+  const int n_slabs = P.n_pass / kSlab;                               // 0 on the narrow fp32 path
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -164,6 +180,8 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
     for (int b = 0; b < 2; ++b) {
       mbar_init(&S.acc_full[b], 1);
       mbar_init(&S.acc_empty[b], kEpiThreads);
+      mbar_init(&S.in_full[b], 1);
+      mbar_init(&S.in_empty[b], kEpiThreads);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -176,7 +194,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
   // per-column constants of the epilogue -> shared memory (broadcast reads)
   {
     const int ntot = P.n_pass * P.n_passes;
-    for (int i = tid; i < ntot; i += kThreads) S.bias[i] = (P.bias && i < P.n_cols) ? __ldg(&P.bias[i]) : 0.f;
+    for (int i = tid; i < 512; i += kThreads) S.bias[i] = (P.bias && i < P.n_cols && i < ntot) ? __ldg(&P.bias[i]) : 0.f;
     if (P.flags & F_LN)
       for (int i = tid; i < P.n_pass; i += kThreads) {
         S.gamma[i] = __ldg(&P.gamma[i]);
@@ -189,7 +207,7 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
   const uint32_t tmem = S.tmem_base;
 
   if (warp == 0) {
-    // ======================= producer =======================
+    // ======================= producer: A boxes (TMA) + weight images (bulk copy) =======================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
       int slot = 0;
@@ -237,43 +255,138 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
       }
       tc_fence_before();
     }
+  } else if (warp == kInWarp) {
+    // ======================= loader of the TMA-staged epilogue operand (multiplier or addend) ============
+    if (lane == 0 && P.in0_kind != 0 && n_slabs > 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_in0)) : "memory");
+      int ii = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int tile = item / P.n_passes, pass = item - tile * P.n_passes;
+        for (int slab = 0; slab < n_slabs; ++slab, ++ii) {
+          const int ib = ii & 1;
+          mbar_wait(&S.in_empty[ib], (((uint32_t)(ii >> 1)) & 1u) ^ 1u);
+          mbar_expect_tx(&S.in_full[ib], (uint32_t)kSlabBytes);
+          tma_load_2d(in_s + (uint32_t)ib * kSlabBytes, &tmap_in0, pass * P.n_pass + slab * kSlab, tile * kBM,
+                      &S.in_full[ib]);
+        }
+      }
+    }
   } else {
-    // ======================= epilogue: thread = row =======================
+    // ======================= epilogue: 8 warps, thread = (row, 32-column half of a 64-column slab) ========
+    using SW = Swz<64>;
+    const int e = warp - 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int h = e >> 2;                         // column half inside a slab
+    const int row = q * 32 + lane;                // row of the tile
+    const bool elected = (e == 0 && lane == 0);   // issues the TMA stores
     const int flags = P.flags;
     const int N = P.n_pass;
-    int t = 0;
+    const bool dbg_nostore = (flags & F_DBG_NOSTORE) != 0;
+    int t = 0, jj = 0, ii = 0;                    // tile, output staging job, input staging slab counters
+    if (elected) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
+    }
+    // one output slab: stage the 32 values of this thread, store the slab with TMA
+    auto emit = [&](const float* f, const CUtensorMap* map, int col, int tile) {
+      const int ob = jj & 1;
+      if (elected) bulk_wait_read<1>();           // the store that last read this buffer has left shared memory
+      epi_bar(1);
+      uint8_t* dst = smem_raw + (out_s - smem_u32(smem_raw)) + (uint32_t)ob * kSlabBytes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(dst + SW::offset(row, h * 4 + i)) = pack8(f + 8 * i);
+      fence_proxy_async();
+      epi_bar(2);
+      if (elected && !dbg_nostore) {
+        tma_store_2d(map, col, tile * kBM, out_s + (uint32_t)ob * kSlabBytes);
+        bulk_commit();
+      }
+      ++jj;
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++t) {
       const int tile = item / P.n_passes, pass = item - tile * P.n_passes;
       const int ab = t & 1;
-      const int r = tile * kBM + q * 32 + lane;
-      const bool row_ok = r < P.rows;
+      const int r = tile * kBM + row;
+      const bool row_ok = r < P.rows && !dbg_nostore;
       const int cbase = pass * N;                 // first output column of this pass
       const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * 256);
       mbar_wait_relaxed(&S.acc_full[ab], (uint32_t)(t >> 1) & 1u, 1000u);
       tc_fence_after();
-      float sum = 0.f, sumsq = 0.f;
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        if (N - c0 >= 32) {
-          tmem_ld32(lane_base + (uint32_t)c0, v);
-        } else {                                  // narrow heads: N = 16
-          tmem_ld16(lane_base + (uint32_t)c0, v);
+      if (flags & F_DBG_NOEPI) {
+        tc_fence_before();
+        mbar_arrive(&S.acc_empty[ab]);
+        continue;
+      }
+      if (n_slabs == 0) {
+        // ---- narrow fp32 heads (N <= 48 columns, no staging): the h == 0 warps store directly
+        if (h == 0) {
+          for (int c0 = 0; c0 < N; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(lane_base + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (row_ok) {
+              float f[16];
 #pragma unroll
-          for (int j = 16; j < 32; ++j) v[j] = 0u;
+              for (int j = 0; j < 16; ++j) {
+                f[j] = __uint_as_float(v[j]) + S.bias[c0 + j];
+                if (flags & F_RELU1) f[j] = fmaxf(f[j], 0.f);
+              }
+              float* o = reinterpret_cast<float*>(P.out) + (size_t)r * P.ldo;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < P.n_cols) o[c0 + j] = f[j];
+              if ((flags & F_REF) && c0 == 0) {
+                P.ref_out[(size_t)r * 3 + 0] = __ldg(&P.ref_in[(size_t)r * 3 + 0]) + f[0];
+                P.ref_out[(size_t)r * 3 + 1] = __ldg(&P.ref_in[(size_t)r * 3 + 1]) + f[1];
+                P.ref_out[(size_t)r * 3 + 2] = __ldg(&P.ref_in[(size_t)r * 3 + 2]) + f[4];
+              }
+            }
+          }
         }
+        tc_fence_before();
+        mbar_arrive(&S.acc_empty[ab]);
+        continue;
+      }
+      float sum = 0.f, sumsq = 0.f;
+      for (int slab = 0; slab < n_slabs; ++slab) {
+        const int c0 = slab * kSlab + h * 32;     // this thread's 32 columns of the pass
+        uint32_t v[32];
+        tmem_ld32(lane_base + (uint32_t)c0, v);
         tmem_ld_wait();
+        if (flags & F_DBG_LDTM) continue;
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = __uint_as_float(v[j]) + S.bias[cbase + c0 + j];
-          if (flags & F_RELU1) f[j] = fmaxf(f[j], 0.f);
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&S.bias[cbase + c0 + 4 * i]);
+          f[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
+          f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+          f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
         }
-        if (row_ok && N - c0 >= 32) {
+        if (flags & F_RELU1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (P.in0_kind != 0) {                    // the TMA-staged operand slab (same swizzled layout as the output)
+          const int ib = ii & 1;
+          mbar_wait(&S.in_full[ib], (uint32_t)(ii >> 1) & 1u);
+          const uint8_t* src = smem_raw + (in_s - smem_u32(smem_raw)) + (uint32_t)ib * kSlabBytes;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float tv[8];
+            unpack8(*reinterpret_cast<const uint4*>(src + SW::offset(row, h * 4 + i)), tv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              f[8 * i + j] = P.in0_kind == 1 ? f[8 * i + j] * tv[j] : f[8 * i + j] + tv[j];
+          }
+          mbar_arrive(&S.in_empty[ib]);
+          ++ii;
+        }
+        if (row_ok) {
           const size_t off = (size_t)r * P.ldr + cbase + c0;
-          if (flags & F_MUL) mul_row32(f, P.mul + off);
-          if (flags & F_RES1) add_row32(f, P.res1 + off);
-          if (flags & F_RES2) add_row32(f, P.res2 + off);
+          if (P.mul) apply_row32<true>(f, P.mul + off);
+          if (P.res1) apply_row32<false>(f, P.res1 + off);
+          if (P.res2) apply_row32<false>(f, P.res2 + off);
         }
         if (flags & F_LN) {
 #pragma unroll
@@ -283,61 +396,56 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const Params P) {
             v[j] = __float_as_uint(f[j]);
           }
           tmem_st32(lane_base + (uint32_t)c0, v);      // park the pre-norm row in the accumulator
-        } else if (row_ok) {
+        } else {
           if (flags & F_RELU2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          if (flags & F_OUT_F32) {
-            float* o = reinterpret_cast<float*>(P.out) + (size_t)r * P.ldo;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (cbase + c0 + j < P.n_cols) o[cbase + c0 + j] = f[j];
-            if ((flags & F_REF) && c0 == 0) {
-              P.ref_out[(size_t)r * 3 + 0] = __ldg(&P.ref_in[(size_t)r * 3 + 0]) + f[0];
-              P.ref_out[(size_t)r * 3 + 1] = __ldg(&P.ref_in[(size_t)r * 3 + 1]) + f[1];
-              P.ref_out[(size_t)r * 3 + 2] = __ldg(&P.ref_in[(size_t)r * 3 + 2]) + f[4];
-            }
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + (size_t)r * P.ldo + cbase + c0;
-            store_row32(o, f);
-            if (flags & F_OUT2) {
-              const size_t off = (size_t)r * P.ldr + cbase + c0;
-              add_row32(f, P.add2 + off);
-              store_row32(P.out2 + off, f);
-            }
+          emit(f, &tmap_out, cbase + slab * kSlab, tile);
+          if (flags & F_OUT2) {
+            if (row_ok) apply_row32<false>(f, P.add2 + (size_t)r * P.ldr + cbase + c0);
+            emit(f, &tmap_out2, cbase + slab * kSlab, tile);
           }
         }
       }
-      if (flags & F_LN) {
+      if ((flags & F_LN) && !(flags & F_DBG_LDTM)) {
         tmem_st_wait();
-        const float mean = sum / (float)N;
-        const float var = fmaxf(sumsq / (float)N - mean * mean, 0.f);
+        S.stat[h][row] = make_float2(sum, sumsq);
+        epi_bar(3);
+        const float2 s0 = S.stat[0][row], s1 = S.stat[1][row];
+        const float mean = (s0.x + s1.x) / (float)N;
+        const float var = fmaxf((s0.y + s1.y) / (float)N - mean * mean, 0.f);
         const float rstd = rsqrtf(var + P.eps);
-        for (int c0 = 0; c0 < N; c0 += 32) {
+        for (int slab = 0; slab < n_slabs; ++slab) {
+          const int c0 = slab * kSlab + h * 32;
           uint32_t v[32];
           tmem_ld32(lane_base + (uint32_t)c0, v);
           tmem_ld_wait();
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = (__uint_as_float(v[j]) - mean) * rstd * S.gamma[c0 + j] + S.beta[c0 + j];
-            if (flags & F_RELU2) f[j] = fmaxf(f[j], 0.f);
+          for (int i = 0; i < 8; ++i) {
+            const float4 g4 = *reinterpret_cast<const float4*>(&S.gamma[c0 + 4 * i]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&S.beta[c0 + 4 * i]);
+            f[4 * i] = (__uint_as_float(v[4 * i]) - mean) * rstd * g4.x + b4.x;
+            f[4 * i + 1] = (__uint_as_float(v[4 * i + 1]) - mean) * rstd * g4.y + b4.y;
+            f[4 * i + 2] = (__uint_as_float(v[4 * i + 2]) - mean) * rstd * g4.z + b4.z;
+            f[4 * i + 3] = (__uint_as_float(v[4 * i + 3]) - mean) * rstd * g4.w + b4.w;
           }
-          if (row_ok) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + (size_t)r * P.ldo + c0;
-            store_row32(o, f);
-            if (flags & F_OUT2) {
-              const size_t off = (size_t)r * P.ldr + c0;
-              add_row32(f, P.add2 + off);
-              store_row32(P.out2 + off, f);
-            }
+          if (flags & F_RELU2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          emit(f, &tmap_out, slab * kSlab, tile);
+          if (flags & F_OUT2) {
+            if (row_ok) apply_row32<false>(f, P.add2 + (size_t)r * P.ldr + c0);
+            emit(f, &tmap_out2, slab * kSlab, tile);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&S.acc_empty[ab]);
     }
+    if (elected) bulk_wait_all();                 // every output slab has reached global memory
   }
   tc_fence_before();
   __syncthreads();
@@ -378,6 +486,31 @@ __global__ void k_pos3_ln_relu(const float* __restrict__ ref, const float* __res
     const int c = lane * 8 + j;
     if (c < C) out[(size_t)row * C + c] = from_f32<T>(fmaxf((v[j] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]), 0.f));
   }
+}
+
+// Box assembly of Uni3DETRHead.forward (dense_heads/uni3detr_head.py:470-496): the reference point goes
+// through sigmoid -> inverse_sigmoid(eps = 1e-5) (transformer :129 -> head :475), is added to the raw
+// (x, y) = tmp[0:2] and z = tmp[4] offsets, squashed and scaled to pc_range; the other code entries pass.
+__global__ void k_box_assemble(const float* __restrict__ tmp, const float* __restrict__ ref_logit, int rows, int code,
+                               float x0, float y0, float z0, float sx, float sy, float sz, float* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* t = tmp + (size_t)r * code;
+  float* o = out + (size_t)r * code;
+  float inv[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s = 1.f / (1.f + expf(-__ldg(&ref_logit[(size_t)r * 3 + c])));
+    s = fminf(fmaxf(s, 0.f), 1.f);
+    inv[c] = logf(fmaxf(s, 1e-5f) / fmaxf(1.f - s, 1e-5f));
+  }
+  const float bx = 1.f / (1.f + expf(-(t[0] + inv[0])));
+  const float by = 1.f / (1.f + expf(-(t[1] + inv[1])));
+  const float bz = 1.f / (1.f + expf(-(t[4] + inv[2])));
+  for (int c = 0; c < code; ++c) o[c] = t[c];
+  o[0] = bx * sx + x0;
+  o[1] = by * sy + y0;
+  o[4] = bz * sz + z0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -446,6 +579,22 @@ int u3d_linear_pack_weights(const void* w, int N, int K, void* packed, void* str
   return U3D_OK;
 }
 
+static int encode_2d(lin::EncodeTiledFn enc, CUtensorMap* map, const void* base, int cols, int rows, int ld,
+                     int box_cols, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    u3d::set_error("linear: cuTensorMapEncodeTiled failed (%d) cols=%d rows=%d ld=%d", (int)cr, cols, rows, ld);
+    return U3D_EINVAL;
+  }
+  return U3D_OK;
+}
+
 int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed, int N, const float* bias,
                   int flags, const void* mul, const void* res1, const void* res2, int ldr,
                   const float* gamma, const float* beta, float eps, const void* add2, void* out2,
@@ -472,16 +621,17 @@ int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed,
   P.res1 = (const __nv_bfloat16*)res1;
   P.res2 = (const __nv_bfloat16*)res2;
   P.add2 = (const __nv_bfloat16*)add2;
-  P.out2 = (__nv_bfloat16*)out2;
   P.out = out;
   P.ref_in = ref_in;
   P.ref_out = ref_out;
   const bool f32 = (flags & F_OUT_F32) != 0;
-  U3D_CHECK_ARG(!(flags & F_LN) || (P.n_passes == 1 && P.n_pass == N && N % 32 == 0 && gamma && beta),
-                "linear: LayerNorm needs the whole row in one pass (N=%d <= 256, N %% 32 == 0)", N);
-  U3D_CHECK_ARG(f32 || (P.n_pass % 32 == 0 && ldo % 8 == 0), "linear: bf16 output needs N %% 32 == 0 and ldo %% 8 == 0");
-  U3D_CHECK_ARG(!(flags & (F_MUL | F_RES1 | F_RES2 | F_OUT2)) || (ldr % 8 == 0 && P.n_pass % 32 == 0),
-                "linear: residual / multiplier rows need ldr %% 8 == 0");
+  U3D_CHECK_ARG(!(flags & F_LN) || (P.n_passes == 1 && P.n_pass == N && gamma && beta),
+                "linear: LayerNorm needs the whole row in one pass (N=%d <= 256)", N);
+  U3D_CHECK_ARG(f32 ? N <= 48 : (N % 64 == 0 && ldo % 8 == 0),
+                "linear: bf16 outputs need N %% 64 == 0 and ldo %% 8 == 0; fp32 outputs N <= 48 (N=%d)", N);
+  U3D_CHECK_ARG(!f32 || !(flags & (F_MUL | F_RES1 | F_RES2 | F_OUT2 | F_LN | F_RELU2)),
+                "linear: the narrow fp32 path takes bias / ReLU / reference refinement only");
+  U3D_CHECK_ARG(!(flags & (F_MUL | F_RES1 | F_RES2 | F_OUT2)) || ldr % 8 == 0, "linear: epilogue operands need ldr %% 8 == 0");
   U3D_CHECK_ARG(!(flags & F_MUL) || mul, "linear: F_MUL without a multiplier");
   U3D_CHECK_ARG(!(flags & F_RES1) || res1, "linear: F_RES1 without res1");
   U3D_CHECK_ARG(!(flags & F_RES2) || res2, "linear: F_RES2 without res2");
@@ -490,26 +640,49 @@ int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed,
   U3D_CHECK_ARG((((uintptr_t)a | (uintptr_t)w_packed | (uintptr_t)out | (uintptr_t)mul | (uintptr_t)res1 |
                   (uintptr_t)res2 | (uintptr_t)add2 | (uintptr_t)out2) & 15) == 0,
                 "linear: buffers must be 16-byte aligned");
+  if (!(flags & F_MUL)) P.mul = nullptr;
+  if (!(flags & F_RES1)) P.res1 = nullptr;
+  if (!(flags & F_RES2)) P.res2 = nullptr;
 
   EncodeTiledFn enc = encode_tiled_fn();
   U3D_CHECK_ARG(enc != nullptr, "linear: cuTensorMapEncodeTiled is not available from the driver");
-  CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)lda * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  U3D_CHECK_ARG(cr == CUDA_SUCCESS, "linear: cuTensorMapEncodeTiled failed (%d) rows=%d K=%d lda=%d", (int)cr, rows, K, lda);
+  CUtensorMap tmap_a, tmap_in0, tmap_out, tmap_out2;
+  if (encode_2d(enc, &tmap_a, a, K, rows, lda, kBK, kBM) != U3D_OK) return U3D_EINVAL;
+  tmap_in0 = tmap_a;
+  tmap_out = tmap_a;
+  tmap_out2 = tmap_a;
+  // the first epilogue operand (multiplier, else the first residual) is staged through TMA; the others
+  // (rare: output_proj's second residual, query_scale's `+ x`) are read by the row threads
+  P.in0_kind = 0;
+  if (flags & (F_DBG_NOEPI | F_DBG_LDTM)) P.mul = P.res1 = P.res2 = nullptr;   // profiling: epilogue operands unused
+  if (!f32) {
+    const void* in0 = nullptr;
+    if (P.mul) { in0 = P.mul; P.in0_kind = 1; P.mul = nullptr; }
+    else if (P.res1) { in0 = P.res1; P.in0_kind = 2; P.res1 = nullptr; }
+    else if (P.res2) { in0 = P.res2; P.in0_kind = 2; P.res2 = nullptr; }
+    if (in0 && encode_2d(enc, &tmap_in0, in0, N, rows, ldr, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
+    if (encode_2d(enc, &tmap_out, out, N, rows, ldo, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
+    if ((flags & F_OUT2) && encode_2d(enc, &tmap_out2, out2, N, rows, ldr, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
+  }
 
   const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
-  const size_t smem = header + (size_t)kStages * (kABytes + (size_t)P.n_pass * 128) + 1024;
+  const size_t smem = header + (size_t)kStages * (kABytes + (size_t)P.n_pass * 128) + 4 * (size_t)kSlabBytes;
   static int cur_smem = 0;
   U3D_CUDA(ensure_dynamic_smem(k_linear_tc, smem, &cur_smem));
   const int items = cdiv(rows, kBM) * P.n_passes;
   const int grid = items < kNumSMs ? items : kNumSMs;
-  k_linear_tc<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap, P);
+  k_linear_tc<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_a, tmap_in0, tmap_out, tmap_out2, P);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+int u3d_box_assemble(const float* tmp, const float* ref_logit, int rows, int code, const float* pc_range,
+                     float* out, void* stream) {
+  U3D_CHECK_ARG(tmp && ref_logit && out && pc_range && code >= 6, "box_assemble: bad argument (code=%d)", code);
+  if (rows <= 0) return U3D_OK;
+  lin::k_box_assemble<<<cdiv(rows, 128), 128, 0, (cudaStream_t)stream>>>(
+      tmp, ref_logit, rows, code, pc_range[0], pc_range[1], pc_range[2], pc_range[3] - pc_range[0],
+      pc_range[4] - pc_range[1], pc_range[5] - pc_range[2], out);
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }

@@ -574,7 +574,7 @@ class PackedLinear:
 
 @_timed(lambda r, a, lin, **k: dict(rows=a.shape[0], K=lin.K, N=lin.N))
 def linear_tc(a, lin, relu=False, mul=None, res1=None, res2=None, ln=False, relu_out=False, add2=None,
-              out_f32=False, ref_in=None):
+              out_f32=False, ref_in=None, out=None, _debug=0):
     """out = act2(LN(act1(a @ W^T + b) * mul + res1 + res2)); returns out, or (out, out + add2) with
     `add2`, or (out f32, ref_in + (out[:,0], out[:,1], out[:,4])) with `ref_in`. a: (rows, K) bf16 2-D
     view with unit column stride; mul / res1 / res2 / add2: (rows, N) bf16 sharing one row stride."""
@@ -584,7 +584,7 @@ def linear_tc(a, lin, relu=False, mul=None, res1=None, res2=None, ln=False, relu
     rows, K = a.shape
     assert K == lin.K
     N = lin.N
-    flags = (LIN_RELU1 if relu else 0) | (LIN_RELU2 if relu_out else 0)
+    flags = (LIN_RELU1 if relu else 0) | (LIN_RELU2 if relu_out else 0) | _debug
     ldr = N
     for t, f in ((mul, LIN_MUL), (res1, LIN_RES1), (res2, LIN_RES2), (add2, LIN_OUT2)):
         if t is not None:
@@ -601,15 +601,20 @@ def linear_tc(a, lin, relu=False, mul=None, res1=None, res2=None, ln=False, relu
         g, b, eps = lin.ln
         flags |= LIN_LN
     out2 = ref_out = None
+    if out is not None and (not out.is_contiguous() or tuple(out.shape) != (rows, N) or
+                            out.dtype != (torch.float32 if out_f32 else torch.bfloat16)):
+        raise _lib.U3DError("linear_tc: `out` must be a contiguous (rows, N) tensor of the output dtype")
     if out_f32:
         flags |= LIN_OUT_F32
-        out = torch.empty((rows, N), dtype=torch.float32, device=a.device)
+        if out is None:
+            out = torch.empty((rows, N), dtype=torch.float32, device=a.device)
         if ref_in is not None:
             _req(ref_in, torch.float32, "ref_in")
             flags |= LIN_REF
             ref_out = torch.empty_like(ref_in)
     else:
-        out = torch.empty((rows, N), dtype=torch.bfloat16, device=a.device)
+        if out is None:
+            out = torch.empty((rows, N), dtype=torch.bfloat16, device=a.device)
         if add2 is not None:
             out2 = torch.empty((rows, N), dtype=torch.bfloat16, device=a.device)
             if ldr != N:
@@ -632,4 +637,18 @@ def pos3_ln_relu(ref, weight, bias, gamma, beta, eps, dtype=torch.bfloat16):
     out = torch.empty((rows, C), dtype=dtype, device=ref.device)
     _lib.check(lib.u3d_pos3_ln_relu(_p(ref), _p(weight), _p(bias), _p(gamma), _p(beta), float(eps), rows, C,
                                     _p(out), _DT[dtype], _stream()))
+    return out
+
+
+def box_assemble(tmp, ref_logit, pc_range, out=None):
+    """Uni3DETRHead.forward's box assembly (uni3detr_head.py:470-496) for (rows, code) f32 raw branch
+    outputs and the (rows, 3) f32 reference LOGITS the layer started from."""
+    lib = _lib.load()
+    _req(tmp, torch.float32, "tmp")
+    _req(ref_logit, torch.float32, "ref_logit")
+    rows, code = tmp.shape
+    if out is None:
+        out = torch.empty_like(tmp)
+    pr, prp = _farr(pc_range)
+    _lib.check(lib.u3d_box_assemble(_p(tmp), _p(ref_logit), rows, code, prp, _p(out), _stream()))
     return out

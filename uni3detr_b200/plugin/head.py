@@ -204,7 +204,19 @@ class Uni3DETRHead(nn.Module):
                    for m in br if isinstance(m, nn.LayerNorm)]
             cls.append(dict(lin=lin(br), ln=lns))
         self._plan = dict(dtype=dt, cls=cls, reg=[lin(b) for b in self.reg_branches],
-                          iou=[lin(b) for b in self.iou_branches])
+                          iou=[lin(b) for b in self.iou_branches], tc=None)
+        if self.transformer.decoder.uses_tc():
+            from .. import ops
+            PL = ops.PackedLinear
+            tc_cls = []
+            for br in self.cls_branches:
+                mods = list(br)
+                tc_cls.append([PL(m.weight, m.bias, (mods[i + 1].weight, mods[i + 1].bias, mods[i + 1].eps)
+                                  if i + 1 < len(mods) and isinstance(mods[i + 1], nn.LayerNorm) else None)
+                               for i, m in enumerate(mods) if isinstance(m, nn.Linear)])
+            plin = lambda br: [PL(m.weight, m.bias) for m in br if isinstance(m, nn.Linear)]
+            self._plan["tc"] = dict(cls=tc_cls, reg=[plin(b) for b in self.reg_branches],
+                                    iou=[plin(b) for b in self.iou_branches])
         return self._plan
 
     def build_queries(self, fpsbpts, train_mode, random_point=None):
@@ -235,12 +247,15 @@ class Uni3DETRHead(nn.Module):
         query_embeds = self.build_queries(fpsbpts.float(), pts_feats.requires_grad, random_point)
         if pts_feats.dim() == 5:
             pts_feats = pts_feats.unsqueeze(1)
+        tc = p.get("tc")
+        reg_plans = (tc["reg"] if tc is not None else p["reg"]) if self.with_box_refine else None
         hs, init_reference, inter_references = self.transformer(
-            pts_feats, query_embeds, self.num_query,
-            reg_plans=p["reg"] if self.with_box_refine else None, img_metas=img_metas)
+            pts_feats, query_embeds, self.num_query, reg_plans=reg_plans, img_metas=img_metas)
         hs = hs.permute(0, 2, 1, 3)  # (L,B,Q,E)
         E = self.embed_dims
         pc = self.pc_range
+        if tc is not None and hs.is_cuda and hs.dtype == torch.bfloat16:
+            return self._forward_heads_tc(tc, hs)
         classes, coords, ious = [], [], []
         for lvl in range(hs.shape[0]):
             reference = init_reference if lvl == 0 else inter_references[lvl - 1]
@@ -266,6 +281,39 @@ class Uni3DETRHead(nn.Module):
             ious.append(outputs_iou)
         return {"all_cls_scores": torch.stack(classes), "all_bbox_preds": torch.stack(coords),
                 "all_iou_preds": torch.stack(ious)}
+
+    def _forward_heads_tc(self, tc, hs):
+        """bf16 serving path of the branches (uni3detr_head.py:456-496): Linear-LN-ReLU / Linear-ReLU stacks
+        as ops.linear_tc launches writing straight into the stacked fp32 outputs; the reg branch of level
+        l is the one the decoder already evaluated for its reference refinement (same weights, same
+        input: uni3detr_transformer.py:194-196), so its raw output is reused; one box-assembly kernel."""
+        from .. import ops
+        L_ = ops.linear_tc
+        nL, B, Q, E = hs.shape
+        R = B * Q
+        dev = hs.device
+        cls_out = torch.empty((nL, R, self.cls_out_channels), dtype=torch.float32, device=dev)
+        iou_out = torch.empty((nL, R, 1), dtype=torch.float32, device=dev)
+        box_out = torch.empty((nL, R, self.code_size), dtype=torch.float32, device=dev)
+        tmps = self.transformer.decoder.last_reg_tmp if self.with_box_refine else None
+        for lvl in range(nL):
+            x = hs[lvl].reshape(R, E)
+            c = x
+            for lin in tc["cls"][lvl][:-1]:
+                c = L_(c, lin, ln=True, relu_out=True)
+            L_(c, tc["cls"][lvl][-1], out_f32=True, out=cls_out[lvl])
+            i = L_(L_(x, tc["iou"][lvl][0], relu=True), tc["iou"][lvl][1], relu=True)
+            L_(i, tc["iou"][lvl][2], out_f32=True, out=iou_out[lvl])
+            if tmps is not None:
+                tmp = tmps[lvl]
+            else:
+                r = tc["reg"][lvl]
+                tmp = L_(L_(L_(x, r[0], relu=True), r[1], relu=True), r[2], out_f32=True)
+            # the transformer returns sigmoid(ref) and the reference takes inverse_sigmoid of it again
+            # (:129 -> :475); box_assemble does that round trip from the logits level l started from
+            ops.box_assemble(tmp, self.transformer.decoder.last_ref_logits[lvl], self.pc_range, out=box_out[lvl])
+        return {"all_cls_scores": cls_out.view(nL, B, Q, -1), "all_bbox_preds": box_out.view(nL, B, Q, -1),
+                "all_iou_preds": iou_out.view(nL, B, Q, 1)}
 
     def loss(self, *args, **kwargs):
         raise NotImplementedError("Uni3DETRHead.loss (Hungarian matching + SoftFocal/IoU3D losses) "

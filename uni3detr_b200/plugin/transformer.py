@@ -204,6 +204,9 @@ class Uni3DETRTransformerDecoder(nn.Module):
         self.query_scale = MLP(d_model, d_model, d_model, 3)
         self.ref_point_head = MLP(384, d_model, d_model, 3)
         self.compute_dtype = torch.float32
+        self.use_tensor_cores = True   # bf16: linears on tcgen05 with fused epilogues (ops.linear_tc)
+        self.last_reg_tmp = None       # per-layer raw reg-branch outputs (R, code) f32 of the last forward
+        self.last_ref_logits = None    # (R, 3) f32 reference logits each layer started from (+ the final ones)
         self._plan = None
         self._register_load_state_dict_pre_hook(lambda *a, **k: self.invalidate())
 
@@ -240,8 +243,37 @@ class Uni3DETRTransformerDecoder(nn.Module):
                 ffn=[_wb(ffn[0][0], dt), _wb(ffn[1], dt)]))
         self._plan = dict(dtype=dt, layers=layers,
                           query_scale=_mlp_plan(self.query_scale.layers, dt),
-                          ref_point_head=_mlp_plan(self.ref_point_head.layers, dt))
+                          ref_point_head=_mlp_plan(self.ref_point_head.layers, dt), tc=None)
+        dev = self.query_scale.layers[0].weight.device
+        if dt == torch.bfloat16 and dev.type == "cuda" and self.use_tensor_cores:
+            self._plan["tc"] = self._prepare_tc()
         return self._plan
+
+    def _prepare_tc(self):
+        """bf16 serving plan: every nn.Linear as a pre-swizzled tcgen05 operand with its bias (and the
+        LayerNorm that follows it) for ops.linear_tc (csrc/linear_tc.cu)."""
+        PL = ops.PackedLinear
+        E = self.embed_dims
+        ln_of = lambda n: (n.weight, n.bias, n.eps)
+        layers = []
+        for layer in self.layers:
+            mha, ca, ffn = layer.attentions[0].attn, layer.attentions[1], layer.ffns[0].layers
+            w, b = mha.in_proj_weight.detach(), mha.in_proj_bias.detach()
+            pe = ca.position_encoder
+            layers.append(dict(
+                heads=mha.num_heads,
+                in_qk=PL(w[:2 * E], b[:2 * E]), in_v=PL(w[2 * E:], b[2 * E:]),
+                out=PL(mha.out_proj.weight, mha.out_proj.bias, ln_of(layer.norms[0])),
+                gate_w=ca.attention_weights.weight.detach().float().reshape(-1).contiguous(),
+                gate_b=float(ca.attention_weights.bias.detach().float().item()),
+                pe0=tuple(t.detach().float().contiguous() for t in (pe[0].weight, pe[0].bias, pe[1].weight, pe[1].bias))
+                + (pe[1].eps,),
+                pe1=PL(pe[3].weight, pe[3].bias, ln_of(pe[4])),
+                oproj=PL(ca.output_proj.weight, ca.output_proj.bias, ln_of(layer.norms[1])),
+                ffn0=PL(ffn[0][0].weight, ffn[0][0].bias),
+                ffn1=PL(ffn[1].weight, ffn[1].bias, ln_of(layer.norms[2]))))
+        mlp = lambda m: [PL(l.weight, l.bias) for l in m.layers]
+        return dict(layers=layers, query_scale=mlp(self.query_scale), ref_point_head=mlp(self.ref_point_head))
 
     @torch.no_grad()
     def forward_batched(self, query, value_ndhwc, reference_points, nq, reg_plans=None):
@@ -259,6 +291,9 @@ class Uni3DETRTransformerDecoder(nn.Module):
         out = query.reshape(R, E).to(dt).contiguous()
         ref = reference_points.reshape(R, 3).float().contiguous()
         value = value_ndhwc.to(dt).contiguous()
+        self.last_reg_tmp = None
+        if p.get("tc") is not None and out.is_cuda and E == 256:
+            return self._forward_tc(p["tc"], out, value, ref, B, Q, nq, n_seq, reg_plans)
         inter, inter_ref = [], []
         for lid, L in enumerate(p["layers"]):
             sine = ops.sine_embed(ref, dt)
@@ -291,6 +326,61 @@ class Uni3DETRTransformerDecoder(nn.Module):
             return torch.stack(inter), torch.stack(inter_ref)
         return out.view(1, B, Q, E), ref.view(1, B, Q, 3)
 
+    def uses_tc(self):
+        p = self._plan
+        if p is None or p["dtype"] != self.compute_dtype:
+            p = self.prepare()
+        return p.get("tc") is not None
+
+    def reg_plans_of(self, reg_branches):
+        """Per-layer reg-branch linears in the form forward_batched consumes: packed tcgen05 operands
+        in the bf16 serving mode, (weight, bias) pairs otherwise."""
+        lins = [[m for m in br if isinstance(m, nn.Linear)] for br in reg_branches]
+        if self.uses_tc():
+            return [[ops.PackedLinear(m.weight, m.bias) for m in br] for br in lins]
+        return [[_wb(m, self.compute_dtype) for m in br] for br in lins]
+
+    def _forward_tc(self, T, out, value, ref, B, Q, nq, n_seq, reg_plans):
+        """bf16 serving path: every linear layer is one ops.linear_tc launch whose epilogue carries the
+        bias, ReLU, query_scale multiply, identity adds and LayerNorms that surround it in the reference
+        (uni3detr_transformer.py:179-202, :329-360; mmcv BaseTransformerLayer post-norm blocks) - no
+        library GEMM and no separate elementwise kernel between the neck and the heads."""
+        L_ = ops.linear_tc
+        E = self.embed_dims
+        R = B * Q
+        inter, inter_ref, tmps = [], [], []
+        ref_logits = [ref]                       # the reference logits every layer starts from
+        rph, qs = T["ref_point_head"], T["query_scale"]
+        for lid, L in enumerate(T["layers"]):
+            t = L_(L_(ops.sine_embed(ref, torch.bfloat16), rph[0], relu=True), rph[1], relu=True)
+            if lid == 0:
+                qpos, xq = L_(t, rph[2], add2=out)                       # query_pos, x + query_pos
+            else:
+                qraw = L_(t, rph[2])
+                sc = L_(L_(out, qs[0], relu=True), qs[1], relu=True)
+                qpos, xq = L_(sc, qs[2], mul=qraw, add2=out)             # query_scale(x) * raw, x + query_pos
+            qk = L_(xq, L["in_qk"])                                      # (R, 2E): q | k
+            v = L_(out, L["in_v"])
+            attn = ops.mha_core(qk[:, :E], qk[:, E:], v, n_seq, nq, L["heads"])
+            x = L_(attn, L["out"], res1=out, ln=True)                    # out-proj + identity + LN
+            s = ops.cross_sample(value, ref, x, qpos, L["gate_w"], L["gate_b"], Q)
+            pf = L_(ops.pos3_ln_relu(ref, *L["pe0"]), L["pe1"], ln=True, relu_out=True)
+            x = L_(s, L["oproj"], res1=x, res2=pf, ln=True)              # output_proj + identity + pos + LN
+            out = L_(L_(x, L["ffn0"], relu=True), L["ffn1"], res1=x, ln=True)
+            if reg_plans is not None:
+                rp = reg_plans[lid]
+                tmp, ref = L_(L_(L_(out, rp[0], relu=True), rp[1], relu=True), rp[2], out_f32=True, ref_in=ref)
+                tmps.append(tmp)
+            ref_logits.append(ref)
+            if self.return_intermediate:
+                inter.append(out.view(B, Q, E))
+                inter_ref.append(ref.view(B, Q, 3))
+        self.last_reg_tmp = tmps if reg_plans is not None else None
+        self.last_ref_logits = ref_logits
+        if self.return_intermediate:
+            return torch.stack(inter), torch.stack(inter_ref)
+        return out.view(1, B, Q, E), ref.view(1, B, Q, 3)
+
     def forward(self, query, key, value, query_pos, reference_points=None, reg_branches=None,
                 attn_masks=None, **kwargs):
         """Reference layout: query (nq,B,E) seq-first, value (B,1,C,D,H,W), one group."""
@@ -300,8 +390,7 @@ class Uni3DETRTransformerDecoder(nn.Module):
         vol = v.permute(0, 2, 3, 4, 1)
         reg = None
         if reg_branches is not None:
-            reg = [[_wb(m, self.compute_dtype) for m in br if isinstance(m, nn.Linear)]
-                   for br in reg_branches]
+            reg = self.reg_plans_of(reg_branches)
         hs, refs = self.forward_batched(query.permute(1, 0, 2), vol, reference_points, nq, reg)
         return hs.permute(0, 2, 1, 3), refs  # (L,nq,B,E), (L,B,nq,3)
 
@@ -338,7 +427,6 @@ class Uni3DETRTransformer(nn.Module):
         query = query_embed[..., :self.d_model]
         init_reference_out = reference_points.float().sigmoid()
         if reg_plans is None and reg_branches is not None:
-            dt = self.decoder.compute_dtype
-            reg_plans = [[_wb(m, dt) for m in br if isinstance(m, nn.Linear)] for br in reg_branches]
+            reg_plans = self.decoder.reg_plans_of(reg_branches)
         hs, refs = self.decoder.forward_batched(query, vol, reference_points, num_query, reg_plans)
         return hs.permute(0, 2, 1, 3), init_reference_out, refs.sigmoid()
