@@ -36,6 +36,14 @@ def emit(line):
 
 
 WORKLOAD = "sunrgbd"
+# BASELINE.json configs 2-5: workload -> (dtype, scenes per step per GPU, description). Config 2 is the metric's
+# configuration (the headline line); 3-5 are reported as extra blocks (`configs`) at their stated dtypes.
+WORKLOADS = {
+    "sunrgbd": ("bf16", 32, "uni3detr_sunrgbd.py synthetic 20k-pt scenes, 300 queries x4 groups, 3 decoder layers"),
+    "scannet_large": ("fp32", 4, "uni3detr_scannet_large.py synthetic 100k-pt scenes, dynamic voxelization, 300 queries x4 groups"),
+    "kitti": ("bf16", 8, "uni3detr_kitti_3classes.py synthetic 20k-pt lidar scenes, grid 41x1600x1408, 9 decoder layers"),
+    "nuscenes": ("fp32", 2, "uni3detr_nuscenes.py synthetic 200k-pt multi-sweep scenes, 900 queries x4 groups"),
+}
 RIDGE_NOTE = "bound = tensor if FLOP/byte of the launch exceeds measured bf16 peak / measured HBM peak, else hbm"
 
 
@@ -97,17 +105,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm ----
-def cpu_port_rate(n_scenes, threads, seed=0, warm=0):
+def cpu_port_rate(n_scenes, threads, seed=0, warm=0, workload=None):
     """Oracle (CPU port of the reference path, oracle/model.py) on `n_scenes` 20k-point scenes.
     Returns (scenes/sec, seconds). bench.py is one of the places allowed to execute oracle/."""
     import torch
     from oracle import model as M
     from uni3detr_b200 import synth
     torch.set_num_threads(threads)
-    model, cfg = synth.build_model(WORKLOAD, seed=0)
+    workload = workload or WORKLOAD
+    model, cfg = synth.build_model(workload, seed=0)
     sd = model.state_dict()
     rp = torch.rand(1, cfg["pts_bbox_head"]["num_query"], 3, generator=torch.Generator().manual_seed(seed))
-    scenes = [synth.make_scene(WORKLOAD, 100 + i) for i in range(n_scenes + warm)]
+    scenes = [synth.make_scene(workload, 100 + i) for i in range(n_scenes + warm)]
     for s in scenes[:warm]:
         M.forward(sd, cfg, [s], random_point=rp)
     t0 = time.perf_counter()
@@ -126,13 +135,13 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    steps, warm = max(1, args.steps), min(args.warmup, 1)
-    rate, dt = cpu_port_rate(steps, cores, warm=warm)
+    steps, warm = max(1, args.steps), min(args.warmup, 1)   # one 20k-point scene per step (~1.1 s on 16 cores)
+    rate, dt = cpu_port_rate(steps, cores, warm=warm, workload=args.workload)
     line = {"impl": "reference", "metric": "scenes/sec", "value": rate, "unit": "scenes/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": "uni3detr_sunrgbd.py synthetic 20k-pt scenes, 300 queries x4 groups, full forward",
-                       "scenes_per_step": 1},
+            "note": "warm-up clipped to 1 scene (each CPU step is ~1 s); --steps honoured",
+            "config": {"workload": WORKLOADS[args.workload][2] + ", full forward", "scenes_per_step": 1},
             "cpu_baseline": {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
                              "sample": f"{steps} scene(s), one per step, oracle/model.py full forward + decode"},
             "e2e": {"value": rate, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,6 +230,9 @@ def roofline_pass(step_fn, peaks, reps=3):
                 a["bytes"] += info["rows"] * info["C"] * info["esize"] * (8 + 2)
             elif name == "sine_embed":
                 a["bytes"] += info["bytes"]
+            elif name == "linear_tc":
+                a["bytes"] += (info["rows"] * (info["K"] + info["N"]) + info["N"] * info["K"]) * 2
+                a["flops"] += 2.0 * info["rows"] * info["K"] * info["N"]
             elif name == "mha_core":
                 r = info["n_seq"] * info["seq_len"]
                 a["bytes"] += r * info["heads"] * 32 * info["esize"] * 4
@@ -239,36 +251,26 @@ def roofline_pass(step_fn, peaks, reps=3):
     return roof, kernels[:12], ours_ms
 
 
-def run_gpu(args):
+def measure(workload, B, K, W, dtype_name, args, world, rank, dev, peaks, with_e2e=True, with_roofline=True):
+    """One workload: device-resident scenes/s (CUDA events per step, L2 flush between steps, max over ranks),
+    end-to-end scenes/s from pinned host points, roofline of the dominant libu3d kernel. Returns a dict."""
     import torch
     import torch.distributed as dist
     from uni3detr_b200 import ops, sharding, synth
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback); use --impl reference")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    peaks = load_peaks()
-
-    model, cfg = synth.build_model(WORKLOAD, seed=0)
+    dtype = torch.bfloat16 if dtype_name == "bf16" else torch.float32
+    model, cfg = synth.build_model(workload, seed=0)
     model = model.to(dev)
     model.set_compute_dtype(dtype)
     nq = cfg["pts_bbox_head"]["num_query"]
     coder = model.pts_bbox_head.bbox_coder
     # rank r owns scenes {i : i mod world == r} of the job's B*world scene pool (weak scaling)
     mine = sharding.scene_indices(B * world, rank, world)
-    host_pts = [torch.from_numpy(synth.make_scene(WORKLOAD, i)).pin_memory() for i in mine]
+    host_pts = [torch.from_numpy(synth.make_scene(workload, i)).pin_memory() for i in mine]
     dev_pts = [p.to(dev) for p in host_pts]
     rp = torch.rand(B, nq, 3, generator=torch.Generator().manual_seed(1234 + rank)).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    host_batch = torch.cat(host_pts, 0).pin_memory()                # (B*20000, C) pinned
+    host_batch = torch.cat(host_pts, 0).pin_memory()                # (B*n_points, C) pinned
 
     def eager_step(points):
         outs, _ = model.forward_raw(points, random_point=rp)
@@ -295,7 +297,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     if rank == 0:
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -316,52 +318,105 @@ def run_gpu(args):
     dev_s = sum(s.elapsed_time(e) for s, e in evs) / 1e3
     checksum = float(res[1].float().sum())
     scenes, t_max, checksum = sharding.reduce_metrics(B * K, dev_s, checksum, device=dev)
+    out = {"workload": workload, "value": scenes / t_max, "unit": "scenes/s", "ms_per_step": 1e3 * t_max / K,
+           "dtype": dtype_name, "scenes_per_step_per_gpu": B, "points_per_scene": int(host_pts[0].shape[0]),
+           "steps": K, "gpu_launches": launches, "clocks": clocks, "checksum": checksum,
+           "launch": "eager" if graphed is None else "CUDA graph replay (uni3detr_b200.GraphedForward)"}
 
     # ---- end to end through the reference-facing call with HOST buffers ("e2e")
-    out_host = None
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        if graphed is not None:
-            boxes, scores, labels, mask = step(host_batch)                # H2D of the batch inside
-        else:
-            boxes, scores, labels, mask = step([p.to(dev, non_blocking=True) for p in host_pts])
-        out_host = [t.cpu() for t in (boxes, scores, labels, mask)]      # D2H read of the step's result
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    _, e2e_max, _ = sharding.reduce_metrics(B * K, e2e_s, 0.0, device=dev)
-    h2d = sum(p.numel() * p.element_size() for p in host_pts)
-    d2h = sum(t.numel() * t.element_size() for t in out_host)
+    if with_e2e:
+        out_host = None
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            if graphed is not None:
+                boxes, scores, labels, mask = step(host_batch)                # H2D of the batch inside
+            else:
+                boxes, scores, labels, mask = step([p.to(dev, non_blocking=True) for p in host_pts])
+            out_host = [t.cpu() for t in (boxes, scores, labels, mask)]      # D2H read of the step's result
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        _, e2e_max, _ = sharding.reduce_metrics(B * K, e2e_s, 0.0, device=dev)
+        out["e2e"] = {"value": scenes / e2e_max, "unit": "scenes/s",
+                      "h2d_bytes_per_step": sum(p.numel() * p.element_size() for p in host_pts),
+                      "d2h_bytes_per_step": sum(t.numel() * t.element_size() for t in out_host)}
+    # ---- rank 0 only: roofline of the dominant libu3d kernel
+    if rank == 0 and with_roofline and not args.no_roofline:
+        out["roofline"], out["kernels"], out["libu3d_ms_per_step"] = roofline_pass(lambda: eager_step(dev_pts), peaks)
+    del graphed, model, dev_pts, flush
+    torch.cuda.empty_cache()
+    return out
 
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback); use --impl reference")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    peaks = load_peaks()
+    wl = args.workload
+    dtype_name = args.dtype or WORKLOADS[wl][0]
+    B = args.batch or WORKLOADS[wl][1]
+    main = measure(wl, B, K, W, dtype_name, args, world, rank, dev, peaks)
+
+    # extra blocks (every rank takes part: the metrics all-reduce is collective): the other BASELINE configs at
+    # their stated sizes / dtypes, and the headline workload at the reference's batch sizes 1 and 4 (latency)
+    extra, batches = [], {}
+    if not args.no_extra:
+        k2 = max(3, min(K, 5))
+        for b in (1, 4):
+            if wl == "sunrgbd" and b != B:
+                try:
+                    r = measure(wl, b, k2, 3, dtype_name, args, world, rank, dev, peaks, with_roofline=False)
+                    batches[str(b)] = {"value": r["value"], "ms_per_step": r["ms_per_step"],
+                                       "ms_per_scene": r["ms_per_step"] / b, "e2e": r["e2e"]["value"]}
+                except Exception as ex:   # noqa: BLE001  (report, never lose the headline line)
+                    batches[str(b)] = {"error": repr(ex)[:200]}
+        for name, (dt, b, desc) in WORKLOADS.items():
+            if name == wl:
+                continue
+            try:
+                r = measure(name, b, k2, 3, dt, args, world, rank, dev, peaks)
+                r["config"] = desc
+                r["kernels"] = (r.get("kernels") or [])[:8]
+                extra.append(r)
+            except Exception as ex:       # noqa: BLE001
+                extra.append({"workload": name, "error": repr(ex)[:300]})
+                torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- rank 0 only: roofline of the dominant libu3d kernel + CPU baseline
-    if args.no_roofline:      # profiler runs: skip the per-op timing pass (it launches profile-only kernels)
-        roof, kernels, ours_ms = None, [], None
-    else:
-        roof, kernels, ours_ms = roofline_pass(lambda: eager_step(dev_pts), peaks)
     cores = os.cpu_count() or 1
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, dt = cpu_port_rate(args.cpu_scenes, cores)
+        rate, dt = cpu_port_rate(args.cpu_scenes, cores, workload=wl)
         cpu = {"value": rate, "unit": "scenes/s", "cores": cores, "kind": "port",
                "sample": f"{args.cpu_scenes} scene(s) of the same workload, oracle/model.py full forward + decode, {dt:.1f} s"}
-    line = {"metric": "scenes/sec", "value": scenes / t_max, "unit": "scenes/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "uni3detr_sunrgbd.py synthetic 20k-pt scenes, 300 queries x4 groups, 3 decoder "
-                                   "layers, full forward (voxelize+sparse encoder+dense CNN+FPS+decoder+top-k)"
+    line = {"metric": "scenes/sec", "value": main["value"], "unit": "scenes/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
+            "config": {"workload": WORKLOADS[wl][2] + ", full forward (voxelize+sparse encoder+dense CNN+FPS+decoder+top-k)"
                                    + ("+per-class NMS" if args.postprocess else ""),
-                       "scenes_per_step_per_gpu": B, "points_per_scene": 20000, "parallelism": f"scenes sharded x{world}",
+                       "scenes_per_step_per_gpu": B, "points_per_scene": main["points_per_scene"],
+                       "parallelism": f"scenes sharded x{world}",
                        "l2": "256 MiB flush write between timed steps (untimed)", "timing": "CUDA events per step, max over ranks",
-                       "launch": "eager" if graphed is None else "CUDA graph replay (uni3detr_b200.GraphedForward)"},
-            "e2e": {"value": scenes / e2e_max, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "kernels": kernels, "libu3d_ms_per_step": ours_ms, "checksum": checksum}
+                       "launch": main["launch"]},
+            "e2e": main["e2e"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
+            "roofline": main.get("roofline"), "cpu_baseline": cpu, "kernels": main.get("kernels", []),
+            "libu3d_ms_per_step": main.get("libu3d_ms_per_step"), "checksum": main["checksum"],
+            "batches": batches, "configs": extra}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -372,8 +427,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="scenes per step per GPU")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default=WORKLOAD, choices=sorted(WORKLOADS),
+                    help="BASELINE config of the headline line (default: config 2, the metric's configuration)")
+    ap.add_argument("--batch", type=int, default=0, help="scenes per step per GPU (default: per workload, 32 for sunrgbd)")
+    ap.add_argument("--dtype", default=None, choices=["bf16", "fp32"], help="default: the workload's stated dtype")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the extra blocks (batch 1 / 4 of the headline workload, the other BASELINE configs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-scenes", type=int, default=10, help="bounded CPU-baseline sample (scenes, ~1.1 s each on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -383,8 +442,6 @@ def main():
                     help="also run get_bboxes' device post-processing (per-class NMS) inside the step")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps == 20:
-            args.steps = 3
         run_reference(args)
     else:
         run_gpu(args)

@@ -14,7 +14,7 @@ U3D_TN_SLICE_BUFS=1 timeout 300 python -m pytest tests/test_gpu_features.py test
 tail -3 gpurun_out/pytest_tn_deep.log
 run() {   # name, env assignments...
   local name=$1; shift
-  env "$@" timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-roofline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
+  env "$@" timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-roofline --no-extra > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
   echo "$name: $(cut -c1-110 gpurun_out/bench_$name.json)"
 }
 run default U3D_NOP=1

@@ -16,13 +16,14 @@ def scene_indices(total, rank, world):
 
 
 def reduce_metrics(scenes_done, elapsed_s, checksum, device="cpu"):
-    """One all-reduce: SUM of scenes and checksum, MAX of elapsed time (packed as a second
-    MAX-reduced lane of the same launch group). Returns (total scenes, max elapsed, checksum)."""
-    vec = torch.tensor([float(scenes_done), float(checksum)], dtype=torch.float64, device=device)
-    tmax = torch.tensor([float(elapsed_s)], dtype=torch.float64, device=device)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        work = [dist.all_reduce(vec, op=dist.ReduceOp.SUM, async_op=True),
-                dist.all_reduce(tmax, op=dist.ReduceOp.MAX, async_op=True)]
-        for w in work:
-            w.wait()
-    return float(vec[0]), float(tmax[0]), float(vec[1])
+    """ONE all-reduce for the whole job: every rank writes its (scenes, checksum, elapsed) into its own
+    3 lanes of a (world, 3) float64 vector that is zero elsewhere, the vector is SUM-reduced once, and
+    each rank reads the scene / checksum totals and the slowest rank's time from it.
+    Returns (total scenes, max elapsed, checksum)."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    vec = torch.zeros((world, 3), dtype=torch.float64, device=device)
+    vec[rank] = torch.tensor([float(scenes_done), float(checksum), float(elapsed_s)], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    return float(vec[:, 0].sum()), float(vec[:, 2].max()), float(vec[:, 1].sum())
