@@ -365,6 +365,10 @@ int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed,
  * tmp, out (rows, code) f32; ref_logit (rows,3) f32; pc_range: 6 host floats. */
 int u3d_box_assemble(const float* tmp, const float* ref_logit, int rows, int code, const float* pc_range,
                      float* out, void* stream);
+/* x = hi + lo, hi = x rounded to TF32 (round to nearest), lo = x - hi: operand split of the 3-pass "3xTF32"
+ * tensor-core evaluation of the fp32 dense convolutions (SECOND3D / SECOND3DFPN, models/backbones/second_3d.py:89-114,
+ * models/necks/second3d_fpn.py:112-143): conv(x,w) ~= conv(hi,w_hi) + conv(lo,w_hi) + conv(hi,w_lo), fp32 accumulate. */
+int u3d_split_tf32(const float* x, long long n, float* hi, float* lo, void* stream);
 /* relu(LayerNorm(ref @ w^T + b)): Linear(3 -> C) + LN + ReLU, the first stage of UniCrossAtten.position_encoder
  * (utils/uni3detr_transformer.py:253-260). ref (rows,3) f32, w (C,3) f32, b/gamma/beta (C) f32, C <= 256. */
 int u3d_pos3_ln_relu(const float* ref, const float* w, const float* b, const float* gamma, const float* beta,

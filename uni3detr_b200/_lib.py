@@ -128,6 +128,7 @@ SIGNATURES = {
     "u3d_linear_pack_weights": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "u3d_linear_tc": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _f32,
                              _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "u3d_split_tf32": (_i32, [_vp, ctypes.c_longlong, _vp, _vp, _vp]),
     "u3d_box_assemble": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "u3d_pos3_ln_relu": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _vp, _i32, _vp]),
     "u3d_nms3d_mask_words": (_sz, [_i32]),

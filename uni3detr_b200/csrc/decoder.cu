@@ -419,6 +419,30 @@ extern "C" int u3d_bias_act_sum(const void* x0, const void* x1, const void* x2, 
   return U3D_OK;
 }
 
+// x = hi + lo with hi the value rounded to TF32 (10 explicit mantissa bits, round to nearest on the 13
+// dropped bits) and lo the remainder: operands of the 3-pass "3xTF32" dense convolutions (second_3d.py).
+__global__ void k_split_tf32(const float* __restrict__ x, long long n, float* __restrict__ hi, float* __restrict__ lo) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    uint32_t b = __float_as_uint(v);
+    const uint32_t e = b & 0x7f800000u;
+    float h = v;
+    if (e != 0x7f800000u) h = __uint_as_float((b + 0x1000u) & 0xffffe000u);   // finite: round half up in magnitude
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+extern "C" int u3d_split_tf32(const float* x, long long n, float* hi, float* lo, void* stream) {
+  U3D_CHECK_ARG(x && hi && lo && n >= 0, "u3d_split_tf32: bad argument");
+  if (n == 0) return U3D_OK;
+  long long g = (n + 255) / 256;
+  if (g > kNumSMs * 16) g = kNumSMs * 16;
+  k_split_tf32<<<(int)g, 256, 0, (cudaStream_t)stream>>>(x, n, hi, lo);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
 extern "C" int u3d_sine_embed(const float* ref, int rows, void* out, int dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   U3D_CHECK_ARG(ref && out && rows >= 0, "u3d_sine_embed: bad argument");

@@ -44,6 +44,9 @@ def _timed(info=None):
                 return fn(*a, **k)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.current_stream().synchronize()   # each op is timed alone (profile mode only)
+            # keep the GPU busy (~150 us spin) while the host allocates / marshals / launches, so that the two
+            # events bracket the op's kernels only and not the Python time between them
+            torch.cuda._sleep(300000)
             s.record()
             r = fn(*a, **k)
             e.record()
@@ -652,3 +655,27 @@ def box_assemble(tmp, ref_logit, pc_range, out=None):
     pr, prp = _farr(pc_range)
     _lib.check(lib.u3d_box_assemble(_p(tmp), _p(ref_logit), rows, code, prp, _p(out), _stream()))
     return out
+
+
+def is_dense(x):
+    """Contiguous in the default or the channels-last layout of its rank (elementwise kernels may then
+    walk the storage linearly)."""
+    if x.is_contiguous():
+        return True
+    if x.dim() == 4:
+        return x.is_contiguous(memory_format=torch.channels_last)
+    if x.dim() == 5:
+        return x.is_contiguous(memory_format=torch.channels_last_3d)
+    return False
+
+
+def split_tf32(x):
+    """(hi, lo) with hi = x rounded to TF32 and lo = x - hi (both fp32, same shape / strides as x)."""
+    lib = _lib.load()
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise _lib.U3DError("split_tf32: x must be a CUDA fp32 tensor")
+    hi, lo = torch.empty_like(x), torch.empty_like(x)     # preserve_format: same memory layout as x
+    if not (is_dense(x) and hi.stride() == x.stride()):
+        raise _lib.U3DError("split_tf32: x must be dense (contiguous or channels-last)")
+    _lib.check(lib.u3d_split_tf32(_p(x), x.numel(), _p(hi), _p(lo), _stream()))
+    return hi, lo
