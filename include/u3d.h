@@ -375,6 +375,34 @@ int u3d_pos3_ln_relu(const float* ref, const float* w, const float* b, const flo
                      float eps, int rows, int C, void* out, int dtype, void* stream);
 
 /*
+ * Training-side entry points (csrc/train.cu). In the reference these steps are
+ * torch.autograd through spconv's indice_conv / F.grid_sample, scipy.optimize.linear_sum_assignment on the CPU
+ * and mmdet3d's bbox_overlaps_3d; all fp32.
+ */
+/* nbr_t[k][i] = o  <=>  nbr[k][o] = i, -1 elsewhere: the rulebook of the DATA gradient of a sparse conv
+ * (sparse_encoder_hd.py:106-138 under autograd): dX = u3d_spconv_fwd(dY, nbr_t, n_in, W_k^T). nbr_t: (K, t_stride). */
+int u3d_rulebook_transpose(const int32_t* nbr, int nbr_stride, const int32_t* n_out, int out_cap, int K,
+                           int32_t* nbr_t, int t_stride, int in_cap, void* stream);
+/* WEIGHT gradient of a sparse conv: dW[k][ci][co] = sum_o x[nbr[k][o]][ci] * dy[o][co]; dW (K,Cin,Cout) f32 (zeroed here). */
+int u3d_spconv_wgrad(const float* x, const float* dy, const int32_t* nbr, int nbr_stride, const int32_t* n_out,
+                     int out_cap, int K, int Cin, int Cout, float* dW, void* stream);
+/* Backward of u3d_cross_sample (utils/uni3detr_transformer.py:329-353 under autograd): given d_out (B*Q,C) returns
+ * d_value (B,D,H,W,C; scatter-add of the 8 trilinear corners; may be NULL), d_q = gradient w.r.t. (query + query_pos)
+ * through the sigmoid gate, d_gate_w (C), d_gate_b (1) and d_ref (B*Q,3) w.r.t. the reference-point logits. */
+int u3d_cross_sample_bwd(const float* value, int B, int D, int H, int W, int C, const float* ref, const float* query,
+                         const float* query_pos, const float* gate_w, float gate_b, int Q, const float* d_out,
+                         float* d_value, float* d_q, float* d_gate_w, float* d_gate_b, float* d_ref, void* stream);
+/* Pairwise-aligned rotated 3-D IoU, torch.diag(bbox_overlaps_3d(a, b, coordinate='lidar')) of
+ * dense_heads/uni3detr_head.py:690: boxes (n,7) [x,y,z(bottom),dx,dy,dz,yaw] -> out (n). */
+int u3d_iou3d_aligned(const float* a, const float* b, int n, float* out, void* stream);
+/* Minimum-cost assignment, one problem per CTA: replaces scipy.optimize.linear_sum_assignment in
+ * core/bbox/assigners/hungarian_assigner_3d.py:124-139 (one call per query group). cost: n_prob blocks of
+ * (rows, ld) f32 (prob_stride elements apart), rows <= cols; row_to_col (n_prob, rows) int32: the column of every row. */
+size_t u3d_hungarian_smem_bytes(int rows, int cols);
+int u3d_hungarian(const float* cost, long long prob_stride, int ld, int n_prob, int rows, int cols,
+                  int32_t* row_to_col, void* stream);
+
+/*
  * Per-class rotated-BEV-IoU NMS, batched over scenes.
  * Replaces: the per-class python loop over mmcv.ops.nms3d (iou3d_nms3d_forward) in
  * Uni3DETRHead.get_bboxes, models/dense_heads/uni3detr_head.py:847-871.

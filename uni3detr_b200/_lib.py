@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libu3d_b200.so")
 _SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_tn.cu", "tilesort.cu", "points.cu",
-            "fps.cu", "decoder.cu", "mha_tc.cu", "linear_tc.cu", "nms.cu"]
-_HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"),
+            "fps.cu", "decoder.cu", "mha_tc.cu", "linear_tc.cu", "train.cu", "nms.cu"]
+_HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"), os.path.join(_CSRC, "bev_geom.cuh"),
             os.path.join(_HERE, "..", "include", "u3d.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -128,6 +128,13 @@ SIGNATURES = {
     "u3d_linear_pack_weights": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "u3d_linear_tc": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _f32,
                              _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "u3d_rulebook_transpose": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _vp]),
+    "u3d_spconv_wgrad": (_i32, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "u3d_cross_sample_bwd": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _f32, _i32, _vp,
+                                    _vp, _vp, _vp, _vp, _vp, _vp]),
+    "u3d_iou3d_aligned": (_i32, [_vp, _vp, _i32, _vp, _vp]),
+    "u3d_hungarian_smem_bytes": (_sz, [_i32, _i32]),
+    "u3d_hungarian": (_i32, [_vp, ctypes.c_longlong, _i32, _i32, _i32, _i32, _vp, _vp]),
     "u3d_split_tf32": (_i32, [_vp, ctypes.c_longlong, _vp, _vp, _vp]),
     "u3d_box_assemble": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "u3d_pos3_ln_relu": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _vp, _i32, _vp]),

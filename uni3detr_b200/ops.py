@@ -679,3 +679,65 @@ def split_tf32(x):
         raise _lib.U3DError("split_tf32: x must be dense (contiguous or channels-last)")
     _lib.check(lib.u3d_split_tf32(_p(x), x.numel(), _p(hi), _p(lo), _stream()))
     return hi, lo
+
+
+# ------------------------------------------------------------------- training-side kernels ----
+def rulebook_transpose(nbr, n_out, out_cap, in_cap):
+    """(K, in_cap) table of the data gradient: nbr_t[k][i] = o iff nbr[k][o] = i (else -1)."""
+    lib = _lib.load()
+    K = nbr.shape[0]
+    pad = max((int(in_cap) + 127) // 128, 1) * 128
+    nbr_t = torch.empty((K, pad), dtype=torch.int32, device=nbr.device)[:, :max(int(in_cap), 1)]
+    _lib.check(lib.u3d_rulebook_transpose(_p(nbr), nbr.stride(0), _p(n_out), int(out_cap), K, _p(nbr_t),
+                                          nbr_t.stride(0), int(in_cap), _stream()))
+    return nbr_t
+
+
+def spconv_wgrad(x, dy, nbr, n_out, out_cap, K, Cin, Cout):
+    """dW (K,Cin,Cout) f32 = sum over rulebook pairs of x[in]^T dy[out]."""
+    lib = _lib.load()
+    _req(x, torch.float32, "x")
+    _req(dy, torch.float32, "dy")
+    dW = torch.empty((K, Cin, Cout), dtype=torch.float32, device=x.device)
+    _lib.check(lib.u3d_spconv_wgrad(_p(x), _p(dy), _p(nbr), nbr.stride(0), _p(n_out), int(out_cap), K, Cin, Cout,
+                                    _p(dW), _stream()))
+    return dW
+
+
+def cross_sample_bwd(value_ndhwc, ref, query, query_pos, gate_w, gate_b, Q, d_out, need_value_grad=True):
+    """Backward of cross_sample (fp32). Returns (d_value or None, d_q, d_gate_w, d_gate_b, d_ref)."""
+    lib = _lib.load()
+    B, D, H, W, C = value_ndhwc.shape
+    for t, n in ((value_ndhwc, "value"), (ref, "ref"), (query, "query"), (d_out, "d_out"), (gate_w, "gate_w")):
+        _req(t, torch.float32, n)
+    dev = query.device
+    d_value = torch.empty_like(value_ndhwc) if need_value_grad else None
+    d_q = torch.empty_like(query)
+    d_gw = torch.empty(C, dtype=torch.float32, device=dev)
+    d_gb = torch.empty(1, dtype=torch.float32, device=dev)
+    d_ref = torch.empty_like(ref)
+    _lib.check(lib.u3d_cross_sample_bwd(_p(value_ndhwc), B, D, H, W, C, _p(ref), _p(query), _p(query_pos), _p(gate_w),
+                                        float(gate_b), Q, _p(d_out), _p(d_value), _p(d_q), _p(d_gw), _p(d_gb),
+                                        _p(d_ref), _stream()))
+    return d_value, d_q, d_gw, d_gb, d_ref
+
+
+def iou3d_aligned(a, b):
+    """Rotated 3-D IoU of box pairs: a, b (n,7) f32 [x,y,z(bottom),dx,dy,dz,yaw] -> (n,) f32."""
+    lib = _lib.load()
+    _req(a, torch.float32, "a")
+    _req(b, torch.float32, "b")
+    out = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+    _lib.check(lib.u3d_iou3d_aligned(_p(a), _p(b), a.shape[0], _p(out), _stream()))
+    return out
+
+
+def hungarian(cost):
+    """cost (P, rows, cols) f32 CUDA, rows <= cols -> (P, rows) int32: the column assigned to every row by the
+    minimum-cost assignment (what scipy.optimize.linear_sum_assignment(cost[p]) returns as col_ind)."""
+    lib = _lib.load()
+    _req(cost, torch.float32, "cost")
+    P, rows, cols = cost.shape
+    out = torch.empty((P, rows), dtype=torch.int32, device=cost.device)
+    _lib.check(lib.u3d_hungarian(_p(cost), rows * cols, cols, P, rows, cols, _p(out), _stream()))
+    return out

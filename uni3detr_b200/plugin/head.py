@@ -3,7 +3,7 @@
 References: projects/mmdet3d_plugin/models/dense_heads/uni3detr_head.py:311-508 (forward),
 projects/mmdet3d_plugin/core/bbox/coders/nms_free_coder.py:9-136,
 projects/mmdet3d_plugin/core/bbox/util.py:44-80 (denormalize_bbox, mmdet3d>=1.0 branch).
-Loss / assigner / NMS post-processing are "next" rows and not built here.
+Training side (`loss`, targets, Hungarian assignment): uni3detr_head.py:510-793 via plugin/losses.py.
 """
 import copy
 import math
@@ -130,6 +130,18 @@ class Uni3DETRHead(nn.Module):
         self.sync_cls_avg_factor = sync_cls_avg_factor
         self.train_cfg, self.test_cfg = train_cfg, test_cfg
         self.loss_cfgs = dict(loss_cls=loss_cls, loss_bbox=loss_bbox, loss_iou=loss_iou)
+        # training side (uni3detr_head.py:340-356 + mmdet DETRHead.__init__): losses, assigner, pseudo sampler
+        from . import losses as LS
+        self.loss_cls = LS.build_loss(loss_cls) if loss_cls and loss_cls.get("type") in LS.LOSSES else None
+        self.loss_bbox = LS.build_loss(loss_bbox) if loss_bbox and loss_bbox.get("type") in LS.LOSSES else None
+        self.loss_iou = LS.build_loss(loss_iou) if loss_iou and loss_iou.get("type") in LS.LOSSES else None
+        self.bg_cls_weight = 0          # mmdet DETRHead: sigmoid classification has no background class weight
+        self.assigner = None
+        if train_cfg and train_cfg.get("assigner"):
+            a = dict(train_cfg["assigner"])
+            if a.pop("type") != "HungarianAssigner3D":
+                raise NotImplementedError("only HungarianAssigner3D (all shipped configs)")
+            self.assigner = LS.HungarianAssigner3D(**a)
         use_sigmoid = bool((loss_cls or {}).get("use_sigmoid", False))
         self.cls_out_channels = num_classes if use_sigmoid else num_classes + 1
         self.use_sigmoid_cls = use_sigmoid
@@ -315,9 +327,111 @@ class Uni3DETRHead(nn.Module):
         return {"all_cls_scores": cls_out.view(nL, B, Q, -1), "all_bbox_preds": box_out.view(nL, B, Q, -1),
                 "all_iou_preds": iou_out.view(nL, B, Q, 1)}
 
-    def loss(self, *args, **kwargs):
-        raise NotImplementedError("Uni3DETRHead.loss (Hungarian matching + SoftFocal/IoU3D losses) "
-                                  "is a 'next' row, SURVEY.md 8f rank 3")
+    # ------------------------------------------------------------------ training ---
+    def get_targets_batched(self, all_cls, all_box, gt_bboxes_list, gt_labels_list):
+        """uni3detr_head.py:510-621 (`_get_target_single` + `get_targets`) for every decoder layer at once.
+        all_cls (L,B,Q,C), all_box (L,B,Q,code); gt boxes (n_i,7) gravity-centre, labels (n_i,).
+        Returns labels (L,B,Q) long (num_classes = background), bbox_targets (L,B,Q,7), pos mask (L,B,Q) bool."""
+        L, B, Q, _ = all_cls.shape
+        dev = all_cls.device
+        labels = torch.full((L, B, Q), self.num_classes, dtype=torch.long, device=dev)
+        targets = torch.zeros((L, B, Q, 7), dtype=torch.float32, device=dev)
+        pos = torch.zeros((L, B, Q), dtype=torch.bool, device=dev)
+        for b in range(B):                                   # one matcher launch per image: L x G problems
+            gb, gl = gt_bboxes_list[b].to(dev).float(), gt_labels_list[b].to(dev).long()
+            if gb.shape[0] == 0:
+                continue
+            # reference quirk kept (uni3detr_head.py:542-543): `self.gt_repeattimes` is passed positionally and
+            # lands in assign()'s unused `eps` parameter, so the loss never repeats the ground-truth columns
+            inds = self.assigner.assign(all_box[:, b].detach(), all_cls[:, b].detach(), gb, gl, self.num_query,
+                                        None, self.gt_repeattimes)                     # (L, Q)
+            m = inds > 0
+            gi = (inds - 1).clamp(min=0)
+            pos[:, b] = m
+            labels[:, b] = torch.where(m, gl[gi], labels[:, b])
+            targets[:, b] = torch.where(m.unsqueeze(-1), gb[gi][..., :7], targets[:, b])
+        return labels, targets, pos
+
+    def loss_layers(self, all_cls, all_box, all_iou, gt_bboxes_list, gt_labels_list, normalize=True):
+        """`loss_single` (uni3detr_head.py:623-698) for all L decoder layers as batched tensor expressions.
+        Returns (loss_cls, loss_bbox, loss_iou, loss_iou_pred) each of shape (L,), and num_total_pos.
+        normalize=False returns the un-normalised sums (x loss weights) instead: the data-parallel train step
+        divides by the rank-averaged positive count AFTER its single gradient all-reduce."""
+        from . import losses as LS
+        L, B, Q, C = all_cls.shape
+        all_cls, all_box, all_iou = all_cls.float(), all_box.float(), all_iou.float()
+        labels, bbox_targets, pos = self.get_targets_batched(all_cls, all_box, gt_bboxes_list, gt_labels_list)
+        num_total_pos = int(pos[0].sum())                   # identical for every layer: all gts are matched
+        num_total_neg = B * Q - num_total_pos
+        if normalize:
+            cls_avg_factor = num_total_pos * 1.0 + num_total_neg * self.bg_cls_weight
+            if self.sync_cls_avg_factor:
+                cls_avg_factor = float(LS.reduce_mean(all_cls.new_tensor([cls_avg_factor])))
+            cls_avg_factor = max(cls_avg_factor, 1)
+            npos = float(torch.clamp(LS.reduce_mean(all_cls.new_tensor([float(num_total_pos)])), min=1))
+        else:
+            cls_avg_factor = npos = 1.0
+        N = B * Q
+        cls = all_cls.reshape(L, N, C)
+        box = all_box.reshape(L, N, -1)
+        tgt = bbox_targets.reshape(L, N, 7)
+        w = pos.reshape(L, N).float()
+        norm_tgt = LS.normalize_bbox(tgt, self.pc_range)
+        boxes3d = denormalize_bbox(box, self.pc_range)
+        iou3d = LS.bbox_overlaps_nearest_3d(boxes3d, tgt, is_aligned=True)
+        pc, tc = LS.bbox_to_corners_aa(boxes3d), LS.bbox_to_corners_aa(tgt)
+        z1, z2, z3, z4 = pc[..., 2], pc[..., 5], tc[..., 2], tc[..., 5]
+        iou_z = torch.max(torch.min(z2, z4) - torch.max(z1, z3), torch.zeros_like(z1)) / (torch.max(z2, z4) - torch.min(z1, z3))
+        iou3d_dec = (iou3d + iou_z) / 2
+        isnotnan = torch.isfinite(norm_tgt).all(dim=-1)
+        bw = w.unsqueeze(-1) * self.code_weights[:box.shape[-1]]
+        iou_true = LS.bbox_overlaps_3d_aligned(boxes3d.reshape(-1, 7), tgt.reshape(-1, 7)).reshape(L, N)
+        out = [[], [], [], []]
+        for l in range(L):                                   # L small reductions; everything above is batched
+            lc = self.loss_cls(cls[l], [labels[l].reshape(-1), iou3d_dec[l]], torch.ones(N, device=cls.device),
+                               avg_factor=cls_avg_factor)
+            nn_ = isnotnan[l]
+            lb = self.loss_bbox(box[l][nn_, :10], norm_tgt[l][nn_, :10], bw[l][nn_, :10], avg_factor=npos)
+            li = self.loss_iou(boxes3d[l][nn_, :10], tgt[l][nn_, :10], bw[l][nn_, :10], avg_factor=npos)
+            li = li + torch.sum((1 - iou_z[l][nn_]) * bw[l][nn_, 0]) / npos
+            lp = torch.sum(F.binary_cross_entropy_with_logits(all_iou[l].reshape(-1), iou_true[l], reduction="none")
+                           * bw[l][nn_, 0]) / npos * 1.2
+            for o, v in zip(out, (lc, lb, li, lp)):
+                o.append(v)
+        return tuple(torch.stack(o) for o in out), num_total_pos
+
+    def loss_single(self, cls_scores, bbox_preds, iou_preds, gt_bboxes_list, gt_labels_list, gt_bboxes_ignore_list=None):
+        """Reference API (uni3detr_head.py:623-698): one decoder layer, (B,Q,.) tensors."""
+        (lc, lb, li, lp), _ = self.loss_layers(cls_scores[None], bbox_preds[None], iou_preds[None], gt_bboxes_list,
+                                               gt_labels_list)
+        return lc[0], lb[0], li[0], lp[0]
+
+    @staticmethod
+    def _gt_tensor(gt_bboxes):
+        """(gravity_center, dims, yaw) rows from an mmdet3d box container or a plain (n,7+) tensor whose
+        first three columns already are the gravity centre (uni3detr_head.py:759-761)."""
+        if hasattr(gt_bboxes, "gravity_center"):
+            return torch.cat((gt_bboxes.gravity_center, gt_bboxes.tensor[:, 3:]), dim=1)
+        return gt_bboxes
+
+    def loss(self, gt_bboxes_list, gt_labels_list, preds_dicts, gt_bboxes_ignore=None, normalize=True):
+        """uni3detr_head.py:716-793: dict of the last layer's four losses + `d{i}.` entries of the others."""
+        assert gt_bboxes_ignore is None, f"{self.__class__.__name__} only supports for gt_bboxes_ignore setting to None."
+        if self.assigner is None or self.loss_cls is None:
+            raise RuntimeError("Uni3DETRHead.loss needs train_cfg.assigner and the loss configs")
+        if preds_dicts["all_bbox_preds"].shape[-1] != 8:
+            raise NotImplementedError("loss: code_size 8 (the reference truncates targets to 7 box values, :554)")
+        dev = preds_dicts["all_cls_scores"].device
+        gts = [self._gt_tensor(g).to(dev) for g in gt_bboxes_list]
+        (lc, lb, li, lp), npos = self.loss_layers(preds_dicts["all_cls_scores"], preds_dicts["all_bbox_preds"],
+                                                  preds_dicts["all_iou_preds"], gts, gt_labels_list, normalize)
+        d = {"loss_cls": lc[-1], "loss_bbox": lb[-1], "loss_iou": li[-1], "loss_iou_pred": lp[-1]}
+        for i in range(len(lc) - 1):
+            d[f"d{i}.loss_cls"], d[f"d{i}.loss_bbox"] = lc[i], lb[i]
+            d[f"d{i}.loss_iou"], d[f"d{i}.loss_iou_pred"] = li[i], lp[i]
+        if not normalize:
+            d["num_total_pos"] = torch.tensor(float(npos), device=dev)
+        return d
 
     def _score_thr(self, thr, like):
         """Per-class score_thr list as a device tensor, cached per (device, dtype): building it inside a
