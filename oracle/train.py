@@ -134,3 +134,16 @@ def loss(preds, gts, gls, nq, C, rep, code_weights=None):
         for n, v in zip(names, per[i]):
             d[f"d{i}.{n}"] = v
     return d
+
+
+def forward_train(sd, model_cfg, points_list, gts, gls):
+    """Uni3DETR.forward_train (detectors/uni3detr.py:232-266): train-mode forward (train max_voxels, BatchNorm
+    batch statistics, 3 query groups, dropout off) + the loss dict, differentiable w.r.t. the tensors in `sd`."""
+    head = model_cfg["pts_bbox_head"]
+    M.BN_TRAIN = True
+    try:
+        outs, _, _ = M.forward(sd, model_cfg, points_list, random_point=None, training=True, keep_graph=True)
+    finally:
+        M.BN_TRAIN = False
+    cw = torch.tensor(head.get("code_weights") or [1.0] * 8)
+    return loss(outs, gts, gls, head["num_query"], head["num_classes"], head.get("gt_repeattimes", 1), cw)

@@ -1,0 +1,139 @@
+"""Training step: backward kernels and the full forward_train under autograd.
+
+GPU tests: (1) each hand-written backward against torch.autograd of the plain-torch definition of the op,
+(2) Uni3DETR.forward_train - loss values and the gradient of EVERY parameter - against the oracle's CPU
+autograd (oracle/train.py forward_train) on the SUN-RGBD model dict with small clouds, dropout off.
+fp32; tolerance 1e-3 relative (max-norm per tensor), as north_star states for fp32 features.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import geometry as G
+from oracle import model as M
+from oracle import train as OT
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def _sparse_case(seed, n, dims, cin, cout):
+    rng = np.random.default_rng(seed)
+    D, H, W = dims
+    lin = rng.choice(D * H * W, size=n, replace=False)
+    coors = np.stack([np.zeros(n, np.int64), lin // (H * W), (lin // W) % H, lin % W], 1).astype(np.int32)
+    x = torch.from_numpy(rng.standard_normal((n, cin)).astype(np.float32))
+    w = torch.from_numpy((rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32))
+    return coors, x, w
+
+
+@pytest.mark.parametrize("cin,cout,strided", [(16, 16, False), (32, 64, True), (64, 64, False), (4, 16, False), (128, 96, False)])
+def test_sparse_conv_backward_vs_autograd(cin, cout, strided):
+    """SparseConvFn: dX through the transposed rulebook + dW from u3d_spconv_wgrad == autograd of the
+    oracle's index_add formulation."""
+    from uni3detr_b200 import ops
+    from uni3detr_b200.plugin.autograd import SparseConvFn
+    dims = (12, 20, 20)
+    coors, x, w = _sparse_case(cin * 7 + cout, 1500, dims, cin, cout)
+    if strided:
+        oc, nbr_np, od = G.down_rulebook(coors.astype(np.int64), dims, (2, 2, 2), (1, 1, 1))
+        n_out = len(oc)
+    else:
+        nbr_np, n_out = G.subm_rulebook(coors.astype(np.int64), dims), len(coors)
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    y_ref = M.sparse_conv(xr, nbr_np, wr.view(3, 3, 3, cin, cout), n_out)
+    g = torch.randn(y_ref.shape, generator=torch.Generator().manual_seed(1))
+    y_ref.backward(g)
+    nbr = torch.from_numpy(np.ascontiguousarray(nbr_np).astype(np.int32)).to(DEV).as_subclass(ops.Rulebook)
+    n_t = torch.tensor([n_out], dtype=torch.int32, device=DEV)
+    xg, wg = x.to(DEV).requires_grad_(), w.to(DEV).requires_grad_()
+    y = SparseConvFn.apply(xg, wg, nbr, n_t, n_out)
+    y.backward(g.to(DEV))
+    assert rel(y, y_ref) < 1e-4
+    assert rel(xg.grad, xr.grad) < 1e-4 and rel(wg.grad, wr.grad) < 1e-4
+
+
+def test_cross_sample_backward_vs_grid_sample_autograd():
+    """CrossSampleFn backward (8-corner scatter-add, gate, reference-point gradients) == autograd through
+    F.grid_sample(align_corners=False) + sigmoid gate, including out-of-volume corners."""
+    from uni3detr_b200.plugin.autograd import CrossSampleFn
+    g = torch.Generator().manual_seed(2)
+    B, D, H, W, C, Q = 2, 5, 9, 7, 64, 50
+    value = torch.randn(B, D, H, W, C, generator=g)
+    ref = torch.randn(B * Q, 3, generator=g) * 2.5          # some samples touch / leave the border
+    query, qpos = torch.randn(B * Q, C, generator=g), torch.randn(B * Q, C, generator=g)
+    gw, gb = torch.randn(1, C, generator=g) * 0.2, torch.randn(1, generator=g) * 0.1
+    d_out = torch.randn(B * Q, C, generator=g)
+    leaves = [t.clone().requires_grad_() for t in (value, ref, query, qpos, gw, gb)]
+    v, r, q, qp, w_, b_ = leaves
+    grid = ((r.sigmoid() - 0.5) * 2).view(B, 1, 1, Q, 3)
+    emb = F.grid_sample(v.permute(0, 4, 1, 2, 3), grid, align_corners=False)            # (B,C,1,1,Q)
+    emb = emb.view(B, C, Q).permute(0, 2, 1).reshape(B * Q, C)
+    out_ref = emb * torch.sigmoid((q + qp) @ w_.t() + b_)
+    out_ref.backward(d_out)
+    dl = [t.clone().to(DEV).requires_grad_() for t in (value, ref, query, qpos, gw, gb)]
+    out = CrossSampleFn.apply(*dl, Q)
+    out.backward(d_out.to(DEV))
+    assert rel(out, out_ref) < 1e-5
+    for name, a, b in zip(("value", "ref", "query", "query_pos", "gate_w", "gate_b"), dl, leaves):
+        assert rel(a.grad, b.grad) < 2e-4, (name, rel(a.grad, b.grad))
+
+
+def _gts(rng, n, pcr, C):
+    lo, hi = np.asarray(pcr[:3]), np.asarray(pcr[3:])
+    ctr = lo + (0.2 + 0.6 * rng.random((n, 3))) * (hi - lo)
+    box = np.concatenate([ctr, 0.4 + rng.random((n, 3)), (rng.random((n, 1)) - 0.5) * 3], 1).astype(np.float32)
+    return torch.from_numpy(box), torch.from_numpy(rng.integers(0, C, n))
+
+
+def test_forward_train_loss_and_all_gradients_vs_oracle():
+    """Whole training forward + backward on the device (hand-written sparse-conv / dense() / cross-sample
+    backward, cuDNN / cuBLAS autograd for the dense CNN and the linears, device matcher) against the oracle's
+    CPU autograd: every loss term and the gradient of every trainable parameter."""
+    from uni3detr_b200 import synth
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model, cfg = synth.build_model("sunrgbd", seed=0)
+    for m in model.modules():                                  # dropout off: deterministic comparison
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    scenes = [synth.make_scene("sunrgbd", 0, n_points=2500), synth.make_scene("sunrgbd", 1, n_points=1800)]
+    rng = np.random.default_rng(0)
+    pcr = cfg["pts_voxel_layer"]["point_cloud_range"]
+    gts, gls = zip(*[_gts(rng, n, pcr, 10) for n in (4, 6)])
+    # oracle: CPU autograd over a state dict of leaves
+    sd = {k: v.detach().clone().float() for k, v in model.state_dict().items()}
+    names = [k for k, p in model.named_parameters() if p.requires_grad]
+    for k in names:
+        sd[k].requires_grad_()
+    want = OT.forward_train(sd, cfg, scenes, list(gts), list(gls))
+    sum(want.values()).backward()
+    # product
+    model = model.to(DEV).train()
+    got = model(return_loss=True, points=[torch.from_numpy(s).to(DEV) for s in scenes], img_metas=[{}, {}],
+                gt_bboxes_3d=[t.to(DEV) for t in gts], gt_labels_3d=[t.to(DEV) for t in gls])
+    assert set(got) == set(want)
+    for k in want:
+        np.testing.assert_allclose(float(got[k]), float(want[k]), rtol=2e-3, atol=1e-5, err_msg=k)
+    sum(got.values()).backward()
+    params = dict(model.named_parameters())
+    worst = {}
+    for k in names:
+        gw = sd[k].grad
+        gp = params[k].grad
+        if gw is None:
+            assert gp is None or float(gp.abs().max()) == 0.0, k
+            continue
+        assert gp is not None, k
+        worst[k] = rel(gp, gw) if float(gw.abs().max()) > 1e-8 else float(gp.abs().max())
+    bad = {k: v for k, v in worst.items() if v > 5e-3}
+    print("max relative gradient error over %d parameters: %.2e" % (len(worst), max(worst.values())))
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]

@@ -69,8 +69,13 @@ class Uni3DETR(nn.Module):
         return self
 
     # ---------------------------------------------------------------- hot path ---
-    @torch.no_grad()
     def extract_pts_feat(self, pts, concat=None):
+        if self.training:
+            return self._extract_pts_feat(pts, concat)
+        with torch.no_grad():
+            return self._extract_pts_feat(pts, concat)
+
+    def _extract_pts_feat(self, pts, concat=None):
         """list[B] of (N_i,C) f32 -> x (B,256,D,H,W), fpsbpts (B,2nq,3) in [0,1].
         concat = (points (Ntot,C), pt_off (B+1) int32 device, lens) replaces `pts` with an already
         concatenated batch (static buffers of a captured CUDA graph)."""
@@ -136,10 +141,15 @@ class Uni3DETR(nn.Module):
         return self.forward_test(**kwargs)
 
     def forward_train(self, points=None, img_metas=None, gt_bboxes_3d=None, gt_labels_3d=None,
-                      **kwargs):
-        raise NotImplementedError(
-            "Uni3DETR.forward_train: backward kernels, matcher and losses are 'next' rows "
-            "(SURVEY.md 8f ranks 2-3); this build covers the inference forward")
+                      gt_labels=None, gt_bboxes=None, gt_bboxes_ignore=None, normalize=True, **kwargs):
+        """uni3detr.py:232-266 (+ forward_pts_train :192-214): features, head, loss dict. Call in .train() mode.
+        `normalize=False` returns the un-normalised loss sums + `num_total_pos` for the data-parallel step that
+        divides after its single all-reduce (uni3detr_b200/train.py)."""
+        if not self.training:
+            raise RuntimeError("Uni3DETR.forward_train: call model.train() first (BatchNorm statistics, query groups)")
+        pts_feat, fpsbpts = self.extract_pts_feat(points)
+        outs = self.pts_bbox_head(pts_feat, img_metas, fpsbpts)
+        return self.pts_bbox_head.loss(gt_bboxes_3d, gt_labels_3d, outs, normalize=normalize)
 
     def forward_test(self, img_metas, points=None, **kwargs):
         if not isinstance(img_metas, list):

@@ -248,10 +248,41 @@ class Uni3DETRHead(nn.Module):
                               inverse_sigmoid(random_point)], 1)
         return torch.cat([tgt.unsqueeze(0).expand(bs, -1, -1), refs], -1)
 
-    @torch.no_grad()
+    def forward_train(self, pts_feats, img_metas, fpsbpts):
+        """uni3detr_head.py:422-508 in training mode under autograd (fp32): 3 query groups (learned + the two
+        FPS groups, :437-443), decoder, per-level branches and box assembly as torch ops on the modules."""
+        query_embeds = self.build_queries(fpsbpts.float(), True)
+        if pts_feats.dim() == 5:
+            pts_feats = pts_feats.unsqueeze(1)
+        hs, init_reference, inter_references = self.transformer(
+            pts_feats, query_embeds, self.num_query,
+            reg_branches=self.reg_branches if self.with_box_refine else None, img_metas=img_metas)
+        hs = hs.permute(0, 2, 1, 3)
+        pc = self.pc_range
+        classes, coords, ious = [], [], []
+        for lvl in range(hs.shape[0]):
+            reference = inverse_sigmoid(init_reference if lvl == 0 else inter_references[lvl - 1])
+            tmp = self.reg_branches[lvl](hs[lvl])
+            xy = (tmp[..., 0:2] + reference[..., 0:2]).sigmoid()
+            z = (tmp[..., 4:5] + reference[..., 2:3]).sigmoid()
+            cx = xy[..., 0:1] * (pc[3] - pc[0]) + pc[0]
+            cy = xy[..., 1:2] * (pc[4] - pc[1]) + pc[1]
+            cz = z * (pc[5] - pc[2]) + pc[2]
+            coords.append(torch.cat([cx, cy, tmp[..., 2:4], cz, tmp[..., 5:]], dim=-1))
+            classes.append(self.cls_branches[lvl](hs[lvl]))
+            ious.append(self.iou_branches[lvl](hs[lvl]))
+        return {"all_cls_scores": torch.stack(classes), "all_bbox_preds": torch.stack(coords),
+                "all_iou_preds": torch.stack(ious)}
+
     def forward(self, pts_feats, img_metas, fpsbpts, random_point=None):
         """pts_feats (B,C,D,H,W); fpsbpts (B,2nq,3) in [0,1]. Returns the reference's dict of
         all_cls_scores (L,B,Q,cls), all_bbox_preds (L,B,Q,code), all_iou_preds (L,B,Q,1), fp32."""
+        if self.training:
+            return self.forward_train(pts_feats, img_metas, fpsbpts)
+        with torch.no_grad():
+            return self._forward_eval(pts_feats, img_metas, fpsbpts, random_point)
+
+    def _forward_eval(self, pts_feats, img_metas, fpsbpts, random_point=None):
         p = self._plan
         if p is None or p["dtype"] != self.compute_dtype:
             p = self.prepare()

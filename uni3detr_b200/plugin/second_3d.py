@@ -205,10 +205,20 @@ class SECOND3D(_PlanMixin, nn.Module):
                                   for b in self.blocks])
         return self._plan
 
-    @torch.no_grad()
     def forward(self, x):
         if self.training:
-            raise NotImplementedError("SECOND3D: training-mode BN is a 'next' row; call .eval()")
+            # second_3d.py:89-114 under autograd: the nn.Conv3d / BatchNorm3d(train) / ReLU stacks on cuDNN
+            outs = []
+            for blk in self.blocks:
+                y = blk(x)
+                outs.append(y)
+                if self.is_cascade:
+                    x = y
+            return tuple(outs)
+        with torch.no_grad():
+            return self._forward_eval(x)
+
+    def _forward_eval(self, x):
         p = self._plan
         if p is None or p["dtype"] != self.compute_dtype or p["as2d"] != self.conv2d_trick:
             p = self.prepare()
@@ -281,11 +291,21 @@ class SECOND3DFPN(_PlanMixin, nn.Module):
                           if self.extra_conv is not None else [])
         return self._plan
 
-    @torch.no_grad()
     def forward(self, x):
-        if self.training:
-            raise NotImplementedError("SECOND3DFPN: training-mode BN is a 'next' row; call .eval()")
         assert len(x) == len(self.in_channels)
+        if self.training:
+            # second3d_fpn.py:112-143 under autograd: upsample every level, sum, extra 3x3x3 convs
+            ups = [d(xi) for d, xi in zip(self.deblocks, x)]
+            out = ups[0]
+            for u in ups[1:]:
+                out = out + u
+            if self.extra_conv is not None:
+                out = self.extra_blocks(out)
+            return out
+        with torch.no_grad():
+            return self._forward_eval(x)
+
+    def _forward_eval(self, x):
         p = self._plan
         if p is None or p["dtype"] != self.compute_dtype or p["as2d"] != self.conv2d_trick:
             p = self.prepare()

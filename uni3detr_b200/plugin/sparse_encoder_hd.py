@@ -252,13 +252,61 @@ class SparseEncoderHD(nn.Module):
         return self._plan
 
     # --------------------------------------------------------------- forward ----
-    @torch.no_grad()
+    def forward_voxels_train(self, feats, coors, n_rows, cap, vmap, B):
+        """Training-mode forward under autograd (sparse_encoder_hd.py:106-138 with train-mode BatchNorm1d over
+        the active rows of the whole batch): fp32, exact-size feature matrices (the live row counts
+        are read back once per resolution), convs through autograd.SparseConvFn (data gradient = the same
+        gather-GEMM over the transposed rulebook, weight gradient = u3d_spconv_wgrad), BN / ReLU / identity add
+        as torch ops on the (n, C) matrices, dense() through autograd.ToDenseFn."""
+        from .autograd import SparseConvFn, ToDenseFn
+        n = int(n_rows)                                           # host sync: once per resolution in training
+        x = feats[:n].float().contiguous()
+        level = dict(coors=coors, n_t=n_rows, n=n, vmap=vmap, nbr=None, dims=tuple(self.sparse_shape))
+        saved = None
+        for s in self.layer_specs():
+            conv = s["conv"]
+            k = conv.kernel_size[0] * conv.kernel_size[1] * conv.kernel_size[2]
+            w = conv.weight.reshape(k, conv.in_channels, conv.out_channels)
+            if k == 1:
+                nbr, out_level = None, level
+            elif conv.subm:
+                if level["nbr"] is None:
+                    level["nbr"] = ops.rulebook_subm(level["coors"], level["n_t"], level["n"], level["vmap"])
+                nbr, out_level = level["nbr"], level
+            else:
+                oc, on, ovm, nbr, ocap = ops.rulebook_down(level["coors"], level["n_t"], level["n"], level["vmap"],
+                                                           conv.stride, conv.padding)
+                m = int(on)
+                nbr = nbr[:, :m].as_subclass(ops.Rulebook) if m < nbr.shape[1] else nbr
+                out_level = dict(coors=oc, n_t=on, n=m, vmap=ovm, nbr=None, dims=ovm.dims)
+            if s["save"]:
+                saved = x
+            y = SparseConvFn.apply(x, w, nbr, out_level["n_t"], out_level["n"])
+            if conv.bias is not None:
+                y = y + conv.bias
+            if s["bn"] is not None:
+                y = s["bn"](y)                                    # train mode: batch statistics over active rows
+            if s["add"]:
+                y = y + saved
+                saved = None
+            x = torch.relu(y) if s["relu"] else y
+            level = out_level
+        dense = ToDenseFn.apply(x, level["coors"], level["n_t"], level["n"], B, tuple(level["dims"]))
+        out = dense.permute(0, 4, 1, 2, 3)
+        if not self.keep_depth:
+            out = out.sum(dim=2)
+        self.last_level = level
+        return out
+
     def forward_voxels(self, feats, coors, n_rows, cap, vmap, B, channels_last=True):
         """feats (cap,Cin) f32/bf16, coors (cap,4) int32, n_rows device int32 (1,), vmap level-0
         VoxelMap. Returns the dense volume (B,C,D,H,W) (channels_last_3d strides by default)."""
         if self.training:
-            raise NotImplementedError("SparseEncoderHD: training-mode BN is a 'next' row "
-                                      "(SURVEY.md 8f); call .eval()")
+            return self.forward_voxels_train(feats, coors, n_rows, cap, vmap, B)
+        with torch.no_grad():
+            return self._forward_voxels_eval(feats, coors, n_rows, cap, vmap, B, channels_last)
+
+    def _forward_voxels_eval(self, feats, coors, n_rows, cap, vmap, B, channels_last=True):
         plan = self._plan
         if plan is None or plan["dtype"] != self.compute_dtype or plan["tc"] != self.use_tensor_cores:
             plan = self.prepare()
@@ -326,7 +374,6 @@ class SparseEncoderHD(nn.Module):
         self.last_level = level
         return out
 
-    @torch.no_grad()
     def forward(self, voxel_features, coors, batch_size):
         """Reference API (sparse_encoder_hd.py:106-138): exact-size (N,C) features and (N,4)
         int32 [b,z,y,x] coordinates -> (B,C,D,H,W)."""

@@ -154,6 +154,16 @@ class BaseTransformerLayer(nn.Module):
         self.norms = nn.ModuleList([nn.LayerNorm(self.embed_dims) for _ in range(3)])
 
 
+def get_sine_pos_embed(pos, num_pos_feats=128, temperature=10000):
+    """uni3detr_transformer.py:33-65 as differentiable torch ops (the training path; inference uses the
+    u3d_sine_embed kernel): pos (..., 3) in [0,1] -> (..., 3*128), [sin v0, cos v1, sin v2, ...] per coordinate."""
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=pos.device)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    v = pos.unsqueeze(-1) * (2 * math.pi) / dim_t                                   # (..., 3, F)
+    e = torch.stack((v[..., 0::2].sin(), v[..., 1::2].cos()), dim=-1).flatten(-2)   # interleave
+    return e.flatten(-2)
+
+
 def _wb(lin, dtype):
     return (lin.weight.detach().to(dtype).contiguous(), lin.bias.detach().to(dtype).contiguous())
 
@@ -326,6 +336,54 @@ class Uni3DETRTransformerDecoder(nn.Module):
             return torch.stack(inter), torch.stack(inter_ref)
         return out.view(1, B, Q, E), ref.view(1, B, Q, 3)
 
+    def forward_train_batched(self, query, value_ndhwc, reference_points, nq, reg_branches=None):
+        """Training-mode decoder under autograd, fp32 (uni3detr_transformer.py:145-212 + mmcv BaseTransformerLayer,
+        SURVEY A.8), the G query groups folded into the batch like the inference path. Linears / LayerNorm /
+        nn.MultiheadAttention run as torch ops on the module parameters; the UniCrossAtten sampling block is
+        autograd.CrossSampleFn (u3d_cross_sample forward, u3d_cross_sample_bwd backward). Dropouts follow the
+        modules' probabilities (mmcv: attention dropout + output dropout 0.1, FFN 0.1, UniCrossAtten 0.1)."""
+        from .autograd import CrossSampleFn
+        B, Q, E = query.shape
+        G = Q // nq
+        R, n_seq = B * Q, B * G
+        out = query.reshape(R, E).float()
+        ref = reference_points.reshape(R, 3).float()
+        value = value_ndhwc.float().contiguous()
+        inter, inter_ref = [], []
+        tr = self.training
+
+        def mlp(m, x):
+            for i, l in enumerate(m.layers):
+                x = F.relu(l(x)) if i < m.num_layers - 1 else l(x)
+            return x
+        for lid, layer in enumerate(self.layers):
+            qpos = mlp(self.ref_point_head, get_sine_pos_embed(ref.sigmoid()))
+            if lid != 0:
+                qpos = mlp(self.query_scale, out) * qpos
+            mha, ca, ffn = layer.attentions[0], layer.attentions[1], layer.ffns[0].layers
+            # self attention: nn.MultiheadAttention over (nq, n_seq, E), q = k = x + pos, v = x (+ identity, dropout)
+            x3 = out.view(n_seq, nq, E).transpose(0, 1)
+            qk = (out + qpos).view(n_seq, nq, E).transpose(0, 1)
+            att = mha.attn(qk, qk, value=x3, need_weights=False)[0].transpose(0, 1).reshape(R, E)
+            x = layer.norms[0](out + F.dropout(att, mha.attn.dropout, tr))
+            # cross attention (uni3detr_transformer.py:318-360)
+            s = CrossSampleFn.apply(value, ref, x, qpos, ca.attention_weights.weight, ca.attention_weights.bias, Q)
+            o = F.dropout(ca.output_proj(s), ca.dropout.p, tr)
+            x = layer.norms[1](o + x + ca.position_encoder(ref))
+            # FFN
+            h = F.dropout(F.relu(ffn[0][0](x)), ffn[0][2].p, tr)
+            x = layer.norms[2](x + F.dropout(ffn[1](h), ffn[2].p, tr))
+            out = x
+            if reg_branches is not None:
+                tmp = reg_branches[lid](out)
+                ref = (ref + torch.stack((tmp[:, 0], tmp[:, 1], tmp[:, 4]), dim=1)).detach()
+            if self.return_intermediate:
+                inter.append(out.view(B, Q, E))
+                inter_ref.append(ref.view(B, Q, 3))
+        if self.return_intermediate:
+            return torch.stack(inter), torch.stack(inter_ref)
+        return out.view(1, B, Q, E), ref.view(1, B, Q, 3)
+
     def uses_tc(self):
         p = self._plan
         if p is None or p["dtype"] != self.compute_dtype:
@@ -415,7 +473,6 @@ class Uni3DETRTransformer(nn.Module):
             if isinstance(m, UniCrossAtten):
                 m.init_weight()
 
-    @torch.no_grad()
     def forward(self, pts_value, query_embed, num_query, reg_branches=None, reg_plans=None,
                 **kwargs):
         """pts_value (B,1,C,D,H,W) / (B,C,D,H,W); query_embed (B,Q,256+3).
@@ -425,6 +482,13 @@ class Uni3DETRTransformer(nn.Module):
         vol = v.permute(0, 2, 3, 4, 1)
         reference_points = query_embed[..., self.d_model:]
         query = query_embed[..., :self.d_model]
+        if self.training:
+            hs, refs = self.decoder.forward_train_batched(query, vol, reference_points, num_query, reg_branches)
+            return hs.permute(0, 2, 1, 3), reference_points.float().sigmoid(), refs.sigmoid()
+        with torch.no_grad():
+            return self._forward_eval(vol, query, reference_points, num_query, reg_branches, reg_plans)
+
+    def _forward_eval(self, vol, query, reference_points, num_query, reg_branches, reg_plans):
         init_reference_out = reference_points.float().sigmoid()
         if reg_plans is None and reg_branches is not None:
             reg_plans = self.decoder.reg_plans_of(reg_branches)
