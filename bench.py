@@ -437,6 +437,74 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """--train: data-parallel TRAINING steps of the same model (SURVEY.md 8f rank 2 / BASELINE configs 4-5 "DDP"):
+    forward_train under autograd (hand-written sparse-conv / cross-sample backward, device matcher + losses),
+    ONE flat gradient all-reduce per step over NCCL (uni3detr_b200/train.py), AdamW. Not the headline metric:
+    reported as its own JSON line with `"mode": "train"`."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from uni3detr_b200 import ops, sharding, synth
+    from uni3detr_b200.train import DataParallelTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --train: no CUDA device")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = args.workload
+    B = args.batch or 4                                   # samples_per_gpu of the reference configs
+    K, W = args.steps, max(args.warmup, 3)
+    model, cfg = synth.build_model(wl, seed=0)
+    model = model.to(dev).train()
+    trainer = DataParallelTrainer(model)
+    pcr = np.asarray(cfg["pts_voxel_layer"]["point_cloud_range"], np.float64)
+    ncls = cfg["pts_bbox_head"]["num_classes"]
+    mine = sharding.scene_indices(B * world, rank, world)
+    pts = [torch.from_numpy(synth.make_scene(wl, i)).to(dev) for i in mine]
+    rng = np.random.default_rng(7 + rank)
+    gts, gls = [], []
+    for _ in mine:
+        n = int(rng.integers(3, 9))
+        ctr = pcr[:3] + (0.2 + 0.6 * rng.random((n, 3))) * (pcr[3:] - pcr[:3])
+        box = np.concatenate([ctr, 0.4 + rng.random((n, 3)), (rng.random((n, 1)) - 0.5) * 3], 1).astype(np.float32)
+        gts.append(torch.from_numpy(box).to(dev))
+        gls.append(torch.from_numpy(rng.integers(0, ncls, n)).to(dev))
+    first = None
+    for _ in range(W):
+        l = trainer.step(pts, gts, gls)
+        first = first or {k: float(v) for k, v in l.items()}
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n0 = ops.launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(K):
+        l = trainer.step(pts, gts, gls)
+    e.record()
+    torch.cuda.synchronize()
+    launches = ops.launch_count() - n0
+    scenes, t_max, _ = sharding.reduce_metrics(B * K, s.elapsed_time(e) / 1e3, 0.0, device=dev)
+    if rank == 0:
+        last = {k: float(v) for k, v in l.items()}
+        emit({"mode": "train", "metric": "train scenes/sec", "value": scenes / t_max, "unit": "scenes/s", "n_gpus": world,
+              "steps": K, "warmup": W, "ms_per_step": 1e3 * t_max / K, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+              "config": {"workload": WORKLOADS[wl][2] + ", forward_train + backward + AdamW", "scenes_per_step_per_gpu": B,
+                         "parallelism": f"scenes sharded x{world}, one flat gradient all-reduce per step"},
+              "collective": {"all_reduce_per_step": trainer.collectives_per_step, "bytes": int(trainer.flat.numel() * 4),
+                             "backend": "nccl" if world > 1 else None},
+              "gpu_launches": launches, "loss_total_first": sum(first.values()), "loss_total_last": sum(last.values())})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -455,7 +523,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--postprocess", action="store_true",
                     help="also run get_bboxes' device post-processing (per-class NMS) inside the step")
+    ap.add_argument("--train", action="store_true", help="time data-parallel training steps instead of the forward")
     args = ap.parse_args()
+    if args.train:
+        return run_train(args)
     if args.impl == "reference":
         run_reference(args)
     else:
