@@ -187,12 +187,18 @@ def test_sine_embed_golden(golden):
     np.testing.assert_allclose(out.cpu().numpy().reshape(golden["sine_out"].shape), golden["sine_out"], atol=2e-5)
 
 
-@pytest.mark.parametrize("qsplit", ["0", "1"])   # tcgen05 kernel: 0 = one CTA loops over the query blocks, 1 = CTA per block
-@pytest.mark.parametrize("seq_len,n_seq", [(300, 8), (900, 2), (5, 4), (64, 3), (129, 1)])
+# bf16 kernels: "v2" = mha_tc2.cu (default: persistent, P in TMEM, TMA loads); "v1q0" / "v1q1" = the first tcgen05 kernel
+# (U3D_MHA_V1=1) with one CTA looping over the query blocks / one CTA per block; fp32 = the SIMT kernel
+@pytest.mark.parametrize("variant", ["v2", "v1q0", "v1q1"])
+@pytest.mark.parametrize("seq_len,n_seq", [(300, 8), (900, 2), (5, 4), (64, 3), (129, 1), (300, 40), (161, 5), (1024, 1)])
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
-def test_mha_core(seq_len, n_seq, dtype, tol, qsplit, monkeypatch):
+def test_mha_core(seq_len, n_seq, dtype, tol, variant, monkeypatch):
     from uni3detr_b200 import ops
-    monkeypatch.setenv("U3D_MHA_QSPLIT", qsplit)
+    if variant != "v2":
+        if dtype == torch.float32:
+            pytest.skip("fp32 has one kernel")
+        monkeypatch.setenv("U3D_MHA_V1", "1")
+        monkeypatch.setenv("U3D_MHA_QSPLIT", variant[-1])
     g = torch.Generator().manual_seed(seq_len)
     heads, E = 8, 256
     qk = torch.randn(n_seq * seq_len, 2 * E, generator=g).to(dtype)

@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "libu3d_b200.so")
 _SOURCES = ["voxmap.cu", "voxelize.cu", "rulebook.cu", "spconv_simt.cu", "spconv_tc.cu", "spconv_tn.cu", "tilesort.cu", "points.cu",
-            "fps.cu", "decoder.cu", "mha_tc.cu", "linear_tc.cu", "train.cu", "nms.cu"]
-_HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"), os.path.join(_CSRC, "bev_geom.cuh"),
+            "fps.cu", "decoder.cu", "mha_tc.cu", "mha_tc2.cu", "linear_tc.cu", "train.cu", "nms.cu"]
+_HEADERS = [os.path.join(_CSRC, "common.cuh"), os.path.join(_CSRC, "tc_common.cuh"), os.path.join(_CSRC, "bev_geom.cuh"), os.path.join(_CSRC, "tma.cuh"),
             os.path.join(_HERE, "..", "include", "u3d.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

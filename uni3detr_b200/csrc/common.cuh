@@ -153,6 +153,10 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride,
 bool spconv_tn_supported(int Cin, int Cout, const int32_t* nbr);
 bool mha_tc_supported(int seq_len, int ldq, int ldk, int ldv, const void* q, const void* k, const void* v,
                       const void* out);
+bool mha_tc2_supported(int seq_len, int ldq, int ldk, int ldv, const void* q, const void* k, const void* v,
+                       const void* out);
+int mha_core_tc2(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int n_seq,
+                 int seq_len, int heads, void* out, cudaStream_t st);
 int mha_core_tc(const void* q, const void* k, const void* v, int ldq, int ldk, int ldv, int n_seq,
                 int seq_len, int heads, void* out, cudaStream_t st);
 

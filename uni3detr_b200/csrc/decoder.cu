@@ -465,9 +465,13 @@ extern "C" int u3d_mha_core(const void* q, const void* k, const void* v, int ldq
   U3D_CHECK_ARG(n_seq <= 65535 && heads <= 65535, "u3d_mha_core: grid too large");
   U3D_CHECK_ARG(dtype == U3D_F32 || dtype == U3D_BF16, "u3d_mha_core: bad dtype");
   // bf16: tcgen05 kernel (mha_tc.cu); fp32 (parity mode) and unsupported shapes: SIMT kernel below
-  if (dtype == U3D_BF16 && getenv("U3D_MHA_SIMT") == nullptr &&
-      mha_tc_supported(seq_len, ldq, ldk, ldv, q, k, v, out))
-    return mha_core_tc(q, k, v, ldq, ldk, ldv, n_seq, seq_len, heads, out, st);
+  if (dtype == U3D_BF16 && getenv("U3D_MHA_SIMT") == nullptr) {
+    // v2 (mha_tc2.cu: persistent, three warpgroups, P in TMEM, TMA loads) unless U3D_MHA_V1=1 asks for the first kernel
+    if (getenv("U3D_MHA_V1") == nullptr && mha_tc2_supported(seq_len, ldq, ldk, ldv, q, k, v, out))
+      return mha_core_tc2(q, k, v, ldq, ldk, ldv, n_seq, seq_len, heads, out, st);
+    if (mha_tc_supported(seq_len, ldq, ldk, ldv, q, k, v, out))
+      return mha_core_tc(q, k, v, ldq, ldk, ldv, n_seq, seq_len, heads, out, st);
+  }
   dim3 grid(cdiv(seq_len, kQBlock), heads, n_seq);
   if (dtype == U3D_F32)
     k_mha_core<float><<<grid, kMhaWarps * 32, 0, st>>>((const float*)q, (const float*)k,

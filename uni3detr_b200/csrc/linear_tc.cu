@@ -23,13 +23,13 @@
 //            bf16 (or fp32 for the narrow final heads) stores, optional second output out + add2
 //            (the next GEMM's A operand, e.g. x + query_pos).
 // N > 256 (in_proj 512, FFN 512) runs as independent 256-column halves.
-#include <cuda.h>
-#include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace u3d {
 namespace lin {
 
 using namespace tc;
+using namespace tma;
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
@@ -91,23 +91,6 @@ struct Smem {
   float2 stat[2][kBM];
 };
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1), "r"(src)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(kEpiThreads) : "memory");
 }
@@ -513,22 +496,6 @@ __global__ void k_box_assemble(const float* __restrict__ tmp, const float* __res
   o[4] = bz * sz + z0;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 }  // namespace lin
 }  // namespace u3d
 
@@ -576,22 +543,6 @@ int u3d_linear_pack_weights(const void* w, int N, int K, void* packed, void* str
   k_linear_pack<<<cdiv(total, 256) < 1024 ? cdiv(total, 256) : 1024, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)w, N, K, n_pass, passes, (__nv_bfloat16*)packed);
   U3D_LAUNCH_CHECK();
-  return U3D_OK;
-}
-
-static int encode_2d(lin::EncodeTiledFn enc, CUtensorMap* map, const void* base, int cols, int rows, int ld,
-                     int box_cols, int box_rows) {
-  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult cr = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) {
-    u3d::set_error("linear: cuTensorMapEncodeTiled failed (%d) cols=%d rows=%d ld=%d", (int)cr, cols, rows, ld);
-    return U3D_EINVAL;
-  }
   return U3D_OK;
 }
 
@@ -644,10 +595,8 @@ int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed,
   if (!(flags & F_RES1)) P.res1 = nullptr;
   if (!(flags & F_RES2)) P.res2 = nullptr;
 
-  EncodeTiledFn enc = encode_tiled_fn();
-  U3D_CHECK_ARG(enc != nullptr, "linear: cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMap tmap_a, tmap_in0, tmap_out, tmap_out2;
-  if (encode_2d(enc, &tmap_a, a, K, rows, lda, kBK, kBM) != U3D_OK) return U3D_EINVAL;
+  if (tma::encode_2d_bf16(&tmap_a, a, K, rows, lda, kBK, kBM) != U3D_OK) return U3D_EINVAL;
   tmap_in0 = tmap_a;
   tmap_out = tmap_a;
   tmap_out2 = tmap_a;
@@ -660,9 +609,9 @@ int u3d_linear_tc(const void* a, int lda, int rows, int K, const void* w_packed,
     if (P.mul) { in0 = P.mul; P.in0_kind = 1; P.mul = nullptr; }
     else if (P.res1) { in0 = P.res1; P.in0_kind = 2; P.res1 = nullptr; }
     else if (P.res2) { in0 = P.res2; P.in0_kind = 2; P.res2 = nullptr; }
-    if (in0 && encode_2d(enc, &tmap_in0, in0, N, rows, ldr, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
-    if (encode_2d(enc, &tmap_out, out, N, rows, ldo, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
-    if ((flags & F_OUT2) && encode_2d(enc, &tmap_out2, out2, N, rows, ldr, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
+    if (in0 && tma::encode_2d_bf16(&tmap_in0, in0, N, rows, ldr, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
+    if (tma::encode_2d_bf16(&tmap_out, out, N, rows, ldo, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
+    if ((flags & F_OUT2) && tma::encode_2d_bf16(&tmap_out2, out2, N, rows, ldr, kSlab, kBM) != U3D_OK) return U3D_EINVAL;
   }
 
   const size_t header = (sizeof(Smem) + 1023) & ~(size_t)1023;
