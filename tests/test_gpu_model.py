@@ -184,7 +184,7 @@ def test_reference_call_convention():
         assert set(r) == {"boxes_3d", "scores_3d", "labels_3d"}
         assert r["boxes_3d"].shape[1] == 7 and r["scores_3d"].ndim == 1
         assert r["labels_3d"].max() < 10
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):       # forward_train needs model.train() (tests/test_train.py covers it)
         model(return_loss=True, points=pts, img_metas=[{}, {}])
 
 
