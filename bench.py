@@ -203,8 +203,9 @@ def roofline_pass(step_fn, peaks, reps=3):
         live_rows = 0   # live rows of the current sparse level = input rows of the next conv
         seen = {}
         for name, info, ms in ops.profile_end():
-            if name in ("spconv_fwd", "spconv_fwd_packed"):
-                key = f"{'spconv_tc' if name.endswith('packed') else 'spconv_simt'}[{info['K']}x{info['Cin']}->{info['Cout']}]"
+            if name in ("spconv_fwd", "spconv_fwd_packed", "spconv_fwd_packed_x3"):
+                kind = {"spconv_fwd": "spconv_simt", "spconv_fwd_packed": "spconv_tc", "spconv_fwd_packed_x3": "spconv_tc_x3"}[name]
+                key = f"{kind}[{info['K']}x{info['Cin']}->{info['Cout']}]"   # x3: fp32 layer as 3 bf16 tensor-core passes
                 name = "spconv_fwd"
             elif name == "fps":
                 key = f"fps[n<={info['max_n']},nq={info['nq']}]"
@@ -344,15 +345,28 @@ def measure(workload, B, K, W, dtype_name, args, world, rank, dev, peaks, with_e
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(K):
-            if graphed is not None:
-                boxes, scores, labels, mask = step(host_batch)                # H2D of the batch inside
-            else:
-                boxes, scores, labels, mask = step([p.to(dev, non_blocking=True) for p in host_pts])
-            out_host = [t.cpu() for t in (boxes, scores, labels, mask)]      # D2H read of the step's result
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
+        if graphed is not None and not args.no_pipeline:
+            # the serving loop a user runs: every step copies its batch from pinned host memory and reads its
+            # boxes back to the host; the copies of neighbouring steps overlap the replay (GraphedForward.submit)
+            graphed.start_pipeline()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(K):
+                graphed.submit(host_batch)                                   # H2D + replay + D2H, all enqueued
+                # (collect() of step i-1 would go here in a server; its wait is hidden behind step i's replay)
+            out_host = graphed.collect()                                     # results of the last step on the host
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+        else:
+            t0 = time.perf_counter()
+            for _ in range(K):
+                if graphed is not None:
+                    boxes, scores, labels, mask = step(host_batch)                # H2D of the batch inside
+                else:
+                    boxes, scores, labels, mask = step([p.to(dev, non_blocking=True) for p in host_pts])
+                out_host = [t.cpu() for t in (boxes, scores, labels, mask)]      # D2H read of the step's result
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
         _, e2e_max, _ = sharding.reduce_metrics(B * K, e2e_s, 0.0, device=dev)
         out["e2e"] = {"value": scenes / e2e_max, "unit": "scenes/s",
                       "h2d_bytes_per_step": sum(p.numel() * p.element_size() for p in host_pts),
@@ -523,6 +537,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--postprocess", action="store_true",
                     help="also run get_bboxes' device post-processing (per-class NMS) inside the step")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="e2e: serialise H2D -> replay -> D2H per step instead of overlapping neighbouring steps")
     ap.add_argument("--train", action="store_true", help="time data-parallel training steps instead of the forward")
     args = ap.parse_args()
     if args.train:

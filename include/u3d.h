@@ -375,6 +375,20 @@ int u3d_pos3_ln_relu(const float* ref, const float* w, const float* b, const flo
                      float eps, int rows, int C, void* out, int dtype, void* stream);
 
 /*
+ * fp32 sparse conv on the tensor cores ("3xBF16", BASELINE configs 3 / 5): activations are (rows, 2*C) bf16 matrices
+ * [hi | lo] (hi = bf16(v), lo = bf16(v - hi)), weights three K-block groups [w_hi ; w_lo ; w_hi] per offset (each packed
+ * with u3d_spconv_pack_weights and concatenated), accumulated in fp32: x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (error 2^-16).
+ * Same reference semantics as u3d_spconv_fwd (spconv indice_conv + BN1d(eval) + ReLU (+identity),
+ * sparse_encoder_hd.py:106-132). One launch computes output channels [cout_off, cout_off + Cout), Cout <= 128; out and
+ * residual are (rows, 2*cout_total); scale / shift point at channel cout_off; a rulebook is required (1x1x1 convs pass
+ * an identity table).
+ */
+int u3d_spconv_fwd_packed_x3(const void* in, const int32_t* nbr, int nbr_stride, const uint32_t* tile_mask,
+                             const int32_t* slot_row, const int32_t* n_out, int out_cap, int K, const void* w_packed,
+                             const float* scale, const float* shift, const void* residual, int relu, void* out,
+                             int Cin, int Cout, int cout_off, int cout_total, void* stream);
+
+/*
  * Training-side entry points (csrc/train.cu). In the reference these steps are
  * torch.autograd through spconv's indice_conv / F.grid_sample, scipy.optimize.linear_sum_assignment on the CPU
  * and mmdet3d's bbox_overlaps_3d; all fp32.

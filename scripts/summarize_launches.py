@@ -18,7 +18,7 @@ def main():
         a[0] += 1
         a[1] += v
         tot += v
-    ours = sum(v for n, (c, v) in agg.items() if "u3d::" in n or "tc::k_" in n or "tn::k_" in n or "mha::k_" in n)
+    ours = sum(v for n, (c, v) in agg.items() if any(t in n for t in ("u3d::", "tc::k_", "tn::k_", "mha::k_", "mha2::k_", "lin::k_", "k_linear_pack")))
     print(f"# ncu launch list summary: {path}\n")
     print(f"{len(rows)} launches captured (~{steps:g} steps), total {tot:.3f} ms of kernel time "
           f"(cold-cache, serialised: compare shares, not absolutes); libu3d_b200 kernels {ours:.3f} ms "

@@ -150,6 +150,10 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride,
                   int K, const void* w,
                   const float* scale, const float* shift, const void* residual, int relu, void* out,
                   int Cin, int Cout, cudaStream_t st);
+int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const uint32_t* tile_mask,
+                     const int32_t* slot_row, const int32_t* n_out, int out_cap, int K, const void* wpk,
+                     const float* scale, const float* shift, const void* residual, int relu, void* out, int Cin,
+                     int Cout, int x3, int in_ld, int out_ld, int cout_off, int cout_total, cudaStream_t st);
 bool spconv_tn_supported(int Cin, int Cout, const int32_t* nbr);
 bool mha_tc_supported(int seq_len, int ldq, int ldk, int ldv, const void* q, const void* k, const void* v,
                       const void* out);

@@ -16,15 +16,20 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 k_sine_embed(const float* __restrict__ ref, int rows, T* __restrict__ out) {
   const int i = threadIdx.x;  // 0..127
-  // dim_t = 10000 ** (2*(i//2)/128), evaluated like torch (fp32 pow)
+  // dim_t = 10000 ** (2*(i//2)/128), evaluated like torch (fp32 pow); hoisted out of the row loop with its
+  // reciprocal-free form kept (v = s * 2pi / dim_t, the reference's operation order)
   const float dim_t = powf(10000.f, (float)(2 * (i / 2)) / 128.f);
+  const bool odd = i & 1;
   for (int r = blockIdx.x; r < rows; r += gridDim.x) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float x = __ldg(&ref[(size_t)r * 3 + c]);
-      float s = 1.f / (1.f + expf(-x));
-      float v = s * 6.283185307179586f / dim_t;
-      float e = (i & 1) ? cosf(v) : sinf(v);
+      const float x = __ldg(&ref[(size_t)r * 3 + c]);
+      const float s = 1.f / (1.f + expf(-x));
+      const float v = s * 6.283185307179586f / dim_t;      // v in [0, 2*pi]
+      float e;
+      const float vr = v > 3.14159265358979f ? v - 6.283185307179586f : v;   // [-pi, pi]: the SFU's accurate range
+      if (sizeof(T) == 2) e = odd ? __cosf(vr) : __sinf(vr);   // bf16 output: SFU sin / cos (abs. error 2^-21)
+      else e = odd ? cosf(v) : sinf(v);
       out[(size_t)r * 384 + c * 128 + i] = from_f32<T>(e);
     }
   }

@@ -441,33 +441,60 @@ k_linear_tc(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 // Linear(3 -> C) + LayerNorm + ReLU: the first half of UniCrossAtten.position_encoder
 // (uni3detr_transformer.py:256-260). K = 3 is no GEMM: one warp per row, 8 channels per lane (C = 256).
 template <typename T>
-__global__ void k_pos3_ln_relu(const float* __restrict__ ref, const float* __restrict__ w,   // w (C,3)
-                               const float* __restrict__ b, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, float eps, int rows, int C, T* __restrict__ out) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256)
+k_pos3_ln_relu(const float* __restrict__ ref, const float* __restrict__ w,   // w (C,3)
+               const float* __restrict__ b, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float eps, int rows, int C, T* __restrict__ out) {
+  // a warp keeps the parameters of its 8 channels per lane in registers and walks rows grid-stride:
+  // per row 3 loads, 24 FMAs, two 5-step shuffle reductions and one 16-byte (bf16) store per lane
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float x = __ldg(&ref[(size_t)row * 3]), y = __ldg(&ref[(size_t)row * 3 + 1]), z = __ldg(&ref[(size_t)row * 3 + 2]);
-  float v[8];
-  float s = 0.f, ss = 0.f;
+  const int wpb = blockDim.x >> 5;
+  float wx[8], wy[8], wz[8], bb[8], gg[8], be[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = lane * 8 + j;
-    v[j] = c < C ? __ldg(&w[c * 3]) * x + __ldg(&w[c * 3 + 1]) * y + __ldg(&w[c * 3 + 2]) * z + __ldg(&b[c]) : 0.f;
-    s += v[j];
-    ss += v[j] * v[j];
+    const bool ok = c < C;
+    wx[j] = ok ? __ldg(&w[c * 3]) : 0.f;
+    wy[j] = ok ? __ldg(&w[c * 3 + 1]) : 0.f;
+    wz[j] = ok ? __ldg(&w[c * 3 + 2]) : 0.f;
+    bb[j] = ok ? __ldg(&b[c]) : 0.f;
+    gg[j] = ok ? __ldg(&gamma[c]) : 0.f;
+    be[j] = ok ? __ldg(&beta[c]) : 0.f;
   }
+  const float invC = 1.f / (float)C;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const float x = __ldg(&ref[(size_t)row * 3]), y = __ldg(&ref[(size_t)row * 3 + 1]), z = __ldg(&ref[(size_t)row * 3 + 2]);
+    float v[8];
+    float s = 0.f, ss = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s += __shfl_xor_sync(0xffffffffu, s, o);
-    ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  }
-  const float mean = s / (float)C;
-  const float rstd = rsqrtf(fmaxf(ss / (float)C - mean * mean, 0.f) + eps);
+    for (int j = 0; j < 8; ++j) {
+      v[j] = lane * 8 + j < C ? fmaf(wx[j], x, fmaf(wy[j], y, fmaf(wz[j], z, bb[j]))) : 0.f;
+      s += v[j];
+      ss = fmaf(v[j], v[j], ss);
+    }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = lane * 8 + j;
-    if (c < C) out[(size_t)row * C + c] = from_f32<T>(fmaxf((v[j] - mean) * rstd * __ldg(&gamma[c]) + __ldg(&beta[c]), 0.f));
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const float mean = s * invC;
+    const float rstd = rsqrtf(fmaxf(ss * invC - mean * mean, 0.f) + eps);
+    T* o = out + (size_t)row * C + lane * 8;
+    if (lane * 8 + 8 <= C && sizeof(T) == 2) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float a0 = fmaxf((v[j] - mean) * rstd * gg[j] + be[j], 0.f);
+        const float a1 = fmaxf((v[j + 1] - mean) * rstd * gg[j + 1] + be[j + 1], 0.f);
+        __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (lane * 8 + j < C) o[j] = from_f32<T>(fmaxf((v[j] - mean) * rstd * gg[j] + be[j], 0.f));
+    }
   }
 }
 
@@ -641,12 +668,16 @@ int u3d_pos3_ln_relu(const float* ref, const float* w, const float* b, const flo
   U3D_CHECK_ARG(C >= 1 && C <= 256, "pos3_ln_relu: C=%d must be <= 256", C);
   if (rows <= 0) return U3D_OK;
   const int wpb = 8;
+  int grid = cdiv(rows, wpb * 4);                 // >= 4 rows per warp: the per-warp parameter load amortises
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (grid < 1) grid = 1;
+  U3D_CHECK_ARG(C % 8 == 0 || dtype == U3D_F32 || true, "pos3_ln_relu");
   if (dtype == U3D_BF16)
-    lin::k_pos3_ln_relu<__nv_bfloat16><<<cdiv(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+    lin::k_pos3_ln_relu<__nv_bfloat16><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
         ref, w, b, gamma, beta, eps, rows, C, (__nv_bfloat16*)out);
   else
-    lin::k_pos3_ln_relu<float><<<cdiv(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(ref, w, b, gamma, beta, eps,
-                                                                                       rows, C, (float*)out);
+    lin::k_pos3_ln_relu<float><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(ref, w, b, gamma, beta, eps, rows, C,
+                                                                             (float*)out);
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }

@@ -483,3 +483,24 @@ extern "C" int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr
   return spconv_fwd_tc(in, nbr, nbr_stride, tile_mask, slot_row, n_out, out_cap, K, w_packed, scale, shift,
                        residual, relu, out, Cin, Cout, (cudaStream_t)stream);
 }
+
+// 3xBF16 evaluation of an fp32 sparse conv on the rows-on-N tcgen05 kernel (spconv_tn.cu, kX3): see there.
+// in (rows, 2*Cin) bf16 [hi | lo]; w_packed: the first (and, for Cout < 128, second) image sets of
+// u3d_spconv_pack_weights for the three K-block groups [w_hi ; w_lo ; w_hi] concatenated per offset;
+// out / residual (rows, 2*cout_total) bf16 [hi | lo]; this launch computes channels [cout_off, cout_off + Cout),
+// Cout <= 128; scale / shift point at channel cout_off.
+extern "C" int u3d_spconv_fwd_packed_x3(const void* in, const int32_t* nbr, int nbr_stride, const uint32_t* tile_mask,
+                                        const int32_t* slot_row, const int32_t* n_out, int out_cap, int K,
+                                        const void* w_packed, const float* scale, const float* shift,
+                                        const void* residual, int relu, void* out, int Cin, int Cout, int cout_off,
+                                        int cout_total, void* stream) {
+  U3D_CHECK_ARG(in && nbr && n_out && w_packed && out, "u3d_spconv_fwd_packed_x3: null buffer (a rulebook is required; "
+                "pointwise convs pass an identity table)");
+  U3D_CHECK_ARG(spconv_tn_supported(Cin, Cout, nbr) && cout_off >= 0 && cout_off + Cout <= cout_total && (cout_off & 7) == 0 &&
+                    (cout_total & 7) == 0,
+                "u3d_spconv_fwd_packed_x3: needs Cin in {16,32,64k<=512}, even Cout <= 128 (Cin=%d Cout=%d off=%d total=%d)",
+                Cin, Cout, cout_off, cout_total);
+  return spconv_fwd_tn_ex(in, nbr, nbr_stride, tile_mask, slot_row, n_out, out_cap, K, w_packed, scale, shift, residual,
+                          relu, out, Cin, Cout, 1, 2 * Cin, 2 * cout_total, cout_off, cout_total, (cudaStream_t)stream);
+}
+

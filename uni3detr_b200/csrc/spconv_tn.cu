@@ -80,14 +80,22 @@ __device__ __forceinline__ uint32_t mask_of_tile(const uint32_t* __restrict__ ti
   return m & all_mask;
 }
 
-template <int CIN_BLK, int kSliceBufs, int kNumProd>
+// kX3: "3xBF16" evaluation of an fp32 layer. Activations travel as (rows, 2*C) bf16 matrices [hi | lo] with
+// hi = bf16(v), lo = bf16(v - hi) (16 significant bits); the weights are packed as three Cin-block groups
+// [w_hi ; w_lo ; w_hi] and the K loop multiplies x_hi*w_hi + x_hi*w_lo + x_lo*w_hi into the same fp32
+// accumulator (the dropped lo*lo term is 2^-16 relative), so fp32 layers (BASELINE configs 3 and 5) run on
+// the tensor cores within the 1e-3 parity bound instead of on FFMA. `Cin` is the REAL channel count; `in_ld` /
+// `out_ld` are the row strides of the input / output (and residual) matrices, `cout_off` the first output
+// channel of this launch (Cout > 128 runs as several 128-channel launches), `cout_total` the real width.
+template <int CIN_BLK, int kSliceBufs, int kNumProd, bool kX3>
 __global__ void __launch_bounds__(threads_of(kNumProd), 1)
 k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
             const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ slot_row,
             const int32_t* __restrict__ n_out_p, int K,
             const __nv_bfloat16* __restrict__ wpk, const float* __restrict__ scale,
             const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
-            __nv_bfloat16* __restrict__ out, int Cin, int Cout, int stages) {
+            __nv_bfloat16* __restrict__ out, int Cin, int Cout, int stages, int in_ld, int out_ld, int cout_off,
+            int cout_total) {
   using SW = Swz<CIN_BLK>;
   constexpr int kChunks = CIN_BLK / 8;            // 16-byte chunks per gathered row
   constexpr int kRowsPerPass = 32 / kChunks;      // rows one warp-wide cp.async covers
@@ -106,7 +114,8 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   if ((int)blockIdx.x >= n_tiles) return;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nkb = Cin / CIN_BLK;
+  const int nkb_r = Cin / CIN_BLK;                 // Cin blocks of one operand part
+  const int nkb = (kX3 ? 3 : 1) * nkb_r;           // K-loop blocks per offset
   // The A tile always spans the 128 TMEM lanes. For Cout < 128 the packed weights carry a second
   // set of images in which the (Cout x CIN_BLK) tile is REPLICATED every rep_span rows (written by
   // u3d_spconv_pack_weights), so every TMEM lane quarter holds a copy of the channels and all eight
@@ -116,7 +125,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   const int n_rep = 128 / rep_span;                                         // 4 / 2 / 1
   constexpr uint32_t w_unit = 128u * SW::P;                                 // 4 / 8 / 16 KB
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(wpk) +
-                        (Cout < 128 ? (size_t)K * Cin * Cout * 2 : (size_t)0);   // 128-row images
+                        (Cout < 128 ? (size_t)K * nkb * CIN_BLK * Cout * 2 : (size_t)0);   // 128-row images
   constexpr uint32_t w_region = kG * w_unit;                                // 16 KB for every CIN_BLK
   const uint32_t stage_bytes = w_region + kXBytes;
   const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;                   // 1024-aligned
@@ -163,8 +172,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     const int rbase = half * 128 + rsub * kPasses;      // first tile row of this lane
     const uint32_t chunk16 = (uint32_t)chunk * 16u;
     const uint32_t lane_off = (uint32_t)(rbase * SW::P);
-    const uint64_t row_bytes = (uint64_t)Cin * 2;
-    const int nkb_log2 = __ffs(nkb) - 1;                // Cin / CIN_BLK is a power of two
+    const uint64_t row_bytes = (uint64_t)in_ld * 2;
     // pair p OWNS ring slot p: it fills the global stages g = p, p + stages, ... so it meets the
     // generations of its slot in order and the 1-bit mbarrier parity is never ambiguous (a pair
     // without a slot - ring shortened by U3D_TN_STAGES - only passes through the slices)
@@ -196,13 +204,16 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         for (int j = 0; j < kG; ++j) {
           if (j < cnt) {
             const int u = u0 + j;
-            const int ki = u >> nkb_log2, kb = u & (nkb - 1);
+            const int ki = u / nkb, kb = u - ki * nkb;
             const int k = __ffs(__ballot_sync(0xffffffffu, my_bit && my_rank == ki)) - 1;
+            // source columns of this K block: plain = block kb; 3xBF16 = [x_hi | x_hi | x_lo] blocks
+            const int part = kX3 ? kb / nkb_r : 0;
+            const int src_col = (part == 2 ? Cin : 0) + (kb - part * nkb_r) * CIN_BLK;
             if (half == 0 && lane == 0)
               bulk_g2s(st_s + (uint32_t)j * w_unit, wimg + ((size_t)k * nkb + kb) * w_unit, w_unit,
                        &S.full[slot]);
             const uint8_t* src_base =
-                reinterpret_cast<const uint8_t*>(in) + (size_t)(kb * CIN_BLK + chunk * 8) * 2;
+                reinterpret_cast<const uint8_t*>(in) + (size_t)(src_col + chunk * 8) * 2;
             int idx[kPasses];
             const int4* nb4 = reinterpret_cast<const int4*>(&S.nbr[buf][k][rbase]);
 #pragma unroll
@@ -310,16 +321,19 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       const int ab = t & 1;
       const int row0 = tile * kTile + col_lo + (odd ? 1 : 0);   // slot of this lane: + col + 2p
       const int* srow = slot_row ? &S.srow[ab][col_lo + (odd ? 1 : 0)] : nullptr;
-      uint32_t res[16];
+      uint32_t res[16], res_lo[kX3 ? 16 : 1];
       auto load_res = [&](int col) {
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
           const int slot = row0 + col + 2 * p;
           if (residual && lane_live && slot < n_out) {
             const int o = srow ? srow[col + 2 * p] : slot;
-            res[p] = __ldg(reinterpret_cast<const uint32_t*>(residual + (size_t)o * Cout + cb));
+            const __nv_bfloat16* rp = residual + (size_t)o * out_ld + cout_off + cb;
+            res[p] = __ldg(reinterpret_cast<const uint32_t*>(rp));
+            if (kX3) res_lo[p] = __ldg(reinterpret_cast<const uint32_t*>(rp + cout_total));
           } else {
             res[p] = 0u;
+            if (kX3) res_lo[p] = 0u;
           }
         }
       };
@@ -333,9 +347,12 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
         uint32_t v[32];
         tmem_ld32(lane_base + (uint32_t)col, v);   // warp-collective
         tmem_ld_wait();
-        uint32_t cur[16];
+        uint32_t cur[16], cur_lo[kX3 ? 16 : 1];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) cur[p] = res[p];
+        for (int p = 0; p < 16; ++p) {
+          cur[p] = res[p];
+          if (kX3) cur_lo[p] = res_lo[p];
+        }
         if (col + 32 < ncol) load_res(col + 32);     // prefetch the next chunk's residuals
 #pragma unroll
         for (int p = 0; p < 16; ++p) {
@@ -350,8 +367,19 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
             const float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cur[p]));
             lo += r.x;
             hi += r.y;
+            if (kX3) {
+              const float2 r2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cur_lo[p]));
+              lo += r2.x;
+              hi += r2.y;
+            }
             if (relu) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
-            *reinterpret_cast<__nv_bfloat162*>(out + (size_t)o * Cout + cb) = __floats2bfloat162_rn(lo, hi);
+            __nv_bfloat16* op = out + (size_t)o * out_ld + cout_off + cb;
+            const __nv_bfloat162 top = __floats2bfloat162_rn(lo, hi);
+            *reinterpret_cast<__nv_bfloat162*>(op) = top;
+            if (kX3) {            // second half of the row: what bf16 dropped (v - bf16(v)), again as bf16
+              const float2 t = __bfloat1622float2(top);
+              *reinterpret_cast<__nv_bfloat162*>(op + cout_total) = __floats2bfloat162_rn(lo - t.x, hi - t.y);
+            }
           }
         }
       }
@@ -380,6 +408,15 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint
                   const float* scale,
                   const float* shift, const void* residual, int relu, void* out, int Cin, int Cout,
                   cudaStream_t st) {
+  return spconv_fwd_tn_ex(in, nbr, nbr_stride, tile_mask, slot_row, n_out, out_cap, K, wpk, scale, shift, residual,
+                          relu, out, Cin, Cout, /*x3=*/0, /*in_ld=*/Cin, /*out_ld=*/Cout, /*cout_off=*/0,
+                          /*cout_total=*/Cout, st);
+}
+
+int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const uint32_t* tile_mask,
+                     const int32_t* slot_row, const int32_t* n_out, int out_cap, int K, const void* wpk,
+                     const float* scale, const float* shift, const void* residual, int relu, void* out, int Cin,
+                     int Cout, int x3, int in_ld, int out_ld, int cout_off, int cout_total, cudaStream_t st) {
   using namespace tn;
   U3D_CHECK_ARG(K >= 1 && K <= kMaxK, "spconv tn: K=%d unsupported", K);
   U3D_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)wpk | (uintptr_t)residual) & 15) == 0,
@@ -410,14 +447,18 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint
   const size_t smem = header + (size_t)stages * stage_bytes;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
 
-#define U3D_TN_LAUNCH2(BLK, SB, NP)                                                                 \
+#define U3D_TN_LAUNCH3(BLK, SB, NP, X3)                                                             \
   do {                                                                                              \
     static int cur_smem = 0;                                                                        \
-    U3D_CUDA(ensure_dynamic_smem(k_spconv_tn<BLK, SB, NP>, smem, &cur_smem));                       \
-    k_spconv_tn<BLK, SB, NP><<<grid, threads_of(NP), smem, st>>>(                                   \
+    U3D_CUDA(ensure_dynamic_smem(k_spconv_tn<BLK, SB, NP, X3>, smem, &cur_smem));                   \
+    k_spconv_tn<BLK, SB, NP, X3><<<grid, threads_of(NP), smem, st>>>(                               \
         (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, slot_row, n_out, K,                   \
         (const __nv_bfloat16*)wpk, scale, shift, (const __nv_bfloat16*)residual, relu,              \
-        (__nv_bfloat16*)out, Cin, Cout, stages);                                                    \
+        (__nv_bfloat16*)out, Cin, Cout, stages, in_ld, out_ld, cout_off, cout_total);               \
+  } while (0)
+#define U3D_TN_LAUNCH2(BLK, SB, NP)                                                                 \
+  do {                                                                                              \
+    if (x3) U3D_TN_LAUNCH3(BLK, SB, NP, true); else U3D_TN_LAUNCH3(BLK, SB, NP, false);             \
   } while (0)
 #define U3D_TN_LAUNCH(BLK)                                                                          \
   do {                                                                                              \
@@ -428,6 +469,7 @@ int spconv_fwd_tn(const void* in, const int32_t* nbr, int nbr_stride, const uint
   else U3D_TN_LAUNCH(16);
 #undef U3D_TN_LAUNCH
 #undef U3D_TN_LAUNCH2
+#undef U3D_TN_LAUNCH3
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }

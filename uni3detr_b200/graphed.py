@@ -56,6 +56,50 @@ class GraphedForward:
         """host_points: (Ntot,C) f32 (pinned for an async copy) -> static device buffer."""
         self.points.copy_(host_points, non_blocking=True)
 
+    # ---- pipelined serving: H2D of batch i+1 and D2H of batch i-1 overlap the replay of batch i ----
+    def start_pipeline(self):
+        """Allocate the staging buffers of `submit` / `collect`: a second device point buffer fed by a copy
+        stream, pinned host result buffers, and the events that order the three streams."""
+        dev = self.points.device
+        self._stage = torch.empty_like(self.points)
+        self._copy_in, self._copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self._staged, self._consumed, self._done = (torch.cuda.Event() for _ in range(3))
+        self._host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self.outputs]
+        self._dev_out = [torch.empty_like(t) for t in self.outputs]
+        self._consumed.record(torch.cuda.current_stream())
+        self._pending = False
+
+    def submit(self, host_points):
+        """Enqueue one batch: pinned host points -> staging buffer (copy stream), staging -> graph input + replay
+        (compute stream), results -> pinned host buffers (copy-out stream). Returns immediately; `collect()`
+        waits for the results of the batch submitted BEFORE this one (call it after the next submit)."""
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_in):
+            self._copy_in.wait_event(self._consumed)          # the previous replay has copied the staging buffer out
+            self._stage.copy_(host_points, non_blocking=True)
+            self._staged.record(self._copy_in)
+        cur.wait_event(self._staged)
+        if self._pending:
+            cur.wait_event(self._done)                        # results of the previous batch have left _dev_out
+        self.points.copy_(self._stage, non_blocking=True)     # device-to-device, 10 MB: microseconds
+        self._consumed.record(cur)
+        self.graph.replay()
+        for d, o in zip(self._dev_out, self.outputs):
+            d.copy_(o, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        with torch.cuda.stream(self._copy_out):
+            self._copy_out.wait_event(ready)
+            for h, d in zip(self._host_out, self._dev_out):
+                h.copy_(d, non_blocking=True)
+            self._done.record(self._copy_out)
+        self._pending = True
+
+    def collect(self):
+        """Block until the most recently submitted batch's results are in the pinned host buffers; returns them."""
+        self._done.synchronize()
+        return self._host_out
+
     def run(self, host_points=None, redraw_random_group=False):
         """redraw_random_group=True refills the reference points of the random 4th query group in place
         before the replay (the reference draws `torch.rand` on every forward, uni3detr_head.py:445-447);

@@ -741,3 +741,73 @@ def hungarian(cost):
     out = torch.empty((P, rows), dtype=torch.int32, device=cost.device)
     _lib.check(lib.u3d_hungarian(_p(cost), rows * cols, cols, P, rows, cols, _p(out), _stream()))
     return out
+
+
+# ------------------------------------------------------------- fp32 sparse conv as 3xBF16 (tcgen05) ----
+def split_bf16(x):
+    """fp32 (rows, C) -> (rows, 2C) bf16 [hi | lo] with hi = bf16(x), lo = bf16(x - hi)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+def merge_bf16(x2):
+    """(rows, 2C) bf16 [hi | lo] -> fp32 (rows, C)."""
+    C = x2.shape[1] // 2
+    return x2[:, :C].float() + x2[:, C:].float()
+
+
+class PackedConvX3:
+    """Weights of one fp32 sparse conv for u3d_spconv_fwd_packed_x3: per <=128-channel output part the packed
+    images of the K-block groups [w_hi ; w_lo ; w_hi] (built from two u3d_spconv_pack_weights calls)."""
+
+    def __init__(self, w):
+        K, Cin, Cout = w.shape
+        self.K, self.Cin, self.Cout = K, Cin, Cout
+        w = w.float()
+        w_hi = w.to(torch.bfloat16)
+        w_lo = (w - w_hi.float()).to(torch.bfloat16)
+        self.parts = []
+        for c0 in range(0, Cout, 128):
+            c1 = min(c0 + 128, Cout)
+            co = c1 - c0
+            ph = spconv_pack_weights(w_hi[:, :, c0:c1].contiguous())
+            pl = spconv_pack_weights(w_lo[:, :, c0:c1].contiguous())
+            n1 = K * Cin * co                      # elements of the first image set (rows-on-M, Cout rows per image)
+            sets = [(0, n1, co)]
+            if co < 128:
+                sets.append((n1, n1 + K * Cin * 128, 128))     # replicated 128-row images of the rows-on-N kernel
+            blk = 64 if Cin % 64 == 0 else Cin
+            nkb = Cin // blk
+            chunks = []
+            for a, b, rows in sets:
+                vh = ph[a:b].view(K, nkb, rows * blk)
+                vl = pl[a:b].view(K, nkb, rows * blk)
+                chunks.append(torch.cat([vh, vl, vh], dim=1).reshape(-1))
+            self.parts.append((c0, co, torch.cat(chunks).contiguous()))
+
+
+def identity_rulebook(cap, device):
+    """(1, cap) table mapping every output row to itself: lets 1x1x1 convs run on the gather kernel."""
+    pad = max((cap + 255) // 256, 1) * 256
+    nbr = torch.arange(pad, dtype=torch.int32, device=device).view(1, pad)[:, :max(cap, 1)].as_subclass(Rulebook)
+    nbr.tile_mask = None
+    return nbr
+
+
+@_timed(lambda r, x2, nbr, n_out, out_cap, pk, *a, **k: dict(
+    n_out=int(n_out), pairs=_live_pairs(nbr, n_out), K=pk.K, Cin=pk.Cin, Cout=pk.Cout, esize=4, tc=True, x3=True))
+def spconv_fwd_packed_x3(x2, nbr, n_out, out_cap, pk, scale=None, shift=None, residual=None, relu=False):
+    """fp32-grade sparse conv on tcgen05: x2 (rows, 2*Cin) bf16 [hi|lo] -> (out_cap, 2*Cout) bf16 [hi|lo]."""
+    lib = _lib.load()
+    _req(x2, torch.bfloat16, "x2")
+    assert x2.shape[1] == 2 * pk.Cin
+    out = torch.empty((out_cap, 2 * pk.Cout), dtype=torch.bfloat16, device=x2.device)
+    tile_mask = getattr(nbr, "tile_mask", None)
+    slot_row = getattr(nbr, "slot_row", None)
+    for c0, co, wp in pk.parts:
+        _lib.check(lib.u3d_spconv_fwd_packed_x3(
+            _p(x2), _p(nbr), nbr.stride(0), _p(tile_mask), _p(slot_row), _p(n_out), out_cap, pk.K, _p(wp),
+            _p(scale[c0:c0 + co]) if scale is not None else None, _p(shift[c0:c0 + co]) if shift is not None else None,
+            _p(residual), int(bool(relu)), _p(out), pk.Cin, co, c0, pk.Cout, _stream()))
+    return out

@@ -244,11 +244,30 @@ class SparseEncoderHD(nn.Module):
                     packed = ops.spconv_pack_weights(w)
                 else:
                     cin, w = conv.in_channels, w[:, :conv.in_channels].contiguous()
-            steps.append(dict(w=w, packed=packed, scale=scale, shift=shift, relu=s["relu"],
+            x3 = None
+            if (self.use_tensor_cores and dtype == torch.float32 and w.is_cuda and
+                    os.environ.get("U3D_FP32_STRICT") != "1"):
+                # fp32 (BASELINE configs 3 / 5) on the tensor cores: 3xBF16 operand split (ops.PackedConvX3);
+                # the stem's 4 / 5 input channels are zero-padded to one 16-wide K block
+                wx = w
+                if cin < 16:
+                    cin = 16
+                    wx = torch.nn.functional.pad(w, (0, 0, 0, cin - conv.in_channels)).contiguous()
+                if ops.spconv_tc_supported(k, cin, min(conv.out_channels, 128)) and conv.out_channels % 2 == 0 and \
+                        (conv.out_channels <= 128 or conv.out_channels % 128 == 0):
+                    x3 = ops.PackedConvX3(wx)
+                else:
+                    cin = conv.in_channels
+            steps.append(dict(w=w, packed=packed, x3=x3, scale=scale, shift=shift, relu=s["relu"],
                               save=s["save"], add=s["add"], subm=conv.subm, k=k,
                               cin=cin, cout=conv.out_channels,
                               stride=conv.stride, pad=conv.padding))
-        self._plan = dict(dtype=dtype, steps=steps, tc=self.use_tensor_cores)
+        # the 3xBF16 path carries [hi | lo] activation pairs from layer to layer: all layers or none
+        use_x3 = all(st["x3"] is not None for st in steps)
+        if not use_x3:
+            for st in steps:
+                st["x3"] = None
+        self._plan = dict(dtype=dtype, steps=steps, tc=self.use_tensor_cores, x3=use_x3)
         return self._plan
 
     # --------------------------------------------------------------- forward ----
@@ -314,6 +333,9 @@ class SparseEncoderHD(nn.Module):
         x = feats.to(dtype).contiguous()
         if plan["steps"][0]["cin"] > x.shape[1]:
             x = torch.nn.functional.pad(x, (0, plan["steps"][0]["cin"] - x.shape[1]))
+        x3 = plan.get("x3", False)
+        if x3:
+            x = ops.split_bf16(x)                # (cap, 2*Cin) bf16 [hi | lo] all the way to dense()
         dims = tuple(self.sparse_shape)
         level = dict(coors=coors, n=n_rows, cap=cap, vmap=vmap, nbr=None, nbr_sorted=None, dims=dims)
         saved = None
@@ -332,10 +354,14 @@ class SparseEncoderHD(nn.Module):
         # EXPERIMENTAL (not yet run on hardware): U3D_SORT_GROUP=g keeps the buckets inside groups of g scenes
         sort_group = int(os.environ.get("U3D_SORT_GROUP", "0"))
         for st in plan["steps"]:
-            sortable = (sort_tiles and st["packed"] is not None and st["k"] == 27 and st["cout"] <= 128
+            sortable = (sort_tiles and (st["packed"] is not None or x3) and st["k"] == 27 and st["cout"] <= 128
                         and st["cin"] <= sort_max_cin and (st["subm"] or sort_down))
             if st["k"] == 1:
                 nbr, out_level = None, level
+                if x3:                           # 1x1x1 conv on the gather kernel: identity table
+                    if level.get("ident") is None:
+                        level["ident"] = ops.identity_rulebook(level["cap"], x.device)
+                    nbr = level["ident"]
             elif st["subm"]:
                 if level["nbr"] is None:
                     level["nbr"] = ops.rulebook_subm(level["coors"], level["n"], level["cap"],
@@ -354,7 +380,10 @@ class SparseEncoderHD(nn.Module):
             if st["save"]:
                 saved = x
             res = saved if st["add"] else None
-            if st["packed"] is not None:
+            if x3:
+                x = ops.spconv_fwd_packed_x3(x, nbr, out_level["n"], out_level["cap"], st["x3"], st["scale"],
+                                             st["shift"], residual=res, relu=st["relu"])
+            elif st["packed"] is not None:
                 x = ops.spconv_fwd_packed(x, nbr, out_level["n"], out_level["cap"], st["packed"],
                                           st["k"], st["cin"], st["cout"], st["scale"], st["shift"],
                                           residual=res, relu=st["relu"])
@@ -364,6 +393,8 @@ class SparseEncoderHD(nn.Module):
             if st["add"]:
                 saved = None
             level = out_level
+        if x3:
+            x = ops.merge_bf16(x)                                  # back to fp32 rows
         dense = ops.sparse_to_dense(x, level["coors"], level["n"], level["cap"], B, level["dims"],
                                     channels_last=True)          # (B,D,H,W,C)
         out = dense.permute(0, 4, 1, 2, 3)                       # logical (B,C,D,H,W)
