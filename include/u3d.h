@@ -217,11 +217,13 @@ int u3d_spconv_fwd(const void* in, const int32_t* nbr, int nbr_stride, const int
  */
 size_t u3d_spconv_packed_bytes(int K, int Cin, int Cout);
 int u3d_spconv_pack_weights(const void* w, int K, int Cin, int Cout, void* packed, void* stream);
+#define U3D_CONV_REVERSE_TILES 2   /* `flags`: walk the output tiles from the last row back (the previous layer left its
+                                      last rows in L2; feature matrices of the wide levels exceed it at batch 32) */
 int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr_stride,
                           const uint32_t* tile_mask, const int32_t* slot_row, const int32_t* n_out,
                           int out_cap, int K, const void* w_packed, const float* scale,
                           const float* shift, const void* residual, int relu, void* out, int Cin,
-                          int Cout, void* stream);
+                          int Cout, int flags, void* stream);
 
 /*
  * SparseConvTensor.dense(): scatter rows into a zero-filled volume.
@@ -386,7 +388,7 @@ int u3d_pos3_ln_relu(const float* ref, const float* w, const float* b, const flo
 int u3d_spconv_fwd_packed_x3(const void* in, const int32_t* nbr, int nbr_stride, const uint32_t* tile_mask,
                              const int32_t* slot_row, const int32_t* n_out, int out_cap, int K, const void* w_packed,
                              const float* scale, const float* shift, const void* residual, int relu, void* out,
-                             int Cin, int Cout, int cout_off, int cout_total, void* stream);
+                             int Cin, int Cout, int cout_off, int cout_total, int flags, void* stream);
 
 /*
  * Training-side entry points (csrc/train.cu). In the reference these steps are

@@ -108,9 +108,9 @@ SIGNATURES = {
     "u3d_spconv_packed_bytes": (_sz, [_i32, _i32, _i32]),
     "u3d_spconv_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "u3d_spconv_fwd_packed": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
-                                     _i32, _vp, _i32, _i32, _vp]),
+                                     _i32, _vp, _i32, _i32, _i32, _vp]),
     "u3d_spconv_fwd_packed_x3": (_i32, [_vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
-                                        _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
+                                        _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "u3d_tile_sort_scratch_ints": (_sz, [_i32]),
     "u3d_tile_sort_grouped_scratch_ints": (_sz, [_i32, _i32]),
     "u3d_rulebook_sort_tiles_grouped": (_i32, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32,

@@ -474,12 +474,19 @@ extern "C" int u3d_spconv_fwd_packed(const void* in, const int32_t* nbr, int nbr
                                      const uint32_t* tile_mask, const int32_t* slot_row,
                                      const int32_t* n_out, int out_cap, int K, const void* w_packed,
                                      const float* scale, const float* shift, const void* residual,
-                                     int relu, void* out, int Cin, int Cout, void* stream) {
+                                     int relu, void* out, int Cin, int Cout, int flags, void* stream) {
   U3D_CHECK_ARG(in && n_out && w_packed && out, "u3d_spconv_fwd_packed: null buffer");
   U3D_CHECK_ARG(nbr != nullptr || K == 1, "u3d_spconv_fwd_packed: nbr==NULL requires K==1");
   U3D_CHECK_ARG(spconv_tc_supported(Cin, Cout, U3D_BF16),
                 "u3d_spconv_fwd_packed: needs Cin in {16,32,64k<=512}, Cout a power of two in [16,512] "
                 "(Cin=%d Cout=%d)", Cin, Cout);
+  // flags bit 1 (U3D_CONV_REVERSE_TILES): rows-on-N kernel walks its tiles from the last row back
+  {
+    const char* e = getenv("U3D_TC_KERNEL");
+    if ((flags & 2) && !(e && atoi(e) == 1) && spconv_tn_supported(Cin, Cout, nbr))
+      return spconv_fwd_tn_ex(in, nbr, nbr_stride, tile_mask, slot_row, n_out, out_cap, K, w_packed, scale, shift,
+                              residual, relu, out, Cin, Cout, 2, Cin, Cout, 0, Cout, (cudaStream_t)stream);
+  }
   return spconv_fwd_tc(in, nbr, nbr_stride, tile_mask, slot_row, n_out, out_cap, K, w_packed, scale, shift,
                        residual, relu, out, Cin, Cout, (cudaStream_t)stream);
 }
@@ -493,7 +500,7 @@ extern "C" int u3d_spconv_fwd_packed_x3(const void* in, const int32_t* nbr, int 
                                         const int32_t* slot_row, const int32_t* n_out, int out_cap, int K,
                                         const void* w_packed, const float* scale, const float* shift,
                                         const void* residual, int relu, void* out, int Cin, int Cout, int cout_off,
-                                        int cout_total, void* stream) {
+                                        int cout_total, int flags, void* stream) {
   U3D_CHECK_ARG(in && nbr && n_out && w_packed && out, "u3d_spconv_fwd_packed_x3: null buffer (a rulebook is required; "
                 "pointwise convs pass an identity table)");
   U3D_CHECK_ARG(spconv_tn_supported(Cin, Cout, nbr) && cout_off >= 0 && cout_off + Cout <= cout_total && (cout_off & 7) == 0 &&
@@ -501,6 +508,7 @@ extern "C" int u3d_spconv_fwd_packed_x3(const void* in, const int32_t* nbr, int 
                 "u3d_spconv_fwd_packed_x3: needs Cin in {16,32,64k<=512}, even Cout <= 128 (Cin=%d Cout=%d off=%d total=%d)",
                 Cin, Cout, cout_off, cout_total);
   return spconv_fwd_tn_ex(in, nbr, nbr_stride, tile_mask, slot_row, n_out, out_cap, K, w_packed, scale, shift, residual,
-                          relu, out, Cin, Cout, 1, 2 * Cin, 2 * cout_total, cout_off, cout_total, (cudaStream_t)stream);
+                          relu, out, Cin, Cout, 1 | (flags & 2), 2 * Cin, 2 * cout_total, cout_off, cout_total,
+                          (cudaStream_t)stream);
 }
 

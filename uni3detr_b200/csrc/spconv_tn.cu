@@ -95,7 +95,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
             const __nv_bfloat16* __restrict__ wpk, const float* __restrict__ scale,
             const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int relu,
             __nv_bfloat16* __restrict__ out, int Cin, int Cout, int stages, int in_ld, int out_ld, int cout_off,
-            int cout_total) {
+            int cout_total, int m64) {
   using SW = Swz<CIN_BLK>;
   constexpr int kChunks = CIN_BLK / 8;            // 16-byte chunks per gathered row
   constexpr int kRowsPerPass = 32 / kChunks;      // rows one warp-wide cp.async covers
@@ -123,10 +123,16 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   // 16/32-channel layer becomes epilogue-bound). One bulk copy per (offset, Cin block) either way.
   const int rep_span = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);           // rows between replicas
   const int n_rep = 128 / rep_span;                                         // 4 / 2 / 1
-  constexpr uint32_t w_unit = 128u * SW::P;                                 // 4 / 8 / 16 KB
+  // m64 (Cout == 64): an M = 64 instruction on the UN-replicated 64-row weight image. A dispatch costs the same
+  // cycles as M = 128, but the image is half the bytes (8 instead of 16 KB per unit: 40 % less L2 -> SM traffic
+  // for this kernel) and a stage shrinks to 40 KB, which buys a 4th ring slot. The M = 64 accumulator puts 16
+  // rows in the first 16 lanes of every TMEM lane quarter, so all eight epilogue warps still drain a tile.
+  const int flags_ = m64;
+  m64 &= 1;
+  const uint32_t w_unit = (m64 ? 64u : 128u) * SW::P;                       // 4 / 8 / 16 KB (m64: 8 KB)
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(wpk) +
-                        (Cout < 128 ? (size_t)K * nkb * CIN_BLK * Cout * 2 : (size_t)0);   // 128-row images
-  constexpr uint32_t w_region = kG * w_unit;                                // 16 KB for every CIN_BLK
+                        ((Cout < 128 && !m64) ? (size_t)K * nkb * CIN_BLK * Cout * 2 : (size_t)0);   // 128-row images
+  const uint32_t w_region = kG * w_unit;                                    // 16 KB for every CIN_BLK (m64: 8 KB)
   const uint32_t stage_bytes = w_region + kXBytes;
   const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;                   // 1024-aligned
   const uint32_t all_mask = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
@@ -182,7 +188,8 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     int g0 = 0;          // global index of the first stage of the current tile
     int t = 0;
     const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++t) {
+      const int tile = (flags_ & 2) ? n_tiles - 1 - tl : tl;   // bit 1: walk the tiles from the last row back (L2 reuse)
       const int buf = t % kSliceBufs;
       const int m0 = tile * kTile;
       const uint32_t mask = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
@@ -244,7 +251,8 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     // ======================= rulebook-slice loader (one thread) =======================
     if (lane == 0) {
       int t = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++t) {
+      const int tile = (flags_ & 2) ? n_tiles - 1 - tl : tl;   // bit 1: walk the tiles from the last row back (L2 reuse)
         const int buf = t % kSliceBufs;
         mbar_wait_relaxed(&S.slice_empty[buf], (((uint32_t)(t / kSliceBufs)) & 1u) ^ 1u, 2000u);
         uint32_t m = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
@@ -265,10 +273,11 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     if (lane == 0) {
       // kind::f16: D = f32, A = B = bf16, both K-major, N = 256, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
+                             ((uint32_t)((m64 ? 64 : 128) >> 4) << 24);
       int slot = 0, t = 0;
       uint32_t fph = 0u;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++t) {
+      const int tile = (flags_ & 2) ? n_tiles - 1 - tl : tl;   // bit 1: walk the tiles from the last row back (L2 reuse)
         const int ab = t & 1;
         const uint32_t mask = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
         const int n_units = __popc(mask) * nkb;
@@ -307,17 +316,19 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     // ======================= epilogue: TMEM -> registers -> global =======================
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int h = warp >> 2;           // column (= row of the tile) half
-    const int c = (q * 32 + lane) % rep_span;   // output channel of this lane
-    const int rho = (q * 32) / rep_span;        // which replica this quarter holds
-    const int ncol = 128 / n_rep;               // columns of the half this warp drains: 128 / 64 / 32
+    // m64: accumulator row r sits in lane 32 * (r / 16) + r % 16: quarter q holds channels 16q .. 16q + 15
+    const int c = m64 ? q * 16 + lane : (q * 32 + lane) % rep_span;   // output channel of this lane
+    const int rho = m64 ? 0 : (q * 32) / rep_span;                     // which replica this quarter holds
+    const int ncol = m64 ? 128 : 128 / n_rep;   // columns of the half this warp drains: 128 / 64 / 32
     const int col_lo = h * 128 + rho * ncol;    // first column (tile row) of this warp
-    const bool lane_live = c < Cout;
+    const bool lane_live = m64 ? lane < 16 : c < Cout;
     const bool odd = lane & 1;
     const int cb = c & ~1;             // channel pair this lane stores
     const float sc = (lane_live && scale) ? __ldg(&scale[c]) : 1.f;
     const float sh = (lane_live && shift) ? __ldg(&shift[c]) : 0.f;
     int t = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++t) {
+      const int tile = (flags_ & 2) ? n_tiles - 1 - tl : tl;   // bit 1: walk the tiles from the last row back (L2 reuse)
       const int ab = t & 1;
       const int row0 = tile * kTile + col_lo + (odd ? 1 : 0);   // slot of this lane: + col + 2p
       const int* srow = slot_row ? &S.srow[ab][col_lo + (odd ? 1 : 0)] : nullptr;
@@ -432,14 +443,23 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
   const int blk = Cin % 64 == 0 ? 64 : Cin;
   const uint32_t P = 2 * blk;
   const uint32_t kg = 64 / blk;
-  const uint32_t stage_bytes = kg * 128u * P + kg * kTile * P;   // 16 KB weights (replicated) + 32 KB rows
+  // Cout == 64 on 64-wide K blocks: M = 64 instruction, un-replicated 8 KB weight images, 4 stages of 40 KB filled by
+  // 8 producer warps (U3D_TN_M64=0 keeps the replicated M = 128 form)
+  // tile order: the previous layer left its LAST rows in L2 (feature matrices of the wide levels exceed it at batch
+  // 32), so every other launch walks the tiles backwards and starts on rows that are still resident
+  const bool reverse_tiles = (x3 & 2) != 0;
+  x3 &= 1;
+  bool m64 = Cout == 64 && blk == 64;
+  if (const char* e = getenv("U3D_TN_M64")) m64 = m64 && atoi(e) != 0;
+  const uint32_t stage_bytes = kg * (m64 ? 64u : 128u) * P + kg * kTile * P;   // weights (16 KB replicated / 8 KB) + 32 KB rows
   // Default: double-buffered rulebook slices, 6 producer warps, 3 stages. EXPERIMENTAL (not yet run on
   // hardware): U3D_TN_SLICE_BUFS=1 single-buffers the slices, which frees 28 KB for a 4th stage filled by a
   // 4th producer pair (576 threads).
   bool deep = false;
   if (const char* e = getenv("U3D_TN_SLICE_BUFS")) deep = atoi(e) == 1;
-  const int max_stages = deep ? 4 : 3;                        // one ring slot per producer pair
-  const size_t header = ((deep ? sizeof(Smem<1, 4>) : sizeof(Smem<2, 3>)) + 1023) & ~(size_t)1023;
+  if (m64) deep = false;
+  const int max_stages = (deep || m64) ? 4 : 3;               // one ring slot per producer pair
+  const size_t header = ((deep ? sizeof(Smem<1, 4>) : (m64 ? sizeof(Smem<2, 4>) : sizeof(Smem<2, 3>))) + 1023) & ~(size_t)1023;
   int stages = (int)((227u * 1024u - header) / stage_bytes);
   if (const char* e = getenv("U3D_TN_STAGES")) stages = atoi(e);
   if (stages > max_stages) stages = max_stages;
@@ -454,7 +474,8 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
     k_spconv_tn<BLK, SB, NP, X3><<<grid, threads_of(NP), smem, st>>>(                               \
         (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, slot_row, n_out, K,                   \
         (const __nv_bfloat16*)wpk, scale, shift, (const __nv_bfloat16*)residual, relu,              \
-        (__nv_bfloat16*)out, Cin, Cout, stages, in_ld, out_ld, cout_off, cout_total);               \
+        (__nv_bfloat16*)out, Cin, Cout, stages, in_ld, out_ld, cout_off, cout_total,                \
+        (m64 ? 1 : 0) | (reverse_tiles ? 2 : 0));                                                   \
   } while (0)
 #define U3D_TN_LAUNCH2(BLK, SB, NP)                                                                 \
   do {                                                                                              \
@@ -464,7 +485,8 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
   do {                                                                                              \
     if (deep) U3D_TN_LAUNCH2(BLK, 1, 8); else U3D_TN_LAUNCH2(BLK, 2, 6);                            \
   } while (0)
-  if (blk == 64) U3D_TN_LAUNCH(64);
+  if (blk == 64 && m64) U3D_TN_LAUNCH2(64, 2, 8);
+  else if (blk == 64) U3D_TN_LAUNCH(64);
   else if (blk == 32) U3D_TN_LAUNCH(32);
   else U3D_TN_LAUNCH(16);
 #undef U3D_TN_LAUNCH

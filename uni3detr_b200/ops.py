@@ -348,7 +348,7 @@ def spconv_pack_weights(w):
 @_timed(lambda r, x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, *a, **k: dict(
     n_out=int(n_out), pairs=_live_pairs(nbr, n_out), K=K, Cin=Cin, Cout=Cout, esize=2, tc=True))
 def spconv_fwd_packed(x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, scale=None, shift=None,
-                      residual=None, relu=False, out=None):
+                      residual=None, relu=False, out=None, reverse=False):
     """tcgen05 sparse conv: bf16 in/out, weights from spconv_pack_weights."""
     lib = _lib.load()
     _req(x, torch.bfloat16, "x")
@@ -362,7 +362,7 @@ def spconv_fwd_packed(x, nbr, n_out, out_cap, w_packed, K, Cin, Cout, scale=None
     _lib.check(lib.u3d_spconv_fwd_packed(_p(x), _p(nbr), stride, _p(tile_mask), _p(slot_row), _p(n_out),
                                          out_cap, K, _p(w_packed),
                                          _p(scale), _p(shift), _p(residual), int(bool(relu)), _p(out),
-                                         Cin, Cout, _stream()))
+                                         Cin, Cout, 2 if reverse else 0, _stream()))
     return out
 
 
@@ -797,7 +797,7 @@ def identity_rulebook(cap, device):
 
 @_timed(lambda r, x2, nbr, n_out, out_cap, pk, *a, **k: dict(
     n_out=int(n_out), pairs=_live_pairs(nbr, n_out), K=pk.K, Cin=pk.Cin, Cout=pk.Cout, esize=4, tc=True, x3=True))
-def spconv_fwd_packed_x3(x2, nbr, n_out, out_cap, pk, scale=None, shift=None, residual=None, relu=False):
+def spconv_fwd_packed_x3(x2, nbr, n_out, out_cap, pk, scale=None, shift=None, residual=None, relu=False, reverse=False):
     """fp32-grade sparse conv on tcgen05: x2 (rows, 2*Cin) bf16 [hi|lo] -> (out_cap, 2*Cout) bf16 [hi|lo]."""
     lib = _lib.load()
     _req(x2, torch.bfloat16, "x2")
@@ -809,5 +809,5 @@ def spconv_fwd_packed_x3(x2, nbr, n_out, out_cap, pk, scale=None, shift=None, re
         _lib.check(lib.u3d_spconv_fwd_packed_x3(
             _p(x2), _p(nbr), nbr.stride(0), _p(tile_mask), _p(slot_row), _p(n_out), out_cap, pk.K, _p(wp),
             _p(scale[c0:c0 + co]) if scale is not None else None, _p(shift[c0:c0 + co]) if shift is not None else None,
-            _p(residual), int(bool(relu)), _p(out), pk.Cin, co, c0, pk.Cout, _stream()))
+            _p(residual), int(bool(relu)), _p(out), pk.Cin, co, c0, pk.Cout, 2 if reverse else 0, _stream()))
     return out
