@@ -180,6 +180,8 @@ def roofline_of(top, peaks):
         with open(tpath) as f:
             tj = json.load(f).get(top["kernel"], {})
         traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("commit"):
+            roof["traffic_capture_commit"] = tj["commit"]      # binary the ncu capture was taken from
         if tj.get("tensor_pipe_active_pct") is not None:   # same committed ncu capture
             roof["tensor_pipe_active_pct_ncu"] = tj["tensor_pipe_active_pct"]
     roof.update({"traffic": traffic, "kernel": top["kernel"], "avg_launch_ms": top["avg_launch_ms"],

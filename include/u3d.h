@@ -249,11 +249,14 @@ int u3d_sparse_to_dense(const void* feats, const int32_t* coors, const int32_t* 
  *   seg (B+1) DEVICE int32 segment offsets; max_n HOST upper bound of points/scene
  *   reverse != 0: output columns are (src[2],src[1],src[0]) (zyx -> xyz, uni3detr.py:186)
  *   idx (B,nq) int32 (out); out (B,nq,3) f32 in [0,1] (out)
- *   Tie-break: lowest index wins; distance = ((dx*dx + dy*dy) + dz*dz) without FMA.
+ *   distance = ((dx*dx + dy*dy) + dz*dz) without FMA. Exact ties: tie_block = 0 -> lowest index;
+ *   tie_block = 1024 -> the point mmcv's kernel picks (block of min(1024, 2^floor(log2 n)) threads,
+ *   strided per-thread scan with strict >, shared-memory tree reduction that keeps the lower slot
+ *   on ties: smallest bit-reversed thread id, then lowest index; csrc/fps.cu header).
  */
 int u3d_fps(const float* dist_src, int dist_stride, int dist_seg_stride,
             const float* gather_src, int gather_stride, const int32_t* seg, int B, int max_n,
-            int nq, int reverse, int32_t* idx, float* out, void* stream);
+            int nq, int reverse, int tie_block, int32_t* idx, float* out, void* stream);
 
 /* int32 coors (rows,4)[b,z,y,x] -> f32 (rows,3) (z,y,x); feeds u3d_fps for FPS #2
  * (uni3detr.py:183). */

@@ -198,21 +198,64 @@ def pairs_from_table(nbr):
 
 
 # --------------------------------------------------------------------- FPS ----
-def furthest_point_sample(xyz, npoint):
+def fps_tie_key(n, tie_block=1024):
+    """Order in which mmcv's furthest_point_sample kernel resolves exact distance ties (smaller wins). The kernel
+    runs bs = min(tie_block, 2^floor(log2 n)) threads; thread t scans k = t, t+bs, ... keeping its first maximum
+    (strict >), then a shared-memory tree (s = bs/2 .. 1: slot t takes slot t+s only if strictly greater) picks the
+    block winner: two tied candidates meet at the level of the lowest bit in which their thread ids differ and the
+    one with that bit clear survives, i.e. the smallest BIT-REVERSED thread id wins, then the lowest k.
+    (mmcv/ops/csrc/common/cuda/furthest_point_sample_cuda_kernel.cuh - recalled, the source is not vendored;
+    literal restatement: fps_block_reference below.) tie_block=0: plain lowest index."""
+    k = np.arange(n, dtype=np.int64)
+    if not tie_block or n == 0:
+        return k
+    lg = min(int(np.floor(np.log2(n))), int(np.log2(tie_block)))
+    bs = 1 << lg
+    r = k % bs
+    rev = np.zeros(n, np.int64)
+    for b in range(lg):
+        rev |= ((r >> b) & 1) << (lg - 1 - b)
+    return (rev << 12) | (k // bs)
+
+
+def fps_block_reference(temp, bs):
+    """Literal restatement of the arg-max of one FPS iteration as the reference kernel computes it (per-thread strided
+    scan + shared-memory tree), for pinning fps_tie_key: returns the selected index."""
+    n = len(temp)
+    dists = np.full(bs, -1.0, F32)
+    dists_i = np.zeros(bs, np.int64)
+    for t in range(bs):
+        best, besti = F32(-1.0), 0
+        for k in range(t, n, bs):
+            if temp[k] > best:
+                best, besti = temp[k], k
+        dists[t], dists_i[t] = best, besti
+    s = bs // 2
+    while s >= 1:
+        for t in range(s):
+            if dists[t + s] > dists[t]:
+                dists[t], dists_i[t] = dists[t + s], dists_i[t + s]
+        s //= 2
+    return int(dists_i[0])
+
+
+def furthest_point_sample(xyz, npoint, tie_block=1024):
     """mmcv furthest_point_sample / D-FPS (call sites uni3detr.py:138,179,184):
-    idx[0]=0, temp=1e10, d = ((dx*dx+dy*dy)+dz*dz) in fp32 without FMA, ties -> lowest index."""
+    idx[0]=0, temp=1e10, d = ((dx*dx+dy*dy)+dz*dz) in fp32 without FMA, exact ties by fps_tie_key."""
     p = np.ascontiguousarray(xyz, F32)
     n = len(p)
     idx = np.zeros(npoint, np.int32)
     if n == 0:
         return idx
     temp = np.full(n, 1e10, F32)
+    key = fps_tie_key(n, tie_block)
     last = 0
     for j in range(1, npoint):
         d = p - p[last]
         d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
         temp = np.minimum(temp, d2)
-        last = int(np.argmax(temp))                 # first maximum == lowest index
+        cand = np.nonzero(temp == temp.max())[0]
+        last = int(cand[np.argmin(key[cand])]) if len(cand) > 1 else int(cand[0])
         idx[j] = last
     return idx
 

@@ -708,3 +708,40 @@ def test_spconv_x3_pointwise_identity_table():
                                   shift.to(DEV), relu=True)
     ref = torch.relu((x @ w[0]) * scale + shift)
     assert relerr(ops.merge_bf16(y2), ref) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (32, 32), (32, 64), (16, 32)])
+def test_spconv_switches_reverse_tiles_and_deep_ring(monkeypatch, cin, cout):
+    """Instruction-form / ring variants of the rows-on-N kernel give the same result as the default launch (the
+    weight-stationary `tcgen05.mma.ws` form with M = Cout for Cout = 32 / 64): reverse tile order (`reverse=True`), the
+    plain M = 64 form (U3D_TN_WS=0), the replicated M = 128 form (+ U3D_TN_M64=0) and the single-buffered-slice 4-stage
+    ring (+ U3D_TN_SLICE_BUFS=1), bf16 and the 3xBF16 fp32 form; and the default agrees with the fp32 reference."""
+    from uni3detr_b200 import ops
+    dims, B, n = (8, 24, 24), 2, 3000
+    coors, x, w, scale, shift = conv_case(n, dims, B, cin, cout, 4242)
+    c = T(coors).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    nbr = ops.rulebook_subm(c, n_rows, n, ops.voxmap_build(c, n_rows, n, B, dims))
+    wd = w.reshape(27, cin, cout).to(DEV)
+    wp = ops.spconv_pack_weights(wd.bfloat16().contiguous())
+    pk = ops.PackedConvX3(wd)
+    xb, x2 = x.to(DEV).bfloat16(), ops.split_bf16(x.to(DEV))
+
+    def run(**kw):
+        a = ops.spconv_fwd_packed(xb, nbr, n_rows, n, wp, 27, cin, cout, scale.to(DEV), shift.to(DEV), relu=True, **kw)
+        b = ops.spconv_fwd_packed_x3(x2, nbr, n_rows, n, pk, scale.to(DEV), shift.to(DEV), relu=True, **kw)
+        return a.clone(), b.clone()
+    base = run()
+    ref = oracle_conv(x, G.subm_rulebook(coors, dims), w, n, scale, shift, None, True)
+    assert relerr(base[0][:n], ref) < 1e-2
+    assert relerr(ops.merge_bf16(base[1])[:n], ref) < 1e-4
+    for name, env, kw in (("reverse", {}, dict(reverse=True)), ("m64", {"U3D_TN_WS": "0"}, {}),
+                          ("m128", {"U3D_TN_WS": "0", "U3D_TN_M64": "0"}, {}),
+                          ("deep", {"U3D_TN_WS": "0", "U3D_TN_SLICE_BUFS": "1", "U3D_TN_M64": "0"}, {})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = run(**kw)
+        for k in env:
+            monkeypatch.delenv(k)
+        for g_, b_ in zip(got, base):
+            assert torch.equal(g_, b_), name     # same accumulation order per row: bit-identical

@@ -223,8 +223,26 @@ def test_fps_lattice_ties_and_reverse():
     seg = torch.tensor([0, 6000], dtype=torch.int32, device=DEV)
     idx, out = ops.fps(cf, 3, 3, cf, 3, seg, 1, 6000, 300, reverse=True)
     ref = G.furthest_point_sample(cz, 300)
-    np.testing.assert_array_equal(idx[0].cpu().numpy(), ref)           # exact ties -> lowest index
+    np.testing.assert_array_equal(idx[0].cpu().numpy(), ref)           # exact ties -> the reference kernel's order
     np.testing.assert_allclose(out[0].cpu().numpy(), G.shift_scale_unit(cz[ref][:, [2, 1, 0]]), atol=1e-6)
+    idx0, _ = ops.fps(cf, 3, 3, cf, 3, seg, 1, 6000, 300, reverse=True, tie_block=0)
+    ref0 = G.furthest_point_sample(cz, 300, tie_block=0)
+    np.testing.assert_array_equal(idx0[0].cpu().numpy(), ref0)         # tie_block = 0 -> lowest index
+    assert (ref0 != ref).any()                                         # the two orders do differ on a lattice
+
+
+@pytest.mark.parametrize("n,cap", [(27, 1024), (700, 1024), (3000, 1024), (3000, 256), (21000, 1024), (70000, 1024)])
+def test_fps_tie_order_small_lattices(n, cap):
+    """Exact ties at every iteration (points on a coarse integer lattice, duplicates included) for every kernel
+    configuration size class: picks equal the oracle's under the reference kernel's tie order."""
+    from uni3detr_b200 import ops
+    rng = np.random.default_rng(n + cap)
+    pts_np = rng.integers(0, 6, (n, 3)).astype(np.float32)
+    pts = torch.from_numpy(pts_np).to(DEV)
+    seg = torch.tensor([0, n], dtype=torch.int32, device=DEV)
+    nq = min(n, 40)
+    idx, _ = ops.fps(pts, 3, 3, pts, 3, seg, 1, n, nq, tie_block=cap)
+    np.testing.assert_array_equal(idx[0].cpu().numpy(), G.furthest_point_sample(pts_np, nq, tie_block=cap))
 
 
 def test_fps_stride_quirk_and_queries():

@@ -60,7 +60,9 @@ D_PAIRS = {(13, 0): 0, (26, 7): 2, (14, 0): 3, (12, 1): 3,
 F_LINE = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [10, 0, 0], [4, 0, 0]], np.float32)
 F_LINE_IDX = [0, 3, 4, 2]          # start at 0; farthest 10; then 4 (16 vs 4, 1); then 2 (4 vs 1)
 F_TIE = np.array([[0, 0, 0], [2, 0, 0], [-2, 0, 0], [0, 1, 0]], np.float32)
-F_TIE_IDX = [0, 1, 2]              # rows 1 and 2 tie at distance 4: the lowest index first
+F_TIE_IDX = [0, 1, 2]              # rows 1 and 2 tie at distance 4: the lowest index first (tie_block = 0)
+F_TIE_IDX_BLOCK = [0, 2, 1]        # the reference kernel's 4-thread tree: slot 0 <- max(0, 2), slot 1 <- max(1, 3), then
+                                   # slot 0 keeps its own on the tie with slot 1 -> thread 2's point first
 
 
 def table_from_pairs(pairs, n_out):
@@ -109,7 +111,8 @@ def test_oracle_sparse_conv_known_answer():
 
 def test_oracle_fps_known_answer():
     np.testing.assert_array_equal(G.furthest_point_sample(F_LINE, 4), F_LINE_IDX)
-    np.testing.assert_array_equal(G.furthest_point_sample(F_TIE, 3), F_TIE_IDX)
+    np.testing.assert_array_equal(G.furthest_point_sample(F_TIE, 3, tie_block=0), F_TIE_IDX)
+    np.testing.assert_array_equal(G.furthest_point_sample(F_TIE, 3), F_TIE_IDX_BLOCK)
 
 
 # ------------------------------------------------------------------ product (GPU) ----
@@ -207,10 +210,10 @@ def test_gpu_sparse_conv_known_answer():
 @pytest.mark.gpu
 def test_gpu_fps_known_answer():
     from uni3detr_b200 import ops
-    for pts_np, want in ((F_LINE, F_LINE_IDX), (F_TIE, F_TIE_IDX)):
+    for pts_np, want, tb in ((F_LINE, F_LINE_IDX, 1024), (F_TIE, F_TIE_IDX, 0), (F_TIE, F_TIE_IDX_BLOCK, 1024)):
         pts = torch.from_numpy(pts_np).to(DEV)
         seg = torch.tensor([0, len(pts_np)], dtype=torch.int32, device=DEV)
-        idx, _ = ops.fps(pts, 3, 3, pts, 3, seg, 1, len(pts_np), len(want))
+        idx, _ = ops.fps(pts, 3, 3, pts, 3, seg, 1, len(pts_np), len(want), tie_block=tb)
         np.testing.assert_array_equal(idx[0].cpu().numpy(), want)
 
 

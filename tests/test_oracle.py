@@ -159,10 +159,32 @@ def test_fps_bruteforce_and_ties():
     assert idx.tolist() == ref
     # integer lattice: exact ties everywhere -> lowest index wins
     lat = np.array([[z, y, x] for z in range(3) for y in range(3) for x in range(3)], np.float32)
-    idx = G.furthest_point_sample(lat, 5)
+    idx = G.furthest_point_sample(lat, 5, tie_block=0)
     assert idx[0] == 0 and idx[1] == 26           # unique farthest corner
     assert idx[2] == 5                            # (0,1,2),(0,2,1),(1,0,2).. all at min-dist 5 -> lowest index
     assert len(set(idx.tolist())) == 5
+    # reference tie order (block of 16 threads for 27 points): candidates 5,7,11,15,19,21 -> thread ids 5,7,11,15,3,5;
+    # bit-reversed (4 bits) 10,14,13,15,12,10 -> thread 5 wins, its first maximum is k = 5
+    idx = G.furthest_point_sample(lat, 5)
+    assert idx[:3].tolist() == [0, 26, 5] and len(set(idx.tolist())) == 5
+
+
+def test_fps_tie_order_matches_block_reduction():
+    """The closed-form tie key (bit-reversed thread id, then index) against a literal restatement of the reference
+    kernel's arg-max: per-thread strided scan with strict '>' + shared-memory tree that keeps the lower slot."""
+    rng = np.random.default_rng(11)
+    for n, cap in ((27, 1024), (100, 1024), (1000, 64), (2500, 1024), (5000, 512), (3, 1024), (1, 1024)):
+        bs = min(cap, 1 << int(np.floor(np.log2(n))))
+        key = G.fps_tie_key(n, cap)
+        assert len(set(key.tolist())) == n                     # a total order
+        for trial in range(6):
+            temp = rng.integers(0, 4, n).astype(np.float32)    # few distinct values: ties everywhere
+            if trial == 5:
+                temp[:] = 0.0
+            want = G.fps_block_reference(temp, bs)
+            cand = np.nonzero(temp == temp.max())[0]
+            assert int(cand[np.argmin(key[cand])]) == want, (n, cap, trial)
+    np.testing.assert_array_equal(G.fps_tie_key(10, 0), np.arange(10))
 
 
 def test_fps_stride_quirk_view():

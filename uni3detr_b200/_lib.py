@@ -118,7 +118,7 @@ SIGNATURES = {
     "u3d_rulebook_sort_tiles": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "u3d_sparse_to_dense": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
                                    _vp, _vp]),
-    "u3d_fps": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "u3d_fps": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "u3d_coors_to_float": (_i32, [_vp, _i32, _vp, _vp]),
     "u3d_sine_embed": (_i32, [_vp, _i32, _vp, _i32, _vp]),
     "u3d_add_layernorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _f32, _i32, _i32, _i32, _vp, _i32, _vp]),

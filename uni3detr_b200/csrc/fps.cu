@@ -16,8 +16,14 @@
 // All scenes of the batch run concurrently (grid = B clusters).
 //
 // Defined arithmetic (mirrored by oracle/): d = ((dx*dx + dy*dy) + dz*dz) with no FMA
-// contraction, running distance initialised to 1e10, first pick = index 0, ties -> the
-// lowest index.
+// contraction, running distance initialised to 1e10, first pick = index 0. Exact distance ties
+// (the rule on the integer voxel lattice of FPS #2): `tie_block` = 0 -> the lowest index;
+// `tie_block` = T (the reference kernel's block-size cap, 1024 in mmcv) -> the winner of mmcv's
+// reduction: that kernel runs bs = min(T, 2^floor(log2 n)) threads, thread t scans k = t, t + bs, ...
+// keeping its FIRST maximum (strict >), then a shared-memory tree (s = bs/2 .. 1: slot t takes slot
+// t + s only if strictly greater) - so among tied points the one whose thread id has the smallest
+// BIT-REVERSED value wins, and within a thread the lowest k. Both are a total order on indices, so
+// they fold into the arg-max key: key(k) = bitrev_log2(bs)(k mod bs) << 12 | k / bs.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -30,7 +36,7 @@ constexpr int kFpsMaxNq = 4096;
 
 // One candidate travelling between CTAs: 32 bytes = two 16-byte DSMEM stores.
 // (hi, lo) is the arg-max key: hi = bits of the (non-negative) distance, lo = ~index, so an
-// unsigned 64-bit max picks the largest distance and, on exact ties, the LOWEST index.
+// unsigned 64-bit max picks the largest distance and, on exact ties, the LOWEST tie key (fps_key).
 struct __align__(16) FpsMsg {
   uint32_t hi, lo;
   float x, y, z;
@@ -39,6 +45,19 @@ struct __align__(16) FpsMsg {
 
 __device__ __forceinline__ uint32_t fps_smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// tie order of point i (smaller wins): i itself, or mmcv's reduction order for a block of 2^lg threads (lg < 0: off)
+__device__ __forceinline__ uint32_t fps_key(uint32_t i, int lg) {
+  if (lg < 0) return i;
+  if (lg == 0) return i;
+  const uint32_t r = i & ((1u << lg) - 1u);
+  return ((__brev(r) >> (32 - lg)) << 12) | (i >> lg);
+}
+__device__ __forceinline__ uint32_t fps_unkey(uint32_t key, int lg) {
+  if (lg <= 0) return key;
+  const uint32_t r = __brev(key >> 12) >> (32 - lg);
+  return ((key & 0xfffu) << lg) | r;
 }
 
 // warp arg-max of a (hi, lo) key with two REDUX instructions; returns true on the winning lane
@@ -52,7 +71,7 @@ template <int THREADS, int PPT, int CS, bool SMEM_XYZ>
 __global__ void __launch_bounds__(THREADS, 1)
 k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
       const float* __restrict__ gather_src, int gather_stride, const int32_t* __restrict__ seg,
-      int nq, int reverse, int32_t* __restrict__ idx_out, float* __restrict__ out) {
+      int nq, int reverse, int tie_block, int32_t* __restrict__ idx_out, float* __restrict__ out) {
   constexpr int NW = THREADS / 32;
   extern __shared__ float s_dyn[];              // SMEM_XYZ: x[PPT*THREADS], y[..], z[..]
   __shared__ FpsMsg s_warp[NW];
@@ -68,6 +87,13 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
   const int s0 = seg[scene];
   const int n = seg[scene + 1] - s0;
   const float* base = dist_src + (size_t)s0 * dist_seg_stride;
+  // log2 of the reference kernel's block size for this scene (-1: lowest-index ties)
+  int lg = -1;
+  if (tie_block > 0 && n > 0) {
+    lg = 31 - __clz(n);
+    const int cap = 31 - __clz(tie_block);
+    if (lg > cap) lg = cap;
+  }
 
   float px[SMEM_XYZ ? 1 : PPT], py[SMEM_XYZ ? 1 : PPT], pz[SMEM_XYZ ? 1 : PPT], td[PPT];
   float* sx = s_dyn;
@@ -107,9 +133,9 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
   else __syncthreads();
 
   for (int it = 1; it < nq; ++it) {
-    // 1. update running distances, thread-local arg-max (ascending index: strict '>' keeps the lowest)
+    // 1. update running distances, thread-local arg-max (ties: the smaller key)
     float bt = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
-    int bj = 0;
+    uint32_t bkey = 0xffffffffu;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       const float x = SMEM_XYZ ? sx[j * THREADS + tid] : px[j];
@@ -119,10 +145,13 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
       const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
       const float t = fminf(td[j], d);
       td[j] = t;
-      if (t > bt) { bt = t; bj = j; bx = x; by = y; bz = z; }
+      const uint32_t i = (uint32_t)((j * CS + crank) * THREADS + tid);
+      // padding (distance 0, i >= n) keeps a key above every real point's: it loses every tie
+      const uint32_t key = (int)i < n ? fps_key(i, lg) : (0x7f000000u | i);
+      if (t > bt || (t == bt && key < bkey)) { bt = t; bkey = key; bx = x; by = y; bz = z; }
     }
     const uint32_t hi = __float_as_uint(bt);
-    const uint32_t lo = 0xffffffffu - (uint32_t)((bj * CS + crank) * THREADS + tid);
+    const uint32_t lo = 0xffffffffu - bkey;
     // 2. warp arg-max (2 REDUX); the winning lane publishes key + coordinates
     uint32_t whi, wlo;
     if (warp_argmax(hi, lo, whi, wlo)) {
@@ -175,7 +204,7 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
       if (c.hi > w.hi || (c.hi == w.hi && c.lo > w.lo)) w = c;
     }
     lx = w.x; ly = w.y; lz = w.z;
-    if (tid == 0) s_sel[it] = (int)(0xffffffffu - w.lo);
+    if (tid == 0) s_sel[it] = (int)fps_unkey(0xffffffffu - w.lo, lg);
   }
   __syncthreads();
   if (crank != 0) return;  // every CTA holds the same selection; rank 0 writes it
@@ -230,7 +259,7 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
 template <int THREADS, int PPT, int CS, bool SMEM_XYZ>
 static int launch_fps(const float* dist_src, int dist_stride, int dist_seg_stride,
                       const float* gather_src, int gather_stride, const int32_t* seg, int B, int nq,
-                      int reverse, int32_t* idx, float* out, cudaStream_t st) {
+                      int reverse, int tie_block, int32_t* idx, float* out, cudaStream_t st) {
   auto kern = k_fps<THREADS, PPT, CS, SMEM_XYZ>;
   const size_t dyn = SMEM_XYZ ? (size_t)3 * PPT * THREADS * sizeof(float) : 0;
   cudaLaunchConfig_t cfg = {};
@@ -253,7 +282,7 @@ static int launch_fps(const float* dist_src, int dist_stride, int dist_seg_strid
     configured = true;
   }
   U3D_CUDA(cudaLaunchKernelEx(&cfg, kern, dist_src, dist_stride, dist_seg_stride, gather_src,
-                              gather_stride, seg, nq, reverse, idx, out));
+                              gather_stride, seg, nq, reverse, tie_block, idx, out));
   count_launch();
   return U3D_OK;
 }
@@ -273,16 +302,18 @@ using namespace u3d;
 
 extern "C" int u3d_fps(const float* dist_src, int dist_stride, int dist_seg_stride,
                        const float* gather_src, int gather_stride, const int32_t* seg, int B,
-                       int max_n, int nq, int reverse, int32_t* idx, float* out, void* stream) {
+                       int max_n, int nq, int reverse, int tie_block, int32_t* idx, float* out, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   U3D_CHECK_ARG(dist_src && gather_src && seg && idx && out, "u3d_fps: null buffer");
   U3D_CHECK_ARG(B >= 1 && nq >= 1 && nq <= kFpsMaxNq && max_n >= 0, "u3d_fps: bad B/nq (nq<=%d)",
                 kFpsMaxNq);
   U3D_CHECK_ARG(dist_stride >= 3 && gather_stride >= 3 && dist_seg_stride >= 3, "u3d_fps: strides");
+  U3D_CHECK_ARG(tie_block >= 0 && tie_block <= 1024 && (tie_block & (tie_block - 1)) == 0,
+                "u3d_fps: tie_block=%d must be 0 or a power of two <= 1024", tie_block);
 #define U3D_FPS_CASE(THREADS, PPT, CS, SM)                                                         \
   if ((long long)max_n <= (long long)THREADS * PPT * CS)                                          \
     return launch_fps<THREADS, PPT, CS, SM>(dist_src, dist_stride, dist_seg_stride, gather_src,   \
-                                           gather_stride, seg, B, nq, reverse, idx, out, st);
+                                           gather_stride, seg, B, nq, reverse, tie_block, idx, out, st);
   // smallest configuration that keeps every point of a scene on chip: registers up to 16
   // points/thread, shared memory for the coordinates beyond that (distances stay in registers)
   U3D_FPS_CASE(256, 8, 1, false)     //   2 048

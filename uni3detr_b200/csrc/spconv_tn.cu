@@ -129,9 +129,16 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   // rows in the first 16 lanes of every TMEM lane quarter, so all eight epilogue warps still drain a tile.
   const int flags_ = m64;
   m64 &= 1;
-  const uint32_t w_unit = (m64 ? 64u : 128u) * SW::P;                       // 4 / 8 / 16 KB (m64: 8 KB)
+  // ws (bit 2, Cout == 32 / 64): the weight-stationary instruction form `tcgen05.mma.ws` with M = Cout. Its accumulator
+  // spreads the N = 256 columns over the idle lane groups (M = 64: lanes 64-127 hold columns 128-255; M = 32: lane
+  // quarter q holds columns 64q .. 64q+63), so the datapath is full: a dispatch costs N/4 = 64 cycles instead of 128
+  // (scripts/ubench/mma_cost.cu, profiles/r02_ubench_mma.txt), the un-replicated image is Cout rows, and every lane
+  // of all eight epilogue warps holds live data.
+  const bool ws = (flags_ & 4) != 0;
+  const uint32_t a_rows = ws ? (uint32_t)Cout : (m64 ? 64u : 128u);         // rows of one weight image
+  const uint32_t w_unit = a_rows * SW::P;                                   // 4 / 8 / 16 KB (m64: 8 KB)
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(wpk) +
-                        ((Cout < 128 && !m64) ? (size_t)K * nkb * CIN_BLK * Cout * 2 : (size_t)0);   // 128-row images
+                        ((Cout < 128 && !m64 && !ws) ? (size_t)K * nkb * CIN_BLK * Cout * 2 : (size_t)0);   // 128-row images
   const uint32_t w_region = kG * w_unit;                                    // 16 KB for every CIN_BLK (m64: 8 KB)
   const uint32_t stage_bytes = w_region + kXBytes;
   const uint32_t tiles_s = smem_u32(smem_raw) + kHeader;                   // 1024-aligned
@@ -273,7 +280,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     if (lane == 0) {
       // kind::f16: D = f32, A = B = bf16, both K-major, N = 256, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) |
-                             ((uint32_t)((m64 ? 64 : 128) >> 4) << 24);
+                             ((uint32_t)(a_rows >> 4) << 24);
       int slot = 0, t = 0;
       uint32_t fph = 0u;
       for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++t) {
@@ -300,9 +307,11 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
               const uint64_t w_desc = SW::desc(st_s + (uint32_t)j * w_unit);
               const uint64_t x_desc = SW::desc(st_s + w_region + (uint32_t)(j * kUnitX));
 #pragma unroll
-              for (int kk = 0; kk < CIN_BLK / 16; ++kk)
-                umma_bf16(d_tmem, w_desc + (uint64_t)(kk * 2), x_desc + (uint64_t)(kk * 2), idesc,
-                          (st > 0 || j > 0 || kk > 0) ? 1u : 0u);
+              for (int kk = 0; kk < CIN_BLK / 16; ++kk) {
+                const uint32_t acc = (st > 0 || j > 0 || kk > 0) ? 1u : 0u;
+                if (ws) umma_bf16_ws(d_tmem, w_desc + (uint64_t)(kk * 2), x_desc + (uint64_t)(kk * 2), idesc, acc);
+                else umma_bf16(d_tmem, w_desc + (uint64_t)(kk * 2), x_desc + (uint64_t)(kk * 2), idesc, acc);
+              }
             }
           }
           umma_commit(&S.empty[slot]);
@@ -317,11 +326,14 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     const int q = warp & 3;            // TMEM lane quarter this warp may read
     const int h = warp >> 2;           // column (= row of the tile) half
     // m64: accumulator row r sits in lane 32 * (r / 16) + r % 16: quarter q holds channels 16q .. 16q + 15
-    const int c = m64 ? q * 16 + lane : (q * 32 + lane) % rep_span;   // output channel of this lane
+    // ws: TMEM lane 32q + lane holds channel (32q + lane) % Cout of the tile rows (32q / Cout) * (256 Cout / 128) + column
+    const int c = ws ? (q * 32 + lane) % Cout : (m64 ? q * 16 + lane : (q * 32 + lane) % rep_span);   // output channel of this lane
     const int rho = m64 ? 0 : (q * 32) / rep_span;                     // which replica this quarter holds
-    const int ncol = m64 ? 128 : 128 / n_rep;   // columns of the half this warp drains: 128 / 64 / 32
-    const int col_lo = h * 128 + rho * ncol;    // first column (tile row) of this warp
-    const bool lane_live = m64 ? lane < 16 : c < Cout;
+    const int ws_cols = 2 * Cout;               // ws: TMEM columns of one accumulator (128 / 64)
+    const int ncol = ws ? ws_cols / 2 : (m64 ? 128 : 128 / n_rep);   // columns this warp drains: 128 / 64 / 32
+    const int tcol_lo = ws ? h * ncol : h * 128 + rho * ncol;         // first TMEM column of this warp
+    const int col_lo = ws ? ((q * 32) / Cout) * ws_cols + h * ncol : tcol_lo;   // first tile row of this warp
+    const bool lane_live = ws ? true : (m64 ? lane < 16 : c < Cout);
     const bool odd = lane & 1;
     const int cb = c & ~1;             // channel pair this lane stores
     const float sc = (lane_live && scale) ? __ldg(&scale[c]) : 1.f;
@@ -352,7 +364,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       mbar_wait_relaxed(&S.acc_full[ab], (uint32_t)(t >> 1) & 1u, 2000u);
       tc_fence_after();
       if (srow) load_res(0);
-      const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * kTile + col_lo);
+      const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * kTile + tcol_lo);
 #pragma unroll 1
       for (int col = 0; col < ncol; col += 32) {
         uint32_t v[32];
@@ -451,15 +463,21 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
   x3 &= 1;
   bool m64 = Cout == 64 && blk == 64;
   if (const char* e = getenv("U3D_TN_M64")) m64 = m64 && atoi(e) != 0;
-  const uint32_t stage_bytes = kg * (m64 ? 64u : 128u) * P + kg * kTile * P;   // weights (16 KB replicated / 8 KB) + 32 KB rows
-  // Default: double-buffered rulebook slices, 6 producer warps, 3 stages. EXPERIMENTAL (not yet run on
-  // hardware): U3D_TN_SLICE_BUFS=1 single-buffers the slices, which frees 28 KB for a 4th stage filled by a
-  // 4th producer pair (576 threads).
+  // Cout == 32 / 64: weight-stationary instruction form with M = Cout on the un-replicated images (U3D_TN_WS=0 falls
+  // back to the M = 64 / replicated M = 128 forms); 8 producer warps, 4 stages of 36 / 40 KB
+  bool ws = Cout == 32 || Cout == 64;
+  if (const char* e = getenv("U3D_TN_WS")) ws = ws && atoi(e) != 0;
+  if (ws) m64 = false;
+  const uint32_t a_rows = ws ? (uint32_t)Cout : (m64 ? 64u : 128u);
+  const uint32_t stage_bytes = kg * a_rows * P + kg * kTile * P;   // weight images (16 KB replicated / <= 8 KB) + 32 KB rows
+  // Default: double-buffered rulebook slices, 6 producer warps, 3 stages. U3D_TN_SLICE_BUFS=1 single-buffers the slices,
+  // which frees 28 KB for a 4th stage filled by a 4th producer pair (576 threads; measured slower).
   bool deep = false;
   if (const char* e = getenv("U3D_TN_SLICE_BUFS")) deep = atoi(e) == 1;
-  if (m64) deep = false;
-  const int max_stages = (deep || m64) ? 4 : 3;               // one ring slot per producer pair
-  const size_t header = ((deep ? sizeof(Smem<1, 4>) : (m64 ? sizeof(Smem<2, 4>) : sizeof(Smem<2, 3>))) + 1023) & ~(size_t)1023;
+  const bool wide = m64 || ws;                                 // 8 producer warps, double-buffered slices
+  if (wide) deep = false;
+  const int max_stages = (deep || wide) ? 4 : 3;               // one ring slot per producer pair
+  const size_t header = ((deep ? sizeof(Smem<1, 4>) : (wide ? sizeof(Smem<2, 4>) : sizeof(Smem<2, 3>))) + 1023) & ~(size_t)1023;
   int stages = (int)((227u * 1024u - header) / stage_bytes);
   if (const char* e = getenv("U3D_TN_STAGES")) stages = atoi(e);
   if (stages > max_stages) stages = max_stages;
@@ -475,7 +493,7 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
         (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, slot_row, n_out, K,                   \
         (const __nv_bfloat16*)wpk, scale, shift, (const __nv_bfloat16*)residual, relu,              \
         (__nv_bfloat16*)out, Cin, Cout, stages, in_ld, out_ld, cout_off, cout_total,                \
-        (m64 ? 1 : 0) | (reverse_tiles ? 2 : 0));                                                   \
+        (m64 ? 1 : 0) | (reverse_tiles ? 2 : 0) | (ws ? 4 : 0));                                                   \
   } while (0)
 #define U3D_TN_LAUNCH2(BLK, SB, NP)                                                                 \
   do {                                                                                              \
@@ -485,7 +503,11 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
   do {                                                                                              \
     if (deep) U3D_TN_LAUNCH2(BLK, 1, 8); else U3D_TN_LAUNCH2(BLK, 2, 6);                            \
   } while (0)
-  if (blk == 64 && m64) U3D_TN_LAUNCH2(64, 2, 8);
+  if (wide) {
+    if (blk == 64) U3D_TN_LAUNCH2(64, 2, 8);
+    else if (blk == 32) U3D_TN_LAUNCH2(32, 2, 8);
+    else U3D_TN_LAUNCH2(16, 2, 8);
+  }
   else if (blk == 64) U3D_TN_LAUNCH(64);
   else if (blk == 32) U3D_TN_LAUNCH(32);
   else U3D_TN_LAUNCH(16);

@@ -106,6 +106,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// weight-stationary form (M = 32 / 64 / 128, N = 64 / 128 / 256): for M < 128 the accumulator's columns are spread over
+// the lane groups a plain M < 128 instruction leaves idle (M = 64: element (m, n) in lane m + 64 (n / (N/2)), column
+// n % (N/2); M = 32: lane m + 32 (n / (N/4)), column n % (N/4)), so the instruction runs at the full datapath rate
+__device__ __forceinline__ void umma_bf16_ws(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.ws.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "

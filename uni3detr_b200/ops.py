@@ -382,8 +382,10 @@ def sparse_to_dense(feats, coors, n_rows, cap, B, dims, channels_last=True, out=
 
 @_timed(lambda r, dist_src, ds, dss, gs, gst, seg, B, max_n, nq, **k: dict(B=B, max_n=max_n, nq=nq))
 def fps(dist_src, dist_stride, dist_seg_stride, gather_src, gather_stride, seg, B, max_n, nq,
-        reverse=False):
-    """Batched D-FPS + gather + min-max normalise. Returns (idx (B,nq) int32, pts (B,nq,3) f32)."""
+        reverse=False, tie_block=1024):
+    """Batched D-FPS + gather + min-max normalise. Returns (idx (B,nq) int32, pts (B,nq,3) f32).
+    tie_block: exact distance ties resolve like mmcv's kernel with that block-size cap (1024, default) or to the
+    lowest index (0)."""
     lib = _lib.load()
     _req(dist_src, torch.float32, "dist_src")
     _req(gather_src, torch.float32, "gather_src")
@@ -391,7 +393,7 @@ def fps(dist_src, dist_stride, dist_seg_stride, gather_src, gather_stride, seg, 
     idx = torch.empty((B, nq), dtype=torch.int32, device=dist_src.device)
     out = torch.empty((B, nq, 3), dtype=torch.float32, device=dist_src.device)
     _lib.check(lib.u3d_fps(_p(dist_src), dist_stride, dist_seg_stride, _p(gather_src),
-                           gather_stride, _p(seg), B, int(max_n), nq, int(bool(reverse)), _p(idx),
+                           gather_stride, _p(seg), B, int(max_n), nq, int(bool(reverse)), int(tie_block), _p(idx),
                            _p(out), _stream()))
     return idx, out
 
