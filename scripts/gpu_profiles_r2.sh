@@ -11,8 +11,9 @@ timeout 600 ncu --clock-control none -k 'regex:k_' -s 620 -c 220 --csv --log-fil
   --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct,lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,launch__grid_size,launch__registers_per_thread \
   $B > gpurun_out/ncu_kernels.log 2>&1
 echo "kernels $?"
-# the 64 -> 64 SubM layers run the <64, 2, 8> instantiation (M = 64 path): 4 launches per forward
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_spconv_tn<64, 2, 8' -s 12 -c 4 -o gpurun_out/ncu_spconv_tn64_r2 $B > gpurun_out/ncu_tn.log 2>&1
+# the 20 k_spconv_tn launches of a forward come in layer order (6 x Cin 16, 5 x Cin 32, then 64->64 x 4, 64->128,
+# 128->128 x 4): skip three warm-up forwards + 11 launches -> the four 64->64 launches, then the four 128->128
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_spconv_tn -s 71 -c 9 -o gpurun_out/ncu_spconv_tn64_r2 $B > gpurun_out/ncu_tn.log 2>&1
 echo "tn64 $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_linear_tc -s 261 -c 12 -o gpurun_out/ncu_linear_r2 $B > gpurun_out/ncu_lin.log 2>&1
 echo "lin $?"

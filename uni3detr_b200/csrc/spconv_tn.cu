@@ -87,7 +87,7 @@ __device__ __forceinline__ uint32_t mask_of_tile(const uint32_t* __restrict__ ti
 // the tensor cores within the 1e-3 parity bound instead of on FFMA. `Cin` is the REAL channel count; `in_ld` /
 // `out_ld` are the row strides of the input / output (and residual) matrices, `cout_off` the first output
 // channel of this launch (Cout > 128 runs as several 128-channel launches), `cout_total` the real width.
-template <int CIN_BLK, int kSliceBufs, int kNumProd, bool kX3>
+template <int CIN_BLK, int kSliceBufs, int kNumProd, bool kX3, bool kWS>
 __global__ void __launch_bounds__(threads_of(kNumProd), 1)
 k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nbr, int nbr_stride,
             const uint32_t* __restrict__ tile_mask, const int32_t* __restrict__ slot_row,
@@ -134,7 +134,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   // quarter q holds columns 64q .. 64q+63), so the datapath is full: a dispatch costs N/4 = 64 cycles instead of 128
   // (scripts/ubench/mma_cost.cu, profiles/r02_ubench_mma.txt), the un-replicated image is Cout rows, and every lane
   // of all eight epilogue warps holds live data.
-  const bool ws = (flags_ & 4) != 0;
+  constexpr bool ws = kWS;   // a template parameter: a run-time branch around the MMA issue cost 30 % (measured)
   const uint32_t a_rows = ws ? (uint32_t)Cout : (m64 ? 64u : 128u);         // rows of one weight image
   const uint32_t w_unit = a_rows * SW::P;                                   // 4 / 8 / 16 KB (m64: 8 KB)
   const uint8_t* wimg = reinterpret_cast<const uint8_t*>(wpk) +
@@ -485,29 +485,30 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
   const size_t smem = header + (size_t)stages * stage_bytes;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
 
-#define U3D_TN_LAUNCH3(BLK, SB, NP, X3)                                                             \
+#define U3D_TN_LAUNCH3(BLK, SB, NP, X3, WS)                                                           \
   do {                                                                                              \
     static int cur_smem = 0;                                                                        \
-    U3D_CUDA(ensure_dynamic_smem(k_spconv_tn<BLK, SB, NP, X3>, smem, &cur_smem));                   \
-    k_spconv_tn<BLK, SB, NP, X3><<<grid, threads_of(NP), smem, st>>>(                               \
+    U3D_CUDA(ensure_dynamic_smem(k_spconv_tn<BLK, SB, NP, X3, WS>, smem, &cur_smem));               \
+    k_spconv_tn<BLK, SB, NP, X3, WS><<<grid, threads_of(NP), smem, st>>>(                           \
         (const __nv_bfloat16*)in, nbr, nbr_stride, tile_mask, slot_row, n_out, K,                   \
         (const __nv_bfloat16*)wpk, scale, shift, (const __nv_bfloat16*)residual, relu,              \
         (__nv_bfloat16*)out, Cin, Cout, stages, in_ld, out_ld, cout_off, cout_total,                \
-        (m64 ? 1 : 0) | (reverse_tiles ? 2 : 0) | (ws ? 4 : 0));                                                   \
+        (m64 ? 1 : 0) | (reverse_tiles ? 2 : 0));                                                   \
   } while (0)
-#define U3D_TN_LAUNCH2(BLK, SB, NP)                                                                 \
+#define U3D_TN_LAUNCH2(BLK, SB, NP, WS)                                                             \
   do {                                                                                              \
-    if (x3) U3D_TN_LAUNCH3(BLK, SB, NP, true); else U3D_TN_LAUNCH3(BLK, SB, NP, false);             \
+    if (x3) U3D_TN_LAUNCH3(BLK, SB, NP, true, WS); else U3D_TN_LAUNCH3(BLK, SB, NP, false, WS);     \
   } while (0)
 #define U3D_TN_LAUNCH(BLK)                                                                          \
   do {                                                                                              \
-    if (deep) U3D_TN_LAUNCH2(BLK, 1, 8); else U3D_TN_LAUNCH2(BLK, 2, 6);                            \
+    if (deep) U3D_TN_LAUNCH2(BLK, 1, 8, false); else U3D_TN_LAUNCH2(BLK, 2, 6, false);              \
   } while (0)
-  if (wide) {
-    if (blk == 64) U3D_TN_LAUNCH2(64, 2, 8);
-    else if (blk == 32) U3D_TN_LAUNCH2(32, 2, 8);
-    else U3D_TN_LAUNCH2(16, 2, 8);
+  if (ws) {
+    if (blk == 64) U3D_TN_LAUNCH2(64, 2, 8, true);
+    else if (blk == 32) U3D_TN_LAUNCH2(32, 2, 8, true);
+    else U3D_TN_LAUNCH2(16, 2, 8, true);
   }
+  else if (m64) U3D_TN_LAUNCH2(64, 2, 8, false);
   else if (blk == 64) U3D_TN_LAUNCH(64);
   else if (blk == 32) U3D_TN_LAUNCH(32);
   else U3D_TN_LAUNCH(16);
