@@ -710,12 +710,13 @@ def test_spconv_x3_pointwise_identity_table():
     assert relerr(ops.merge_bf16(y2), ref) < 1e-4
 
 
-@pytest.mark.parametrize("cin,cout", [(64, 64), (32, 32), (32, 64), (16, 32)])
+@pytest.mark.parametrize("cin,cout", [(64, 64), (32, 32), (32, 64), (16, 32), (64, 128), (128, 128), (16, 16)])
 def test_spconv_switches_reverse_tiles_and_deep_ring(monkeypatch, cin, cout):
     """Instruction-form / ring variants of the rows-on-N kernel give the same result as the default launch (the
     weight-stationary `tcgen05.mma.ws` form with M = Cout for Cout = 32 / 64): reverse tile order (`reverse=True`), the
-    plain M = 64 form (U3D_TN_WS=0), the replicated M = 128 form (+ U3D_TN_M64=0) and the single-buffered-slice 4-stage
-    ring (+ U3D_TN_SLICE_BUFS=1), bf16 and the 3xBF16 fp32 form; and the default agrees with the fp32 reference."""
+    plain M = 64 form (U3D_TN_WS=0), the replicated M = 128 form (+ U3D_TN_M64=0), the single-buffered-slice 4-stage
+    ring (+ U3D_TN_SLICE_BUFS=1), per-stage rulebook rows on / off (U3D_TN_RING), bf16 and the 3xBF16 fp32 form; and
+    the default agrees with the fp32 reference."""
     from uni3detr_b200 import ops
     dims, B, n = (8, 24, 24), 2, 3000
     coors, x, w, scale, shift = conv_case(n, dims, B, cin, cout, 4242)
@@ -736,6 +737,8 @@ def test_spconv_switches_reverse_tiles_and_deep_ring(monkeypatch, cin, cout):
     assert relerr(base[0][:n], ref) < 1e-2
     assert relerr(ops.merge_bf16(base[1])[:n], ref) < 1e-4
     for name, env, kw in (("reverse", {}, dict(reverse=True)), ("m64", {"U3D_TN_WS": "0"}, {}),
+                          ("stage_rows", {"U3D_TN_RING": "1"}, {}), ("tile_slices", {"U3D_TN_RING": "0"}, {}),
+                          ("stage_rows_m64", {"U3D_TN_RING": "1", "U3D_TN_WS": "0"}, {}),
                           ("m128", {"U3D_TN_WS": "0", "U3D_TN_M64": "0"}, {}),
                           ("deep", {"U3D_TN_WS": "0", "U3D_TN_SLICE_BUFS": "1", "U3D_TN_M64": "0"}, {})):
         for k, v in env.items():

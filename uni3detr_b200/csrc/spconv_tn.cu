@@ -57,9 +57,13 @@ constexpr int kProdWarp0 = 10;
 constexpr int threads_of(int n_prod) { return (kProdWarp0 + n_prod) * 32; }   // 512 / 576
 constexpr int kMaxK = 27;
 
-// kSliceBufs: rulebook-slice buffers, 2 (default) or 1 (EXPERIMENTAL: frees 28 KB -> a 4th stage);
+// kSliceBufs: rulebook-slice buffers, 2 (whole-tile slices, double-buffered: 55 KB) or 1 (single-buffered, measured
+// slower), or 0 = STAGE ROWS: the 1 KB rulebook rows travel per gather stage - the rows of stage g (one per unit) sit
+// in slot g % (2 x stages) of a small ring with a full / empty barrier pair per slot, filled by the loader thread a
+// few stages ahead and released by the two producer warps that own the stage (10 - 20 KB instead of 55 KB, which
+// frees shared memory for one more gather stage);
 // kMaxStages: one ring slot per producer warp pair
-template <int kSliceBufs, int kMaxStages>
+template <int kSliceBufs, int kMaxStages, int kG>
 struct Smem {
   uint64_t full[kMaxStages];    // 64 cp.async arrives (the stage's two warps) + 1 arrive.expect_tx
   uint64_t empty[kMaxStages];   // tcgen05.commit: the MMAs that read the stage have retired
@@ -70,6 +74,19 @@ struct Smem {
   uint32_t tmem_base;
   alignas(128) int srow[2][kTile];   // output row of every slot of the tile in accumulator buffer ab (sorted tiles)
   alignas(128) int nbr[kSliceBufs][kMaxK][kTile];
+};
+template <int kMaxStages, int kG>
+struct Smem<0, kMaxStages, kG> {
+  static constexpr int kSlots = 2 * kMaxStages;
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint64_t slice_full[kSlots];     // rows of stage g: slot g % kSlots, generation g / kSlots
+  uint64_t slice_empty[kSlots];    // 2 arrivals: the producer warps of the stage have read their entries
+  uint32_t tmem_base;
+  alignas(128) int srow[2][kTile];
+  alignas(128) int nbr[kSlots][kG][kTile];
 };
 
 __device__ __forceinline__ uint32_t mask_of_tile(const uint32_t* __restrict__ tile_mask, int tile,
@@ -104,7 +121,9 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
   constexpr int kUnitX = kTile * SW::P;           // one 256-row feature sub-tile
   constexpr int kXBytes = kG * kUnitX;            // 32 KB for every CIN_BLK
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using SmemT = Smem<kSliceBufs, kNumProd / 2>;
+  constexpr bool kRing = kSliceBufs == 0;
+  constexpr int kSlots = kNumProd;                // stage-row slots (kRing): 2 x the ring's stages
+  using SmemT = Smem<kSliceBufs, kNumProd / 2, kG>;
   SmemT& S = *reinterpret_cast<SmemT*>(smem_raw);
   constexpr uint32_t kHeader = (uint32_t)((sizeof(SmemT) + 1023) & ~(size_t)1023);
 
@@ -153,9 +172,9 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       mbar_init(&S.acc_full[b], slot_row ? 2 : 1);   // tcgen05.commit (+ the tile's slot->row list)
       mbar_init(&S.acc_empty[b], kEpiThreads);
     }
-    for (int b = 0; b < kSliceBufs; ++b) {
+    for (int b = 0; b < (kRing ? kNumProd : kSliceBufs); ++b) {
       mbar_init(&S.slice_full[b], 1);
-      mbar_init(&S.slice_empty[b], kNumProd);
+      mbar_init(&S.slice_empty[b], kRing ? 2 : kNumProd);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -197,7 +216,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
     const uint32_t st_s = tiles_s + (uint32_t)slot * stage_bytes;
     for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++t) {
       const int tile = (flags_ & 2) ? n_tiles - 1 - tl : tl;   // bit 1: walk the tiles from the last row back (L2 reuse)
-      const int buf = t % kSliceBufs;
+      const int buf = kRing ? 0 : t % (kRing ? 1 : kSliceBufs);
       const int m0 = tile * kTile;
       const uint32_t mask = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
       const int n_units = __popc(mask) * nkb;
@@ -207,13 +226,15 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
       // then one ballot away
       const bool my_bit = (mask >> lane) & 1u;
       const int my_rank = __popc(mask & ((1u << lane) - 1u));
-      mbar_wait(&S.slice_full[buf], (uint32_t)(t / kSliceBufs) & 1u);
+      if (!kRing) mbar_wait(&S.slice_full[buf], (uint32_t)(t / (kRing ? 1 : kSliceBufs)) & 1u);
       for (; g < g0 + n_st; g += stages) {
         const int u0 = (g - g0) * kG;
         const int cnt = n_units - u0 < kG ? n_units - u0 : kG;
+        const int rs = kRing ? g % kSlots : 0;     // stage rows: slot of this stage's rulebook rows
         mbar_wait(&S.empty[slot], eph);
         eph ^= 1u;
         if (half == 0 && lane == 0) mbar_expect_tx(&S.full[slot], (uint32_t)cnt * w_unit);
+        if (kRing) mbar_wait(&S.slice_full[rs], (uint32_t)(g / kSlots) & 1u);
 #pragma unroll
         for (int j = 0; j < kG; ++j) {
           if (j < cnt) {
@@ -229,7 +250,7 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
             const uint8_t* src_base =
                 reinterpret_cast<const uint8_t*>(in) + (size_t)(src_col + chunk * 8) * 2;
             int idx[kPasses];
-            const int4* nb4 = reinterpret_cast<const int4*>(&S.nbr[buf][k][rbase]);
+            const int4* nb4 = reinterpret_cast<const int4*>(kRing ? &S.nbr[rs][j][rbase] : &S.nbr[buf][k][rbase]);
 #pragma unroll
             for (int v = 0; v < kPasses / 4; ++v) {
               const int4 q4 = nb4[v];
@@ -249,29 +270,54 @@ k_spconv_tn(const __nv_bfloat16* __restrict__ in, const int32_t* __restrict__ nb
           }
         }
         cp_async_arrive(&S.full[slot]);
+        if (kRing) {     // every lane's entries are in registers (the gathers above consumed them): free the rows
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&S.slice_empty[rs]);
+        }
       }
       g0 += n_st;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.slice_empty[buf]);
+      if (!kRing) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.slice_empty[buf]);
+      }
     }
   } else if (warp == kSliceWarp) {
     // ======================= rulebook-slice loader (one thread) =======================
     if (lane == 0) {
-      int t = 0;
+      int t = 0, g = 0;
       for (int tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++t) {
-      const int tile = (flags_ & 2) ? n_tiles - 1 - tl : tl;   // bit 1: walk the tiles from the last row back (L2 reuse)
-        const int buf = t % kSliceBufs;
-        mbar_wait_relaxed(&S.slice_empty[buf], (((uint32_t)(t / kSliceBufs)) & 1u) ^ 1u, 2000u);
+        const int tile = (flags_ & 2) ? n_tiles - 1 - tl : tl;   // bit 1: walk the tiles from the last row back (L2 reuse)
         uint32_t m = mask_of_tile(tile_mask, tile, n_tiles128, all_mask);
         int ents = nbr_stride - tile * kTile;     // the last tile of a row may hold 128 entries only
         if (ents > kTile) ents = kTile;
         const uint32_t bytes = (uint32_t)ents * 4u;
-        mbar_expect_tx(&S.slice_full[buf], (uint32_t)__popc(m) * bytes);
-        while (m) {
-          const int k = __ffs(m) - 1;
-          m &= m - 1;
-          bulk_g2s(smem_u32(&S.nbr[buf][k][0]), nbr + (size_t)k * nbr_stride + (size_t)tile * kTile, bytes,
-                   &S.slice_full[buf]);
+        if (kRing) {
+          // stage by stage, in the producers' unit order: unit u of the tile reads the row of its (u / nkb)-th
+          // active offset (a Cin = 128 layer has two units - K blocks - per offset: the row is fetched for both)
+          const int n_units = __popc(m) * nkb;
+          const int n_st = (n_units + kG - 1) / kG;
+          for (int st = 0; st < n_st; ++st, ++g) {
+            const int u0 = st * kG;
+            const int cnt = n_units - u0 < kG ? n_units - u0 : kG;
+            const int rs = g % kSlots;
+            mbar_wait_relaxed(&S.slice_empty[rs], (((uint32_t)(g / kSlots)) & 1u) ^ 1u, 500u);
+            mbar_expect_tx(&S.slice_full[rs], (uint32_t)cnt * bytes);
+            for (int j = 0; j < cnt; ++j) {
+              const int k = (int)__fns(m, 0, (u0 + j) / nkb + 1);
+              bulk_g2s(smem_u32(&S.nbr[rs][j][0]), nbr + (size_t)k * nbr_stride + (size_t)tile * kTile, bytes,
+                       &S.slice_full[rs]);
+            }
+          }
+        } else {
+          const int buf = t % (kRing ? 1 : kSliceBufs);
+          mbar_wait_relaxed(&S.slice_empty[buf], (((uint32_t)(t / (kRing ? 1 : kSliceBufs))) & 1u) ^ 1u, 2000u);
+          mbar_expect_tx(&S.slice_full[buf], (uint32_t)__popc(m) * bytes);
+          while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            bulk_g2s(smem_u32(&S.nbr[buf][k][0]), nbr + (size_t)k * nbr_stride + (size_t)tile * kTile, bytes,
+                     &S.slice_full[buf]);
+          }
         }
       }
     }
@@ -476,8 +522,24 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
   if (const char* e = getenv("U3D_TN_SLICE_BUFS")) deep = atoi(e) == 1;
   const bool wide = m64 || ws;                                 // 8 producer warps, double-buffered slices
   if (wide) deep = false;
-  const int max_stages = (deep || wide) ? 4 : 3;               // one ring slot per producer pair
-  const size_t header = ((deep ? sizeof(Smem<1, 4>) : (wide ? sizeof(Smem<2, 4>) : sizeof(Smem<2, 3>))) + 1023) & ~(size_t)1023;
+  // Per-stage rulebook rows (kSliceBufs = 0: 2 x stages slots of 64 / blk KB instead of 2 x 27 KB slices) free shared
+  // memory for one more gather stage. Measured per step (batch 32): 128->128 0.725 -> 0.672 ms (4 x 48 KB stages instead
+  // of 3), 64->64 unchanged (5 x 40 KB instead of 4: that layer moves 10 TB/s L2 -> SM, the fabric is the bound, not
+  // the ring depth), 32->32 0.635 -> 0.825 ms (two rows per stage: the single loader thread falls behind). Default:
+  // on for the 64-wide K blocks of the M = 128 form (Cout = 128 layers); U3D_TN_RING=1 / 0 forces it everywhere / off.
+  bool ring = blk == 64 && !wide;
+  if (const char* e = getenv("U3D_TN_RING")) ring = atoi(e) != 0;
+  if (deep) ring = false;
+  const size_t ring_hdr5 = blk == 64 ? sizeof(Smem<0, 5, 1>) : (blk == 32 ? sizeof(Smem<0, 5, 2>) : sizeof(Smem<0, 5, 4>));
+  const size_t ring_hdr4 = blk == 64 ? sizeof(Smem<0, 4, 1>) : (blk == 32 ? sizeof(Smem<0, 4, 2>) : sizeof(Smem<0, 4, 4>));
+  int max_stages = (deep || wide) ? 4 : 3;                     // one ring slot per producer pair
+  size_t header = ((deep ? sizeof(Smem<1, 4, 1>) : (wide ? sizeof(Smem<2, 4, 1>) : sizeof(Smem<2, 3, 1>))) + 1023) & ~(size_t)1023;
+  if (ring) {   // 5 stages (10 producer warps) when they fit next to the 5-stage header, else 4 (8 warps)
+    const size_t h5 = (ring_hdr5 + 1023) & ~(size_t)1023, h4 = (ring_hdr4 + 1023) & ~(size_t)1023;
+    const bool five = blk != 16 && h5 + 5 * (size_t)stage_bytes <= 227u * 1024u;
+    max_stages = five ? 5 : 4;
+    header = five ? h5 : h4;
+  }
   int stages = (int)((227u * 1024u - header) / stage_bytes);
   if (const char* e = getenv("U3D_TN_STAGES")) stages = atoi(e);
   if (stages > max_stages) stages = max_stages;
@@ -503,7 +565,16 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
   do {                                                                                              \
     if (deep) U3D_TN_LAUNCH2(BLK, 1, 8, false); else U3D_TN_LAUNCH2(BLK, 2, 6, false);              \
   } while (0)
-  if (ws) {
+#define U3D_TN_RING_LAUNCH(BLK, NP)                                                                 \
+  do {                                                                                              \
+    if (ws) U3D_TN_LAUNCH2(BLK, 0, NP, true); else U3D_TN_LAUNCH2(BLK, 0, NP, false);               \
+  } while (0)
+  if (ring) {
+    if (blk == 64) { if (max_stages == 5) U3D_TN_RING_LAUNCH(64, 10); else U3D_TN_RING_LAUNCH(64, 8); }
+    else if (blk == 32) { if (max_stages == 5) U3D_TN_RING_LAUNCH(32, 10); else U3D_TN_RING_LAUNCH(32, 8); }
+    else U3D_TN_RING_LAUNCH(16, 8);
+  }
+  else if (ws) {
     if (blk == 64) U3D_TN_LAUNCH2(64, 2, 8, true);
     else if (blk == 32) U3D_TN_LAUNCH2(32, 2, 8, true);
     else U3D_TN_LAUNCH2(16, 2, 8, true);
@@ -512,6 +583,7 @@ int spconv_fwd_tn_ex(const void* in, const int32_t* nbr, int nbr_stride, const u
   else if (blk == 64) U3D_TN_LAUNCH(64);
   else if (blk == 32) U3D_TN_LAUNCH(32);
   else U3D_TN_LAUNCH(16);
+#undef U3D_TN_RING_LAUNCH
 #undef U3D_TN_LAUNCH
 #undef U3D_TN_LAUNCH2
 #undef U3D_TN_LAUNCH3
