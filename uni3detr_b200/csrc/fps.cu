@@ -71,7 +71,7 @@ template <int THREADS, int PPT, int CS, bool SMEM_XYZ>
 __global__ void __launch_bounds__(THREADS, 1)
 k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
       const float* __restrict__ gather_src, int gather_stride, const int32_t* __restrict__ seg,
-      int nq, int reverse, int tie_block, int32_t* __restrict__ idx_out, float* __restrict__ out) {
+      int nq, int reverse, int tie_block, int async_msg, int32_t* __restrict__ idx_out, float* __restrict__ out) {
   constexpr int NW = THREADS / 32;
   extern __shared__ float s_dyn[];              // SMEM_XYZ: x[PPT*THREADS], y[..], z[..]
   __shared__ FpsMsg s_warp[NW];
@@ -124,8 +124,9 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
   if (tid == 0) {
     s_sel[0] = 0;
     if (CS > 1) {
+      // async_msg: one local arrive.expect_tx per phase, completed by the peers' st.async bytes; else CS remote arrives
       for (int b = 0; b < 2; ++b)
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&s_bar[b])), "r"(CS));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&s_bar[b])), "r"(async_msg ? 1 : CS));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
   }
@@ -162,6 +163,8 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
     __syncthreads();
     // 3. CTA arg-max by warp 0, then one 32-byte message to every CTA of the cluster
     const int par = it & 1;
+    if (CS > 1 && async_msg && tid == 0)   // this phase completes when the CS x 32 message bytes have landed
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fps_smem_u32(&s_bar[par])), "r"(CS * 32) : "memory");
     if (warp == 0) {
       const bool have = lane < NW;
       const uint32_t chi = have ? s_warp[lane].hi : 0u, clo = have ? s_warp[lane].lo : 0u;
@@ -177,9 +180,16 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
         uint32_t rdst, rbar;
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rdst) : "r"(fps_smem_u32(&s_slot[par][crank])), "r"(lane));
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(fps_smem_u32(&s_bar[par])), "r"(lane));
-        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rdst), "r"(m0.x), "r"(m0.y), "r"(m0.z), "r"(m0.w) : "memory");
-        asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rdst + 16), "r"(m1.x), "r"(m1.y), "r"(m1.z), "r"(m1.w) : "memory");
-        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+        if (async_msg) {
+          // st.async: the stores themselves complete the peer's mbarrier transaction count - no release fence, no
+          // separate remote arrive on the exchange's critical path
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(rdst), "r"(m0.x), "r"(m0.y), "r"(m0.z), "r"(m0.w), "r"(rbar) : "memory");
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(rdst + 16), "r"(m1.x), "r"(m1.y), "r"(m1.z), "r"(m1.w), "r"(rbar) : "memory");
+        } else {
+          asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rdst), "r"(m0.x), "r"(m0.y), "r"(m0.z), "r"(m0.w) : "memory");
+          asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rdst + 16), "r"(m1.x), "r"(m1.y), "r"(m1.z), "r"(m1.w) : "memory");
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+        }
       }
     }
     // 4. wait for the CS candidates of this iteration, resolve the winner (identical in every CTA)
@@ -187,15 +197,27 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
       __syncthreads();
     } else {
       const uint32_t parity = (uint32_t)((it - 1) >> 1) & 1u;   // each barrier is used every 2nd iteration
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "FPS_WAIT:\n\t"
-          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-          "@p bra FPS_DONE;\n\t"
-          "bra FPS_WAIT;\n\t"
-          "FPS_DONE:\n\t"
-          "}" ::"r"(fps_smem_u32(&s_bar[par])), "r"(parity) : "memory");
+      if (async_msg) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "FPS_WAITA:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra FPS_DONEA;\n\t"
+            "bra FPS_WAITA;\n\t"
+            "FPS_DONEA:\n\t"
+            "}" ::"r"(fps_smem_u32(&s_bar[par])), "r"(parity) : "memory");
+      } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "FPS_WAIT:\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra FPS_DONE;\n\t"
+            "bra FPS_WAIT;\n\t"
+            "FPS_DONE:\n\t"
+            "}" ::"r"(fps_smem_u32(&s_bar[par])), "r"(parity) : "memory");
+      }
     }
     FpsMsg w = s_slot[par][0];
 #pragma unroll
@@ -274,6 +296,8 @@ static int launch_fps(const float* dist_src, int dist_stride, int dist_seg_strid
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  int async_msg = 1;                // st.async message exchange (U3D_FPS_ASYNC=0: plain DSMEM stores + remote arrive)
+  if (const char* e = getenv("U3D_FPS_ASYNC")) async_msg = atoi(e) != 0;
   static bool configured = false;   // per template instantiation
   if (!configured) {
     if (CS > 8) U3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -282,7 +306,7 @@ static int launch_fps(const float* dist_src, int dist_stride, int dist_seg_strid
     configured = true;
   }
   U3D_CUDA(cudaLaunchKernelEx(&cfg, kern, dist_src, dist_stride, dist_seg_stride, gather_src,
-                              gather_stride, seg, nq, reverse, tie_block, idx, out));
+                              gather_stride, seg, nq, reverse, tie_block, async_msg, idx, out));
   count_launch();
   return U3D_OK;
 }
@@ -320,6 +344,15 @@ extern "C" int u3d_fps(const float* dist_src, int dist_stride, int dist_seg_stri
   U3D_FPS_CASE(256, 8, 2, false)     //   4 096
   U3D_FPS_CASE(256, 8, 4, false)     //   8 192
   U3D_FPS_CASE(256, 8, 8, false)     //  16 384
+  if (const char* e = getenv("U3D_FPS_CFG")) {   // experiments: other splits of a <= 20 480-point scene
+    const int c = atoi(e);
+    if (c == 1) { U3D_FPS_CASE(512, 10, 4, false) }
+    if (c == 2) { U3D_FPS_CASE(1024, 10, 2, false) }
+    if (c == 3) { U3D_FPS_CASE(512, 5, 8, false) }
+    if (c == 4) { U3D_FPS_CASE(128, 10, 16, false) }
+    if (c == 5) { U3D_FPS_CASE(1024, 5, 4, false) }
+    if (c == 6) { U3D_FPS_CASE(128, 20, 8, false) }
+  }
   if (getenv("U3D_FPS_FAT") != nullptr) {
     // optional: few fat CTAs (2 x 1024 threads, coordinates in shared memory): one DSMEM exchange
     // partner and only 2 SMs per scene (measured: 0.54 vs 0.34 ms per launch, same step time)

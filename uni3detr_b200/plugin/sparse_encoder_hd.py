@@ -360,8 +360,8 @@ class SparseEncoderHD(nn.Module):
         # U3D_CONV_ZIGZAG=1: every other conv walks its tiles backwards (a layer leaves its LAST rows in L2, the next
         # one would start on them). Measured neutral at batch 32 (64->64: 0.3154 vs 0.3159 ms), so off by default.
         zigzag = os.environ.get("U3D_CONV_ZIGZAG", "0") != "0"
-        rev = False
-        for st in plan["steps"]:
+        def geometry_of(st, level):
+            """(rulebook, output level) of one conv step; tables are built once per resolution."""
             sortable = (sort_tiles and (st["packed"] is not None or x3) and st["k"] == 27 and st["cout"] <= 128
                         and st["cin"] <= sort_max_cin and (st["subm"] or sort_down))
             if st["k"] == 1:
@@ -385,6 +385,23 @@ class SparseEncoderHD(nn.Module):
                 if sortable:
                     nbr = ops.rulebook_sort_tiles(nbr, on, ocap, oc, B, sort_group)
                 out_level = dict(coors=oc, n=on, cap=ocap, vmap=ovm, nbr=None, nbr_sorted=None, dims=ovm.dims)
+            return nbr, out_level
+
+        # Geometry first: every rulebook / tile sort / strided coordinate set depends on the voxel COORDINATES only,
+        # so the whole chain (4 SubM tables, 3 strided tables, the sorts) is issued before the first convolution.
+        # These are small-CTA, low-register kernels that share the SMs with the two FPS launches of the detector's
+        # side streams; the persistent conv kernels (one 55 K-register CTA per SM) cannot, and used to stall behind
+        # the FPS blocks when they were interleaved with the table builds (U3D_GEOMETRY_FIRST=0: interleaved).
+        geom = None
+        if os.environ.get("U3D_GEOMETRY_FIRST", "1") != "0":
+            geom, lv = [], level
+            for st in plan["steps"]:
+                g = geometry_of(st, lv)
+                geom.append(g)
+                lv = g[1]
+        rev = False
+        for i, st in enumerate(plan["steps"]):
+            nbr, out_level = geom[i] if geom is not None else geometry_of(st, level)
             if st["save"]:
                 saved = x
             res = saved if st["add"] else None
