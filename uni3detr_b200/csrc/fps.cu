@@ -73,6 +73,7 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
       const float* __restrict__ gather_src, int gather_stride, const int32_t* __restrict__ seg,
       int nq, int reverse, int tie_block, int async_msg, int32_t* __restrict__ idx_out, float* __restrict__ out) {
   constexpr int NW = THREADS / 32;
+  constexpr bool kSimpleTie = ((THREADS * CS) % 1024) == 0;
   extern __shared__ float s_dyn[];              // SMEM_XYZ: x[PPT*THREADS], y[..], z[..]
   __shared__ FpsMsg s_warp[NW];
   __shared__ FpsMsg s_slot[2][CS];              // written by every CTA of the cluster (DSMEM)
@@ -134,28 +135,57 @@ k_fps(const float* __restrict__ dist_src, int dist_stride, int dist_seg_stride,
   else __syncthreads();
 
   for (int it = 1; it < nq; ++it) {
-    // 1. update running distances, thread-local arg-max (ties: the smaller key)
-    float bt = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+    // 1. update running distances, thread-local arg-max. The kernel is ISSUE bound (20 k points x 300 iterations x 32
+    // scenes), so the loop carries the bare minimum: 8 FP ops + min + compare + two selects per point. A thread's
+    // points ascend in j; when THREADS * CS is a multiple of the reference block size they all share (i mod bs), so the
+    // tie key ascends with j as well and a strict '>' keeps the thread's winner (kSimpleTie; always true for plain
+    // lowest-index ties). The key itself and the coordinates are looked up afterwards, for the winner only.
+    float bt = -1.f;
+    int bj = 0;
     uint32_t bkey = 0xffffffffu;
+    if (kSimpleTie || lg < 0) {
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-      const float x = SMEM_XYZ ? sx[j * THREADS + tid] : px[j];
-      const float y = SMEM_XYZ ? sy[j * THREADS + tid] : py[j];
-      const float z = SMEM_XYZ ? sz[j * THREADS + tid] : pz[j];
-      const float dx = __fsub_rn(x, lx), dy = __fsub_rn(y, ly), dz = __fsub_rn(z, lz);
-      const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      const float t = fminf(td[j], d);
-      td[j] = t;
-      const uint32_t i = (uint32_t)((j * CS + crank) * THREADS + tid);
+      for (int j = 0; j < PPT; ++j) {
+        const float x = SMEM_XYZ ? sx[j * THREADS + tid] : px[j];
+        const float y = SMEM_XYZ ? sy[j * THREADS + tid] : py[j];
+        const float z = SMEM_XYZ ? sz[j * THREADS + tid] : pz[j];
+        const float dx = __fsub_rn(x, lx), dy = __fsub_rn(y, ly), dz = __fsub_rn(z, lz);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float t = fminf(td[j], d);
+        td[j] = t;
+        if (t > bt) { bt = t; bj = j; }
+      }
+      const uint32_t i = (uint32_t)((bj * CS + crank) * THREADS + tid);
       // padding (distance 0, i >= n) keeps a key above every real point's: it loses every tie
-      const uint32_t key = (int)i < n ? fps_key(i, lg) : (0x7f000000u | i);
-      if (t > bt || (t == bt && key < bkey)) { bt = t; bkey = key; bx = x; by = y; bz = z; }
+      bkey = (int)i < n ? fps_key(i, lg) : (0x7f000000u | i);
+    } else {
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        const float x = SMEM_XYZ ? sx[j * THREADS + tid] : px[j];
+        const float y = SMEM_XYZ ? sy[j * THREADS + tid] : py[j];
+        const float z = SMEM_XYZ ? sz[j * THREADS + tid] : pz[j];
+        const float dx = __fsub_rn(x, lx), dy = __fsub_rn(y, ly), dz = __fsub_rn(z, lz);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        const float t = fminf(td[j], d);
+        td[j] = t;
+        const uint32_t i = (uint32_t)((j * CS + crank) * THREADS + tid);
+        const uint32_t key = (int)i < n ? fps_key(i, lg) : (0x7f000000u | i);
+        if (t > bt || (t == bt && key < bkey)) { bt = t; bkey = key; bj = j; }
+      }
     }
     const uint32_t hi = __float_as_uint(bt);
     const uint32_t lo = 0xffffffffu - bkey;
     // 2. warp arg-max (2 REDUX); the winning lane publishes key + coordinates
     uint32_t whi, wlo;
     if (warp_argmax(hi, lo, whi, wlo)) {
+      float bx = 0.f, by = 0.f, bz = 0.f;
+      if (SMEM_XYZ) {
+        bx = sx[bj * THREADS + tid]; by = sy[bj * THREADS + tid]; bz = sz[bj * THREADS + tid];
+      } else {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (j == bj) { bx = px[j]; by = py[j]; bz = pz[j]; }
+      }
       FpsMsg m;
       m.hi = hi; m.lo = lo; m.x = bx; m.y = by; m.z = bz;
       s_warp[warp] = m;
