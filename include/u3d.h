@@ -167,6 +167,15 @@ int u3d_rulebook_sort_tiles_grouped(const int32_t* nbr, int nbr_stride, const in
 int u3d_rulebook_sort_tiles(const int32_t* nbr, int nbr_stride, const int32_t* n_out, int cap, int K,
                             int32_t* scratch, int32_t* slot_row, int32_t* nbr_sorted, int sorted_stride,
                             uint32_t* tile_mask_sorted, void* stream);
+/* The sorted table of a SubM level straight from the coordinates and the VoxelMap (arguments as u3d_rulebook_subm +
+ * the outputs / scratch of u3d_rulebook_sort_tiles_grouped; n_groups <= 1: one global set of buckets): the same
+ * slot_row / nbr_sorted / tile_mask_sorted as u3d_rulebook_subm followed by u3d_rulebook_sort_tiles(_grouped), without
+ * writing, re-reading and permuting the natural-order table (the signature comes from the VoxelMap occupancy words,
+ * the neighbours are looked up again per slot). */
+int u3d_rulebook_subm_sorted(const int32_t* coors, const int32_t* n_rows, int cap, const void* map,
+                             const int32_t* perm, int B, int D, int H, int W, int n_groups, int scenes_per_group,
+                             int32_t* scratch, int32_t* slot_row, int32_t* nbr_sorted, int sorted_stride,
+                             uint32_t* tile_mask_sorted, void* stream);
 
 /*
  * Convert a neighbour table to the (in,out) pair lists of spconv 1.x

@@ -540,6 +540,40 @@ def test_rulebook_sort_tiles_grouped(B, per_group):
     np.testing.assert_array_equal(srt[:, :n].cpu().numpy(), nat[:, slot_row])
 
 
+@pytest.mark.parametrize("n,cap,dims,B,per_group", [(5000, 5077, (8, 24, 24), 2, 0), (300, 300, (6, 10, 10), 1, 0),
+                                                    (1, 130, (4, 4, 4), 1, 0), (60_000, 60_000, (24, 64, 64), 2, 0),
+                                                    (9000, 9000, (8, 24, 24), 5, 2), (9000, 9100, (8, 24, 24), 3, 1)])
+def test_rulebook_subm_sorted_direct(n, cap, dims, B, per_group):
+    """The tile-sorted SubM table built straight from coordinates + VoxelMap (no natural table): slot_row is a permutation
+    bucketed by (scene group, signature), the table is the ORACLE's natural table gathered through it, tile masks are
+    the OR over 128 slots. Rows keep the reference's first-appearance order (perm != identity). Integer work: exact."""
+    from uni3detr_b200 import ops
+    coors = rand_coors(n, dims, B, n + 3)
+    if per_group:                                     # grouped buckets need scene-major rows
+        coors = coors[np.argsort(coors[:, 0], kind="stable")]
+    c = torch.cat([T(coors), torch.zeros(cap - n, 4, dtype=torch.int32)]).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, cap, B, dims)
+    srt = ops.rulebook_subm_sorted(c, n_rows, cap, vm, per_group)
+    nat = G.subm_rulebook(coors, dims)
+    slot_row = srt.slot_row[:n].cpu().numpy()
+    np.testing.assert_array_equal(np.sort(slot_row), np.arange(n))
+    mask = ((nat >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+    grp = coors[:, 0] // per_group if per_group else np.zeros(n, np.int64)
+    if per_group:
+        np.testing.assert_array_equal(grp[slot_row], grp)
+    key = grp[slot_row].astype(np.int64) * 4096 + _tile_key(mask)[slot_row]
+    assert bool((np.diff(key) >= 0).all())
+    got = srt[:, :n].cpu().numpy()
+    np.testing.assert_array_equal(got, nat[:, slot_row])
+    nt = (n + 127) // 128
+    act = np.zeros((27, nt * 128), bool)
+    act[:, :n] = got >= 0
+    want = (act.reshape(27, nt, 128).any(2).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+    tm = srt.tile_mask[:nt].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    np.testing.assert_array_equal(tm, want)
+
+
 @pytest.mark.parametrize("seq_len,n_seq", [(300, 8), (900, 2), (5, 4), (129, 1)])
 def test_mha_core_v_mn_major(seq_len, n_seq, monkeypatch):
     """U3D_MHA_VMN=1 stages V untransposed and uses an MN-major B operand for O = P V."""

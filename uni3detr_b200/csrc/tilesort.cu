@@ -246,6 +246,90 @@ k_key_scatter_seg(const int32_t* __restrict__ row_key, const int32_t* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Sorted SubM rulebook straight from the coordinates (round 2). u3d_rulebook_sort_tiles reads the natural
+// 27 x rows table twice (signature, permute) and writes it once more - 3 x 108 B per row on top of the
+// 108 B the natural build wrote. A SubM level whose convs all take the sorted table never needs the
+// natural one: pass 1 derives the signature from 9 - 12 VoxelMap occupancy words per row, the counting
+// sort yields slot_row, pass 2 looks the neighbours of row slot_row[s] up again (with ranks) and writes
+// the slot-ordered table directly: one 108 B/row write, two passes over the 16 B/row coordinates.
+
+// the 27 neighbour lookups of one SubM output row (stride 1, pad 1): emit(k, input row or -1).
+// kRanks = false: occupancy only (emit gets 0 / -1), no rank arithmetic, no perm load.
+template <bool kRanks, class Emit>
+__device__ __forceinline__ void subm_neighbours(const int4 c, const uint2* __restrict__ map,
+                                                const int32_t* __restrict__ perm, int D, int H, int W, Emit&& emit) {
+  const int z0 = c.y - 1, y0 = c.z - 1, x0 = c.w - 1;
+#pragma unroll
+  for (int kz = 0; kz < 3; ++kz) {
+    const int z = z0 + kz;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = y0 + ky;
+      const bool line_ok = z >= 0 && z < D && y >= 0 && y < H;
+      const uint32_t lin0 = line_ok ? (uint32_t)((((size_t)c.x * D + z) * H + y) * W) : 0u;
+      uint32_t cached = 0xffffffffu;
+      uint2 w = make_uint2(0u, 0u);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int x = x0 + kx;
+        int row = -1;
+        if (line_ok && x >= 0 && x < W) {
+          const uint32_t lin = lin0 + (uint32_t)x;
+          const uint32_t wi = lin >> 5, bit = lin & 31u;
+          if (wi != cached) { w = __ldg(&map[wi]); cached = wi; }
+          if ((w.x >> bit) & 1u) {
+            if (kRanks) {
+              const int rank = (int)w.y + __popc(w.x & ((1u << bit) - 1u));
+              row = perm ? __ldg(&perm[rank]) : rank;
+            } else {
+              row = 0;
+            }
+          }
+        }
+        emit((kz * 3 + ky) * 3 + kx, row);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_row_key_map(const int32_t* __restrict__ coors, const int32_t* __restrict__ n_p, const uint2* __restrict__ map,
+              int D, int H, int W, int32_t* __restrict__ row_key) {
+  const int n = *n_p;
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coors) + o);
+    uint32_t m = 0u;
+    subm_neighbours<false>(c, map, nullptr, D, H, W, [&](int k, int row) { m |= (row >= 0 ? 1u : 0u) << k; });
+    row_key[o] = (int32_t)tile_key_of_mask(m);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_nbr_build_slots(const int32_t* __restrict__ coors, const int32_t* __restrict__ n_p, const uint2* __restrict__ map,
+                  const int32_t* __restrict__ perm, int D, int H, int W, const int32_t* __restrict__ slot_row,
+                  int32_t* __restrict__ sorted, int sorted_stride, uint32_t* __restrict__ tile_mask) {
+  const int n = *n_p;
+  const int per_round = gridDim.x * blockDim.x;
+  const int nrounds = (n + per_round - 1) / per_round;   // uniform trip count: whole warps reach the reduction
+  for (int r = 0; r < nrounds; ++r) {
+    const int s = r * per_round + blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0u;
+    if (s < n) {
+      const int o = __ldg(&slot_row[s]);
+      const int4 c = __ldg(reinterpret_cast<const int4*>(coors) + o);
+      int32_t* dst = sorted + s;
+      subm_neighbours<true>(c, map, perm, D, H, W, [&](int k, int row) {
+        dst[(size_t)k * sorted_stride] = row;
+        m |= (row >= 0 ? 1u : 0u) << k;
+      });
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    if (m && (threadIdx.x & 31) == 0) atomicOr(&tile_mask[s >> 7], m);
+  }
+}
+
 }  // namespace u3d
 
 using namespace u3d;
@@ -331,6 +415,62 @@ extern "C" int u3d_rulebook_sort_tiles_grouped(const int32_t* nbr, int nbr_strid
   U3D_LAUNCH_CHECK();
   k_nbr_permute<<<g, 256, 0, st>>>(nbr, nbr_stride, slot_row, n_out, K, nbr_sorted, sorted_stride,
                                    tile_mask_sorted);
+  U3D_LAUNCH_CHECK();
+  return U3D_OK;
+}
+
+// Sorted SubM rulebook straight from the coordinates (see k_row_key_map / k_nbr_build_slots): the outputs of
+// u3d_rulebook_subm + u3d_rulebook_sort_tiles(_grouped) without the natural-order table in between.
+// n_groups <= 1: one global set of buckets; else buckets inside groups of scenes_per_group scenes.
+// scratch: u3d_tile_sort_grouped_scratch_ints(cap, max(n_groups, 1)) int32.
+extern "C" int u3d_rulebook_subm_sorted(const int32_t* coors, const int32_t* n_rows, int cap, const void* map,
+                                        const int32_t* perm, int B, int D, int H, int W, int n_groups,
+                                        int scenes_per_group, int32_t* scratch, int32_t* slot_row,
+                                        int32_t* nbr_sorted, int sorted_stride, uint32_t* tile_mask_sorted,
+                                        void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  U3D_CHECK_ARG(coors && n_rows && map && scratch && slot_row && nbr_sorted && tile_mask_sorted,
+                "u3d_rulebook_subm_sorted: null buffer");
+  U3D_CHECK_ARG(cap >= 0 && sorted_stride >= cap && B >= 1 && D >= 1 && H >= 1 && W >= 1 && n_groups <= 1024,
+                "u3d_rulebook_subm_sorted: bad shape (cap=%d stride=%d groups=%d)", cap, sorted_stride, n_groups);
+  if (cap == 0) return U3D_OK;
+  const int G = n_groups > 1 ? n_groups : 1;
+  int32_t* row_key = scratch;
+  int32_t* seg = scratch + cap;
+  int32_t* hist = seg + (G + 1);
+  int32_t* cursor = hist + (size_t)kKeyBins * G;
+  U3D_CUDA(cudaMemsetAsync(hist, 0, 2 * (size_t)kKeyBins * G * sizeof(int32_t), st));
+  U3D_CUDA(cudaMemsetAsync(tile_mask_sorted, 0, (size_t)cdiv(cap, 128) * sizeof(uint32_t), st));
+  int g = cdiv(cap, 256);
+  if (g > kNumSMs * 8) g = kNumSMs * 8;
+  k_row_key_map<<<g, 256, 0, st>>>(coors, n_rows, (const uint2*)map, D, H, W, row_key);
+  U3D_LAUNCH_CHECK();
+  if (G > 1) {
+    k_seg_bounds<<<cdiv(G + 1, 128), 128, 0, st>>>(coors, n_rows, G, scenes_per_group, seg);
+    U3D_LAUNCH_CHECK();
+    int per_group = cdiv(cdiv(cap, G), 8 * kSortThreads);
+    if (per_group < 1) per_group = 1;
+    if (per_group * G > kNumSMs * 8) per_group = cdiv(kNumSMs * 8, G);
+    dim3 gs(per_group, G);
+    k_key_hist_seg<<<gs, kSortThreads, 0, st>>>(row_key, seg, hist);
+    U3D_LAUNCH_CHECK();
+    k_key_scan_seg<<<1, 1024, 0, st>>>(hist, kKeyBins * G, cursor);
+    U3D_LAUNCH_CHECK();
+    k_key_scatter_seg<<<gs, kSortThreads, 0, st>>>(row_key, seg, cursor, slot_row);
+    U3D_LAUNCH_CHECK();
+  } else {
+    int gs = cdiv(cap, 8 * kSortThreads);
+    if (gs < 1) gs = 1;
+    if (gs > kNumSMs * 4) gs = kNumSMs * 4;
+    k_key_hist<<<gs, kSortThreads, 0, st>>>(row_key, n_rows, hist);
+    U3D_LAUNCH_CHECK();
+    k_key_scan<<<1, 1024, 0, st>>>(hist, cursor);
+    U3D_LAUNCH_CHECK();
+    k_key_scatter<<<gs, kSortThreads, 0, st>>>(row_key, n_rows, cursor, slot_row);
+    U3D_LAUNCH_CHECK();
+  }
+  k_nbr_build_slots<<<g, 256, 0, st>>>(coors, n_rows, (const uint2*)map, perm, D, H, W, slot_row, nbr_sorted,
+                                       sorted_stride, tile_mask_sorted);
   U3D_LAUNCH_CHECK();
   return U3D_OK;
 }

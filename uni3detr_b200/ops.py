@@ -297,6 +297,27 @@ def rulebook_sort_tiles(nbr, n_out, cap, coors=None, n_scenes=0, scenes_per_grou
     return srt
 
 
+@_timed(lambda r, coors, n_rows, cap, *a, **k: dict(n_out=int(n_rows)))
+def rulebook_subm_sorted(coors, n_rows, cap, vmap: VoxelMap, scenes_per_group=0):
+    """The tile-sorted SubM Rulebook (as rulebook_sort_tiles(rulebook_subm(...))) built straight from the coordinates
+    and the VoxelMap, without the natural-order table (csrc/tilesort.cu: u3d_rulebook_subm_sorted)."""
+    lib = _lib.load()
+    _req(coors, torch.int32, "coors")
+    cap = max(int(cap), 1)
+    dev = coors.device
+    pad = (cap + 255) // 256 * 256
+    srt = torch.empty((27, pad), dtype=torch.int32, device=dev)[:, :cap].as_subclass(Rulebook)
+    srt.tile_mask = torch.empty(pad // 128, dtype=torch.int32, device=dev)
+    srt.slot_row = torch.empty(pad, dtype=torch.int32, device=dev)
+    G = (int(vmap.B) + int(scenes_per_group) - 1) // int(scenes_per_group) if scenes_per_group else 1
+    scratch = torch.empty(lib.u3d_tile_sort_grouped_scratch_ints(cap, max(G, 1)), dtype=torch.int32, device=dev)
+    D, H, W = vmap.dims
+    _lib.check(lib.u3d_rulebook_subm_sorted(_p(coors), _p(n_rows), cap, _p(vmap.words), _p(vmap.perm), vmap.B, D, H, W,
+                                            G, int(scenes_per_group), _p(scratch), _p(srt.slot_row), _p(srt),
+                                            srt.stride(0), _p(srt.tile_mask), _stream()))
+    return srt
+
+
 def rulebook_pairs(nbr, n_out):
     """spconv-1.x style (indice_pairs (2,K,N), indice_num (K)) from a neighbour table."""
     lib = _lib.load()

@@ -339,17 +339,20 @@ class SparseEncoderHD(nn.Module):
         dims = tuple(self.sparse_shape)
         level = dict(coors=coors, n=n_rows, cap=cap, vmap=vmap, nbr=None, nbr_sorted=None, dims=dims)
         saved = None
-        # tile scheduling (csrc/tilesort.cu): the rows-on-N tensor-core kernel takes rulebooks whose
-        # 256-slot tiles group rows with similar neighbour masks. It pays where tile padding dominates
-        # (thin layers: 6-35 % useful slots in natural order) and loses on the 64/128-channel levels at
-        # batch 32, whose feature matrices no longer fit L2 once the gathers lose their spatial order
-        # (measured per launch: 64->64 0.348 -> 0.404 ms, 32->32 0.328 -> 0.211 ms, 16->16 0.131 -> 0.075 ms;
-        # a sort costs ~0.1-0.2 ms, so it is spent on the SubM levels whose table serves 4-5 convs, not on
-        # the single-use strided tables: 1889 scenes/s vs 1885 with them, 1866 for Cin <= 16 only, 1860 for
-        # everything, 1844 unsorted). U3D_SORT_TILES=0 keeps the natural order everywhere;
-        # U3D_SORT_MAX_CIN / U3D_SORT_DOWN tune the policy.
+        # tile scheduling (csrc/tilesort.cu): the rows-on-N tensor-core kernel takes rulebooks whose 256-slot tiles
+        # group rows with similar neighbour masks, so that a tile multiplies (and gathers, and fetches weight images
+        # for) few offsets that feed none of its rows: useful slots 6-72 % in natural order, 45-91 % sorted.
+        # Round 1 sorted only the thin levels (Cin <= 32): on the 64 / 128-channel levels the lost spatial order of
+        # the gathers cost more L2 misses than the padding saved, and a sort cost 0.17 ms per level. Round 2: the
+        # sorted table of a SubM level is built straight from the coordinates (ops.rulebook_subm_sorted: no natural
+        # table, no permute pass) and the weight-stationary MMA form made the padded units cheaper than the fabric
+        # traffic they cause, so every SubM level is sorted (measured per step at batch 32, same box: Cin <= 32 only
+        # 15.60 ms; + the 64-channel level 15.47 (64->64 1.12 -> 0.89 ms); + the 128-channel level 15.28 (128->128
+        # 0.66 -> 0.57); groups of 8 / 16 scenes 15.3 - 15.4; + the single-use strided tables 15.4 - 15.7).
+        # U3D_SORT_TILES=0 keeps the natural order everywhere; U3D_SORT_MAX_CIN / U3D_SORT_DOWN / U3D_SORT_GROUP /
+        # U3D_SORT_FUSED tune the policy.
         sort_tiles = (os.environ.get("U3D_SORT_TILES", "1") != "0" and os.environ.get("U3D_TC_KERNEL") != "1")
-        sort_max_cin = int(os.environ.get("U3D_SORT_MAX_CIN", "32"))
+        sort_max_cin = int(os.environ.get("U3D_SORT_MAX_CIN", "128"))
         sort_down = os.environ.get("U3D_SORT_DOWN", "0") != "0"
         # U3D_SORT_GROUP=g keeps the buckets inside groups of g scenes (measured: 64->64 1.33 -> 1.04 ms per step when
         # that level is sorted in groups of 4, paid back by the +0.29 ms of its sort; neutral on the default policy).
@@ -357,6 +360,7 @@ class SparseEncoderHD(nn.Module):
         # ahead of the convolutions - they depend on coordinates only, but next to a persistent conv grid the
         # table kernels get a sliver of each SM and the convs end up waiting for them.
         sort_group = int(os.environ.get("U3D_SORT_GROUP", "0"))
+        sort_fused = os.environ.get("U3D_SORT_FUSED", "1") != "0"   # sorted SubM tables straight from the coordinates
         # U3D_CONV_ZIGZAG=1: every other conv walks its tiles backwards (a layer leaves its LAST rows in L2, the next
         # one would start on them). Measured neutral at batch 32 (64->64: 0.3154 vs 0.3159 ms), so off by default.
         zigzag = os.environ.get("U3D_CONV_ZIGZAG", "0") != "0"
@@ -371,12 +375,18 @@ class SparseEncoderHD(nn.Module):
                         level["ident"] = ops.identity_rulebook(level["cap"], x.device)
                     nbr = level["ident"]
             elif st["subm"]:
-                if level["nbr"] is None:
-                    level["nbr"] = ops.rulebook_subm(level["coors"], level["n"], level["cap"],
-                                                     level["vmap"])
                 if sortable and level["nbr_sorted"] is None:
-                    level["nbr_sorted"] = ops.rulebook_sort_tiles(level["nbr"], level["n"], level["cap"],
-                                                                  level["coors"], B, sort_group)
+                    if level["nbr"] is None and sort_fused:
+                        # slot-ordered table straight from the coordinates: no natural table to write, re-read, permute
+                        level["nbr_sorted"] = ops.rulebook_subm_sorted(level["coors"], level["n"], level["cap"],
+                                                                       level["vmap"], sort_group)
+                    else:
+                        if level["nbr"] is None:
+                            level["nbr"] = ops.rulebook_subm(level["coors"], level["n"], level["cap"], level["vmap"])
+                        level["nbr_sorted"] = ops.rulebook_sort_tiles(level["nbr"], level["n"], level["cap"],
+                                                                      level["coors"], B, sort_group)
+                if not sortable and level["nbr"] is None:
+                    level["nbr"] = ops.rulebook_subm(level["coors"], level["n"], level["cap"], level["vmap"])
                 nbr, out_level = (level["nbr_sorted"] if sortable else level["nbr"]), level
             else:
                 oc, on, ovm, nbr, ocap = ops.rulebook_down(level["coors"], level["n"],
