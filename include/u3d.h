@@ -176,6 +176,13 @@ int u3d_rulebook_subm_sorted(const int32_t* coors, const int32_t* n_rows, int ca
                              const int32_t* perm, int B, int D, int H, int W, int n_groups, int scenes_per_group,
                              int32_t* scratch, int32_t* slot_row, int32_t* nbr_sorted, int sorted_stride,
                              uint32_t* tile_mask_sorted, void* stream);
+/* The same for a strided SparseConv3d: out_coors / n_out from u3d_rulebook_down (which skips its natural-order table
+ * when called with nbr = NULL), in_map / in_perm / in_dims of the INPUT level, stride / pad (3) of the conv. */
+int u3d_rulebook_down_sorted(const int32_t* out_coors, const int32_t* n_out, int out_cap, const void* in_map,
+                             const int32_t* in_perm, int B, const int32_t* in_dims, const int32_t* stride,
+                             const int32_t* pad, int n_groups, int scenes_per_group, int32_t* scratch,
+                             int32_t* slot_row, int32_t* nbr_sorted, int sorted_stride, uint32_t* tile_mask_sorted,
+                             void* stream);
 
 /*
  * Convert a neighbour table to the (in,out) pair lists of spconv 1.x

@@ -574,6 +574,38 @@ def test_rulebook_subm_sorted_direct(n, cap, dims, B, per_group):
     np.testing.assert_array_equal(tm, want)
 
 
+@pytest.mark.parametrize("n,dims,B,stride,pad,per_group", [(6000, (9, 24, 24), 2, (2, 2, 2), (1, 1, 1), 0),
+                                                           (4000, (8, 20, 20), 3, (2, 2, 2), (0, 1, 1), 2),
+                                                           (50, (5, 6, 6), 1, (1, 2, 2), (1, 1, 1), 0)])
+def test_rulebook_down_sorted_direct(n, dims, B, stride, pad, per_group):
+    """Strided conv: the tile-sorted table built straight from the emitted output coordinates equals the oracle's
+    table gathered through slot_row; output coordinates / count as in the natural-order call. Exact."""
+    from uni3detr_b200 import ops
+    coors = rand_coors(n, dims, B, n + 11)
+    c = T(coors).to(DEV)
+    n_rows = torch.tensor([n], dtype=torch.int32, device=DEV)
+    vm = ops.voxmap_build(c, n_rows, n, B, dims)
+    oc, on, ovm, srt, ocap = ops.rulebook_down(c, n_rows, n, vm, stride, pad, sorted_group=per_group)
+    oc0, on0, _, nat_t, _ = ops.rulebook_down(c, n_rows, n, vm, stride, pad)
+    m = int(on)
+    assert m == int(on0) and torch.equal(oc[:m], oc0[:m])
+    ref_coors, ref_nbr, _ = G.down_rulebook(coors, dims, stride, pad)
+    np.testing.assert_array_equal(oc[:m].cpu().numpy(), ref_coors)
+    slot_row = srt.slot_row[:m].cpu().numpy()
+    np.testing.assert_array_equal(np.sort(slot_row), np.arange(m))
+    np.testing.assert_array_equal(srt[:, :m].cpu().numpy(), ref_nbr[:, slot_row])
+    np.testing.assert_array_equal(nat_t[:, :m].cpu().numpy(), ref_nbr)
+    mask = ((ref_nbr >= 0).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+    grp = ref_coors[:, 0] // per_group if per_group else np.zeros(m, np.int64)
+    key = grp[slot_row].astype(np.int64) * 4096 + _tile_key(mask)[slot_row]
+    assert bool((np.diff(key) >= 0).all())
+    nt = (m + 127) // 128
+    act = np.zeros((27, nt * 128), bool)
+    act[:, :m] = srt[:, :m].cpu().numpy() >= 0
+    want = (act.reshape(27, nt, 128).any(2).astype(np.int64) << np.arange(27)[:, None]).sum(0)
+    np.testing.assert_array_equal(srt.tile_mask[:nt].cpu().numpy().astype(np.int64) & 0xFFFFFFFF, want)
+
+
 @pytest.mark.parametrize("seq_len,n_seq", [(300, 8), (900, 2), (5, 4), (129, 1)])
 def test_mha_core_v_mn_major(seq_len, n_seq, monkeypatch):
     """U3D_MHA_VMN=1 stages V untransposed and uses an MN-major B operand for O = P V."""

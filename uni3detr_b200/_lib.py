@@ -115,6 +115,8 @@ SIGNATURES = {
     "u3d_tile_sort_grouped_scratch_ints": (_sz, [_i32, _i32]),
     "u3d_rulebook_subm_sorted": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32,
                                  _vp, _vp]),
+    "u3d_rulebook_down_sorted": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32,
+                                 _vp, _vp]),
     "u3d_rulebook_sort_tiles_grouped": (_i32, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i32,
                                                _vp, _vp]),
     "u3d_rulebook_sort_tiles": (_i32, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -264,9 +264,9 @@ extern "C" int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, i
                                  int out_cap, int32_t* nbr, int nbr_stride, uint32_t* tile_mask,
                                  void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  U3D_CHECK_ARG(in_coors && n_in && in_map && out_map_ && scan_scratch && out_coors && n_out && nbr,
+  U3D_CHECK_ARG(in_coors && n_in && in_map && out_map_ && scan_scratch && out_coors && n_out,
                 "u3d_rulebook_down: null buffer");
-  U3D_CHECK_ARG(nbr_stride >= out_cap, "u3d_rulebook_down: nbr_stride < out_cap");
+  U3D_CHECK_ARG(nbr == nullptr || nbr_stride >= out_cap, "u3d_rulebook_down: nbr_stride < out_cap");
   Dims3 id{{in_dims[0], in_dims[1], in_dims[2]}}, od{{out_dims[0], out_dims[1], out_dims[2]}};
   Dims3 s{{stride[0], stride[1], stride[2]}}, p{{pad[0], pad[1], pad[2]}};
   for (int i = 0; i < 3; ++i) {
@@ -287,6 +287,7 @@ extern "C" int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, i
   k_map_emit_coors<<<grid_x_for((long long)words, 256, kNumSMs * 8), 256, 0, st>>>(
       out_map, words, od.d[0], od.d[1], od.d[2], out_coors, out_cap);
   U3D_LAUNCH_CHECK();
+  if (nbr == nullptr) return U3D_OK;      // output set only: the caller builds a slot-ordered table (u3d_rulebook_down_sorted)
   if (tile_mask) U3D_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)cdiv(out_cap > 0 ? out_cap : 1, 128) * 4, st));
   const int gn = grid_x_for(out_cap, 256, kNumSMs * 8);
   k_nbr_build<<<gn, 256, 0, st>>>(out_coors, n_out, (const uint2*)in_map, in_perm, id, s, p, nbr,

@@ -255,12 +255,16 @@ k_key_scatter_seg(const int32_t* __restrict__ row_key, const int32_t* __restrict
 // sort yields slot_row, pass 2 looks the neighbours of row slot_row[s] up again (with ranks) and writes
 // the slot-ordered table directly: one 108 B/row write, two passes over the 16 B/row coordinates.
 
-// the 27 neighbour lookups of one SubM output row (stride 1, pad 1): emit(k, input row or -1).
+// the 27 neighbour lookups of one output row (SubM: stride 1, pad 1, the level's own map; strided conv: the input
+// level's map): emit(k, input row or -1).
 // kRanks = false: occupancy only (emit gets 0 / -1), no rank arithmetic, no perm load.
+struct ConvGeo { int D, H, W, sz, sy, sx, pz, py, px; };   // input grid, stride, padding (3x3x3 kernel)
+
 template <bool kRanks, class Emit>
 __device__ __forceinline__ void subm_neighbours(const int4 c, const uint2* __restrict__ map,
-                                                const int32_t* __restrict__ perm, int D, int H, int W, Emit&& emit) {
-  const int z0 = c.y - 1, y0 = c.z - 1, x0 = c.w - 1;
+                                                const int32_t* __restrict__ perm, const ConvGeo g, Emit&& emit) {
+  const int D = g.D, H = g.H, W = g.W;
+  const int z0 = c.y * g.sz - g.pz, y0 = c.z * g.sy - g.py, x0 = c.w * g.sx - g.px;
 #pragma unroll
   for (int kz = 0; kz < 3; ++kz) {
     const int z = z0 + kz;
@@ -296,19 +300,19 @@ __device__ __forceinline__ void subm_neighbours(const int4 c, const uint2* __res
 
 __global__ void __launch_bounds__(256)
 k_row_key_map(const int32_t* __restrict__ coors, const int32_t* __restrict__ n_p, const uint2* __restrict__ map,
-              int D, int H, int W, int32_t* __restrict__ row_key) {
+              const ConvGeo geo, int32_t* __restrict__ row_key) {
   const int n = *n_p;
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
     const int4 c = __ldg(reinterpret_cast<const int4*>(coors) + o);
     uint32_t m = 0u;
-    subm_neighbours<false>(c, map, nullptr, D, H, W, [&](int k, int row) { m |= (row >= 0 ? 1u : 0u) << k; });
+    subm_neighbours<false>(c, map, nullptr, geo, [&](int k, int row) { m |= (row >= 0 ? 1u : 0u) << k; });
     row_key[o] = (int32_t)tile_key_of_mask(m);
   }
 }
 
 __global__ void __launch_bounds__(256)
 k_nbr_build_slots(const int32_t* __restrict__ coors, const int32_t* __restrict__ n_p, const uint2* __restrict__ map,
-                  const int32_t* __restrict__ perm, int D, int H, int W, const int32_t* __restrict__ slot_row,
+                  const int32_t* __restrict__ perm, const ConvGeo geo, const int32_t* __restrict__ slot_row,
                   int32_t* __restrict__ sorted, int sorted_stride, uint32_t* __restrict__ tile_mask) {
   const int n = *n_p;
   const int per_round = gridDim.x * blockDim.x;
@@ -320,7 +324,7 @@ k_nbr_build_slots(const int32_t* __restrict__ coors, const int32_t* __restrict__
       const int o = __ldg(&slot_row[s]);
       const int4 c = __ldg(reinterpret_cast<const int4*>(coors) + o);
       int32_t* dst = sorted + s;
-      subm_neighbours<true>(c, map, perm, D, H, W, [&](int k, int row) {
+      subm_neighbours<true>(c, map, perm, geo, [&](int k, int row) {
         dst[(size_t)k * sorted_stride] = row;
         m |= (row >= 0 ? 1u : 0u) << k;
       });
@@ -423,16 +427,10 @@ extern "C" int u3d_rulebook_sort_tiles_grouped(const int32_t* nbr, int nbr_strid
 // u3d_rulebook_subm + u3d_rulebook_sort_tiles(_grouped) without the natural-order table in between.
 // n_groups <= 1: one global set of buckets; else buckets inside groups of scenes_per_group scenes.
 // scratch: u3d_tile_sort_grouped_scratch_ints(cap, max(n_groups, 1)) int32.
-extern "C" int u3d_rulebook_subm_sorted(const int32_t* coors, const int32_t* n_rows, int cap, const void* map,
-                                        const int32_t* perm, int B, int D, int H, int W, int n_groups,
-                                        int scenes_per_group, int32_t* scratch, int32_t* slot_row,
-                                        int32_t* nbr_sorted, int sorted_stride, uint32_t* tile_mask_sorted,
-                                        void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  U3D_CHECK_ARG(coors && n_rows && map && scratch && slot_row && nbr_sorted && tile_mask_sorted,
-                "u3d_rulebook_subm_sorted: null buffer");
-  U3D_CHECK_ARG(cap >= 0 && sorted_stride >= cap && B >= 1 && D >= 1 && H >= 1 && W >= 1 && n_groups <= 1024,
-                "u3d_rulebook_subm_sorted: bad shape (cap=%d stride=%d groups=%d)", cap, sorted_stride, n_groups);
+static int sorted_from_coords(const int32_t* coors, const int32_t* n_rows, int cap, const void* map, const int32_t* perm,
+                              const ConvGeo geo, int n_groups, int scenes_per_group, int32_t* scratch,
+                              int32_t* slot_row, int32_t* nbr_sorted, int sorted_stride, uint32_t* tile_mask_sorted,
+                              cudaStream_t st) {
   if (cap == 0) return U3D_OK;
   const int G = n_groups > 1 ? n_groups : 1;
   int32_t* row_key = scratch;
@@ -443,7 +441,7 @@ extern "C" int u3d_rulebook_subm_sorted(const int32_t* coors, const int32_t* n_r
   U3D_CUDA(cudaMemsetAsync(tile_mask_sorted, 0, (size_t)cdiv(cap, 128) * sizeof(uint32_t), st));
   int g = cdiv(cap, 256);
   if (g > kNumSMs * 8) g = kNumSMs * 8;
-  k_row_key_map<<<g, 256, 0, st>>>(coors, n_rows, (const uint2*)map, D, H, W, row_key);
+  k_row_key_map<<<g, 256, 0, st>>>(coors, n_rows, (const uint2*)map, geo, row_key);
   U3D_LAUNCH_CHECK();
   if (G > 1) {
     k_seg_bounds<<<cdiv(G + 1, 128), 128, 0, st>>>(coors, n_rows, G, scenes_per_group, seg);
@@ -469,8 +467,38 @@ extern "C" int u3d_rulebook_subm_sorted(const int32_t* coors, const int32_t* n_r
     k_key_scatter<<<gs, kSortThreads, 0, st>>>(row_key, n_rows, cursor, slot_row);
     U3D_LAUNCH_CHECK();
   }
-  k_nbr_build_slots<<<g, 256, 0, st>>>(coors, n_rows, (const uint2*)map, perm, D, H, W, slot_row, nbr_sorted,
-                                       sorted_stride, tile_mask_sorted);
+  k_nbr_build_slots<<<g, 256, 0, st>>>(coors, n_rows, (const uint2*)map, perm, geo, slot_row, nbr_sorted, sorted_stride,
+                                       tile_mask_sorted);
   U3D_LAUNCH_CHECK();
   return U3D_OK;
+}
+
+extern "C" int u3d_rulebook_subm_sorted(const int32_t* coors, const int32_t* n_rows, int cap, const void* map,
+                                        const int32_t* perm, int B, int D, int H, int W, int n_groups,
+                                        int scenes_per_group, int32_t* scratch, int32_t* slot_row,
+                                        int32_t* nbr_sorted, int sorted_stride, uint32_t* tile_mask_sorted,
+                                        void* stream) {
+  U3D_CHECK_ARG(coors && n_rows && map && scratch && slot_row && nbr_sorted && tile_mask_sorted,
+                "u3d_rulebook_subm_sorted: null buffer");
+  U3D_CHECK_ARG(cap >= 0 && sorted_stride >= cap && B >= 1 && D >= 1 && H >= 1 && W >= 1 && n_groups <= 1024,
+                "u3d_rulebook_subm_sorted: bad shape (cap=%d stride=%d groups=%d)", cap, sorted_stride, n_groups);
+  const ConvGeo geo{D, H, W, 1, 1, 1, 1, 1, 1};
+  return sorted_from_coords(coors, n_rows, cap, map, perm, geo, n_groups, scenes_per_group, scratch, slot_row, nbr_sorted,
+                            sorted_stride, tile_mask_sorted, (cudaStream_t)stream);
+}
+
+// The same for the table of a strided SparseConv3d: out_coors / n_out are the output rows u3d_rulebook_down emitted
+// (call it with nbr = NULL to skip its natural-order table), in_map / in_perm / in_dims describe the INPUT level.
+extern "C" int u3d_rulebook_down_sorted(const int32_t* out_coors, const int32_t* n_out, int out_cap, const void* in_map,
+                                        const int32_t* in_perm, int B, const int32_t* in_dims, const int32_t* stride,
+                                        const int32_t* pad, int n_groups, int scenes_per_group, int32_t* scratch,
+                                        int32_t* slot_row, int32_t* nbr_sorted, int sorted_stride,
+                                        uint32_t* tile_mask_sorted, void* stream) {
+  U3D_CHECK_ARG(out_coors && n_out && in_map && in_dims && stride && pad && scratch && slot_row && nbr_sorted &&
+                    tile_mask_sorted, "u3d_rulebook_down_sorted: null buffer");
+  U3D_CHECK_ARG(out_cap >= 0 && sorted_stride >= out_cap && B >= 1 && n_groups <= 1024,
+                "u3d_rulebook_down_sorted: bad shape (cap=%d stride=%d groups=%d)", out_cap, sorted_stride, n_groups);
+  const ConvGeo geo{in_dims[0], in_dims[1], in_dims[2], stride[0], stride[1], stride[2], pad[0], pad[1], pad[2]};
+  return sorted_from_coords(out_coors, n_out, out_cap, in_map, in_perm, geo, n_groups, scenes_per_group, scratch,
+                            slot_row, nbr_sorted, sorted_stride, tile_mask_sorted, (cudaStream_t)stream);
 }

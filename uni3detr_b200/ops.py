@@ -241,7 +241,10 @@ def conv_out_dims(in_dims, stride, pad, k=3):
 
 @_timed(lambda r, coors, n_rows, *a, **k: dict(n_in=int(n_rows), n_out=int(r[1]),
                                                pairs=_live_pairs(r[3], r[1])))
-def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=None):
+def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=None, sorted_group=None):
+    """Strided SparseConv3d geometry: (out_coors, n_out, out VoxelMap, Rulebook, out_cap). sorted_group = None: the
+    natural-order table; an int g >= 0: the tile-sorted table built straight from the output coordinates
+    (u3d_rulebook_down_sorted; buckets inside groups of g scenes when g > 0), no natural table."""
     lib = _lib.load()
     _req(coors, torch.int32, "coors")
     dev = coors.device
@@ -255,16 +258,31 @@ def rulebook_down(coors, n_rows, in_cap, vmap: VoxelMap, stride, pad, out_cap=No
     scratch = _scan_scratch(words, dev)
     out_coors = torch.empty((out_cap, 4), dtype=torch.int32, device=dev)
     n_out = torch.empty(1, dtype=torch.int32, device=dev)
-    nbr = Rulebook.alloc(out_cap, dev)
     a1, p1 = _iarr(in_dims)
     a2, p2 = _iarr(out_dims)
     a3, p3 = _iarr(stride)
     a4, p4 = _iarr(pad)
+    if sorted_group is None:
+        nbr = Rulebook.alloc(out_cap, dev)
+        _lib.check(lib.u3d_rulebook_down(_p(coors), _p(n_rows), in_cap, _p(vmap.words), _p(vmap.perm),
+                                         vmap.B, p1, p2, p3, p4, _p(out_vm), _p(scratch), _p(out_coors),
+                                         _p(n_out), out_cap, _p(nbr), nbr.stride(0), _p(nbr.tile_mask),
+                                         _stream()))
+        return out_coors, n_out, VoxelMap(out_vm, None, vmap.B, out_dims), nbr, out_cap
     _lib.check(lib.u3d_rulebook_down(_p(coors), _p(n_rows), in_cap, _p(vmap.words), _p(vmap.perm),
                                      vmap.B, p1, p2, p3, p4, _p(out_vm), _p(scratch), _p(out_coors),
-                                     _p(n_out), out_cap, _p(nbr), nbr.stride(0), _p(nbr.tile_mask),
-                                     _stream()))
-    return out_coors, n_out, VoxelMap(out_vm, None, vmap.B, out_dims), nbr, out_cap
+                                     _p(n_out), out_cap, None, 0, None, _stream()))
+    pad256 = (out_cap + 255) // 256 * 256
+    srt = torch.empty((27, pad256), dtype=torch.int32, device=dev)[:, :out_cap].as_subclass(Rulebook)
+    srt.tile_mask = torch.empty(pad256 // 128, dtype=torch.int32, device=dev)
+    srt.slot_row = torch.empty(pad256, dtype=torch.int32, device=dev)
+    spg = int(sorted_group)
+    G = (int(vmap.B) + spg - 1) // spg if spg else 1
+    sscr = torch.empty(lib.u3d_tile_sort_grouped_scratch_ints(out_cap, max(G, 1)), dtype=torch.int32, device=dev)
+    _lib.check(lib.u3d_rulebook_down_sorted(_p(out_coors), _p(n_out), out_cap, _p(vmap.words), _p(vmap.perm), vmap.B,
+                                            p1, p3, p4, G, spg, _p(sscr), _p(srt.slot_row), _p(srt), srt.stride(0),
+                                            _p(srt.tile_mask), _stream()))
+    return out_coors, n_out, VoxelMap(out_vm, None, vmap.B, out_dims), srt, out_cap
 
 
 @_timed(lambda r, nbr, n_out, cap, *a, **k: dict(n_out=int(n_out)))

@@ -391,8 +391,9 @@ class SparseEncoderHD(nn.Module):
             else:
                 oc, on, ovm, nbr, ocap = ops.rulebook_down(level["coors"], level["n"],
                                                            level["cap"], level["vmap"],
-                                                           st["stride"], st["pad"])
-                if sortable:
+                                                           st["stride"], st["pad"],
+                                                           sorted_group=sort_group if (sortable and sort_fused) else None)
+                if sortable and not sort_fused:
                     nbr = ops.rulebook_sort_tiles(nbr, on, ocap, oc, B, sort_group)
                 out_level = dict(coors=oc, n=on, cap=ocap, vmap=ovm, nbr=None, nbr_sorted=None, dims=ovm.dims)
             return nbr, out_level
