@@ -101,6 +101,26 @@ def test_sunrgbd_full_forward_fp32_and_bf16():
         assert p99 < lim[0] and p999 < lim[1], (n, p99, p999)
 
 
+@pytest.mark.parametrize("env", [{"U3D_SORT_TILES": "0"}, {"U3D_SORT_MAX_CIN": "32"}, {"U3D_SORT_FUSED": "0"},
+                                 {"U3D_SORT_DOWN": "1"}, {"U3D_SORT_GROUP": "1"},
+                                 {"U3D_TN_WS": "0"}, {"U3D_TN_RING": "0"}, {"U3D_GEOMETRY_FIRST": "0"}])
+def test_encoder_schedule_switches_are_bit_identical(env, monkeypatch):
+    """Tile sorting (which levels, fused or via the natural table, grouped, strided tables too), the MMA instruction
+    form and the rulebook staging are pure scheduling: the bf16 encoder output of a two-scene SUN RGB-D batch is
+    bit-identical to the default's under every switch (every row keeps its accumulation order over the offsets)."""
+    from uni3detr_b200 import synth
+    model, _ = build("sunrgbd")
+    scenes = [synth.make_scene("sunrgbd", 0), synth.make_scene("sunrgbd", 1, n_points=12000)]
+    rp = torch.rand(2, 300, 3, generator=torch.Generator().manual_seed(5))
+    _, _, cap = run_product(model, scenes, rp, torch.bfloat16)
+    base = cap["encoder"].clone()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _, _, cap = run_product(model, scenes, rp, torch.bfloat16)
+    # up to the sign of an exact zero (a padded slot adds +0.0 where the natural order adds nothing)
+    assert torch.equal(cap["encoder"].float() + 0.0, base.float() + 0.0)
+
+
 @pytest.mark.parametrize("workload,npts", [("scannet_large", 6000), ("kitti", 6000), ("nuscenes", 8000)])
 def test_other_configs_encoder_and_decoder_fp32(workload, npts):
     """Configs 3-5 at reduced point counts (the oracle's dense CNN at these grids is minutes of CPU):
