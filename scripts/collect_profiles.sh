@@ -13,3 +13,5 @@ python scripts/make_traffic.py gpurun_out/ncu_kernels.csv $C > profiles/traffic.
 python scripts/summarize_ncu_full.py gpurun_out/ncu_spconv_tn64_r2.ncu-rep "k_spconv_tn: the four 64->64 launches (tcgen05.mma.ws, M = 64), 64->128 and the four 128->128 launches of one forward" > profiles/r02_ncu_spconv_tn64.md
 python scripts/summarize_ncu_full.py gpurun_out/ncu_linear_r2.ncu-rep "k_linear_tc: twelve launches of the decoder" > profiles/r02_ncu_linear.md
 python scripts/summarize_ncu_full.py gpurun_out/ncu_mha_r2.ncu-rep "k_mha_tc2: the three self-attention launches" > profiles/r02_ncu_mha.md
+[ -s gpurun_out/bench_linear.txt ] && cp gpurun_out/bench_linear.txt profiles/r02_linear_ab.txt
+[ -s gpurun_out/bench_mha.txt ] && cp gpurun_out/bench_mha.txt profiles/r02_mha_ab.txt

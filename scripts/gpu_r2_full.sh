@@ -13,4 +13,6 @@ timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_final.json 
 cut -c1-200 gpurun_out/bench_final.json
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 cut -c1-300 gpurun_out/bench_ref.json
+timeout 200 python scripts/bench_linear.py > gpurun_out/bench_linear.txt 2>&1; head -3 gpurun_out/bench_linear.txt | cut -c1-120
+timeout 200 python scripts/bench_mha.py > gpurun_out/bench_mha.txt 2>&1; head -4 gpurun_out/bench_mha.txt | cut -c1-120
 bash scripts/gpu_profiles_r2.sh
