@@ -276,10 +276,16 @@ def test_bench_roofline_arithmetic():
         "            bytes_per_launch=350e6, flops_per_launch=126e9)\n"
         "thin = dict(kernel='spconv_tc[27x16->16]', tflops=7.0, gbs=650.0, avg_launch_ms=0.07,\n"
         "            bytes_per_launch=48e6, flops_per_launch=0.55e9)\n"
-        "b.emit([b.roofline_of(conv, peaks), b.roofline_of(thin, peaks)])\n") % os.path.join(ROOT, "bench.py")
+        "fps = dict(kernel='fps[n<=20000,nq=300]', ms_per_step=0.9)\n"
+        "recs = [fps, dict(conv, ms_per_step=0.88), dict(thin, ms_per_step=0.3), dict(kernel='linear_tc[256->256]', ms_per_step=0.86)]\n"
+        "dom, ms = b.dominant_kernel(recs)\n"
+        "b.emit([b.roofline_of(conv, peaks), b.roofline_of(thin, peaks), dom['kernel'], ms])\n") % os.path.join(ROOT, "bench.py")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-800:]
-    conv, thin = json.loads(r.stdout.strip().splitlines()[-1])
+    conv, thin, dom, dom_ms = json.loads(r.stdout.strip().splitlines()[-1])
+    # the dominant kernel is the FUNCTION with the largest summed time (two conv shapes: 1.18 ms > fps 0.9), reported
+    # for its heaviest shape
+    assert dom == "spconv_tc[27x64->64]" and abs(dom_ms - 1.18) < 1e-9
     assert conv["bound"] == "tensor" and conv["peak"] == 1600.0 and abs(conv["frac"] - 0.25) < 1e-9
     assert abs(conv["frac_of_sustained_peak"] - 400.0 / 1400.0) < 1e-9 and conv["unit"] == "TFLOP/s"
     assert thin["bound"] == "hbm" and thin["peak"] == 6000.0 and abs(thin["frac"] - 650.0 / 6000.0) < 1e-9
