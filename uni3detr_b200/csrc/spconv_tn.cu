@@ -15,28 +15,39 @@
 //
 // Persistent, warp-specialised, one CTA per SM, 256-row output tiles:
 //   warps 0-7    epilogue: TMEM lane = output channel, TMEM column = row of the tile. A warp may
-//                only read the lane quarter warp%4 (hardware rule), so for Cout < 128 the weight
-//                image is replicated every 32 / 64 A rows: every quarter then holds all channels and
-//                the eight warps split the 256 columns (32 / 64 / 128 each for Cout <= 32 / 64 / 128).
+//                only read the lane quarter warp%4 (hardware rule). Cout = 32 / 64 (round 2): the
+//                weight-stationary instruction form tcgen05.mma.ws with M = Cout, whose accumulator
+//                spreads the 256 columns over the lane groups a plain M < 128 instruction leaves idle
+//                (M = 64: lanes 64-127 hold columns 128-255; M = 32: quarter q holds columns 64q..64q+63):
+//                every lane of every warp holds live data, the datapath is full (80 / 76 cycles per
+//                dispatch instead of 128, scripts/ubench/mma_cost.cu) and the weight image is the
+//                un-replicated Cout-row one. Other widths (and U3D_TN_WS=0): plain tcgen05.mma with the
+//                weight image replicated every 32 / 64 A rows so that every quarter holds all channels
+//                (or M = 64 on the un-replicated image for Cout = 64).
 //                tcgen05.ld 32x32b.x32, scale/shift (per-lane constants), adjacent channels paired
 //                by one shuffle so that a lane stores bf16x2, residual (prefetched one chunk ahead),
 //                ReLU, 64 contiguous bytes per row per warp.
-//   warp 8       MMA issue (one thread), accumulators double-buffered in TMEM (2 x 256 columns).
-//   warp 9       rulebook-slice loader (cp.async.bulk of the active 1 KB rulebook rows).
-//   warps 10-15  producers: two warps per stage (128 rows each), three stages of 48 KB (16 KB weight
+//   warp 8       MMA issue (one thread), accumulators double-buffered in TMEM (2 x 256 columns). The
+//                instruction form is a TEMPLATE parameter: a run-time branch around the two asm blocks
+//                slowed every layer shape by 10 - 30 %.
+//   warp 9       rulebook loader (cp.async.bulk of 1 KB rulebook rows): whole-tile slices of the active
+//                offsets, double-buffered (55 KB), or - Cout = 128 layers - the rows of each gather stage
+//                into a small ring (kSliceBufs = 0), which frees shared memory for one more stage.
+//   warps 10+    producers: two warps per stage (128 rows each), 3 - 4 stages of 36 - 48 KB (weight
 //                images + 32 KB gathered rows). A lane owns a CONTIGUOUS run of tile rows, so its
 //                rulebook entries arrive with a few 16-byte shared loads up front, followed by
 //                back-to-back 16-byte cp.async gathers (zero fill for missing neighbours) into the
 //                K-major swizzled B tile, published with cp.async.mbarrier.arrive.noinc; the first
-//                warp of the pair also bulk-copies the stage's 128-row weight images (second image
-//                set of u3d_spconv_pack_weights), one cp.async.bulk per (offset, Cin block).
-// Sorted tiles (tilesort.cu): with a `slot_row` list the rulebook is in slot order, the MMA thread
-// bulk-copies the tile's 256 slot -> row entries next to the accumulator buffer (they complete on
-// acc_full together with the tcgen05.commit) and the epilogue reads the residual of / writes row
-// slot_row[s]; inputs keep their natural row numbers.
+//                warp of the pair also bulk-copies the stage's weight images, one cp.async.bulk per
+//                (offset, Cin block).
+// Sorted tiles (tilesort.cu; every SubM level since round 2): with a `slot_row` list the rulebook is in
+// slot order, the MMA thread bulk-copies the tile's 256 slot -> row entries next to the accumulator
+// buffer (they complete on acc_full together with the tcgen05.commit) and the epilogue reads the
+// residual of / writes row slot_row[s]; inputs keep their natural row numbers.
 // Measured (profiles/): first version (one rulebook load per pass, one weight copy) 0.47 ms on the
-// 64->64 layers at batch 32 vs 0.64 ms rows-on-M; batched rulebook loads 0.33 ms; the replicated
-// image removes the epilogue bound of the 16- and 32-channel layers.
+// 64->64 layers at batch 32 vs 0.64 ms rows-on-M; batched rulebook loads 0.33 ms; M = 64 on un-replicated
+// images + a 4th stage 0.316; tcgen05.mma.ws 0.280; sorted tiles 0.222 ms = 570 TFLOP/s of real pairs, at
+// which point the launch moves 11.6 - 11.9 TB/s over the L2 -> SM crossbar (its cap): DESIGN.md section 4.
 #include <stdlib.h>
 #include "tc_common.cuh"
 
