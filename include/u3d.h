@@ -155,7 +155,7 @@ int u3d_rulebook_down(const int32_t* in_coors, const int32_t* n_in, int in_cap,
  * The order of the rows inside a bucket is not deterministic (atomics); conv results do not depend on it.
  */
 size_t u3d_tile_sort_scratch_ints(int cap);
-/* EXPERIMENTAL (round 1: not yet run on hardware; U3D_SORT_GROUP): the same with the signature buckets kept
+/* U3D_SORT_GROUP (validated in round 2, not the default): the same with the signature buckets kept
  * inside groups of `scenes_per_group` consecutive scenes (coors: (cap,4) [b,z,y,x] of the output rows,
  * scene-major; n_groups = ceil(B / scenes_per_group)), so that a tile's gathers stay within a few scenes. */
 size_t u3d_tile_sort_grouped_scratch_ints(int cap, int n_groups);
@@ -285,8 +285,7 @@ int u3d_coors_to_float(const int32_t* coors, int rows, float* out, void* stream)
 int u3d_sine_embed(const float* ref, int rows, void* out, int dtype, void* stream);
 
 /*
- * Input pre-stage (EXPERIMENTAL in round 1: written after the GPU budget was spent, not yet run on
- * hardware, not on the benchmarked path). The point-cloud part of the reference's test pipeline
+ * Input pre-stage (validated on hardware in round 2; not on the benchmarked path). The point-cloud part of the reference's test pipeline
  * (projects/configs/uni3detr/uni3detr_sunrgbd.py:175-191: LoadPointsFromFile(load_dim, use_dim,
  * shift_height) -> PointsRangeFilter -> PointSample) on the device, producing the (points, offsets)
  * pair u3d_voxelize_* consume.

@@ -48,7 +48,7 @@ __host__ __device__ inline Layout make_layout(int keys_pad64) {
 }
 
 // kVT = true (default): V is staged TRANSPOSED (V^T[d][key], K-major B operand of O = P V).
-// kVT = false (EXPERIMENTAL, U3D_MHA_VMN=1, not yet run on hardware): V is staged as loaded ([key][d], 64-byte
+// kVT = false (U3D_MHA_VMN=1; validated in round 2, test_mha_core_v_mn_major): V is staged as loaded ([key][d], 64-byte
 // rows, the layout of the K tile) and handed to the tensor core as an MN-major B operand (instruction
 // descriptor bit 16), which removes the 2-byte transposing shared stores.
 template <bool kVT>
@@ -249,7 +249,7 @@ int mha_core_tc(const void* q, const void* k, const void* v, int ldq, int ldk, i
                 int seq_len, int heads, void* out, cudaStream_t st) {
   using namespace mha;
   const size_t smem = make_layout((seq_len + 63) & ~63).total + 1024;
-  const bool vmn = getenv("U3D_MHA_VMN") != nullptr && atoi(getenv("U3D_MHA_VMN")) == 1;   // EXPERIMENTAL
+  const bool vmn = getenv("U3D_MHA_VMN") != nullptr && atoi(getenv("U3D_MHA_VMN")) == 1;
   static int cur_smem = 0, cur_smem_vmn = 0;
   if (vmn) U3D_CUDA(ensure_dynamic_smem(k_mha_tc<false>, smem, &cur_smem_vmn));
   else U3D_CUDA(ensure_dynamic_smem(k_mha_tc<true>, smem, &cur_smem));

@@ -6,8 +6,8 @@
 // Reference call sites: projects/configs/uni3detr/uni3detr_sunrgbd.py:175-191 (test_pipeline); the
 // transforms themselves are mmdet3d v1.0.0rc5 (not vendored): semantics restated in oracle/pipeline.py.
 //
-// STATUS: written in round 1 after the GPU budget was spent - NOT yet run on hardware. Nothing on the
-// benchmarked path calls it; its GPU tests are gated behind U3D_EXPERIMENTAL=1.
+// STATUS: validated on hardware in round 2 (tests/test_prestage.py, un-gated). Nothing on the benchmarked path
+// calls it: the bench starts from points that are already in the model's format.
 //
 // HBM-bound byte work: one read of the raw floats, one write of the kept rows; the only non-trivial
 // part is the 0.99th percentile of z behind shift_height (np.percentile(z, 0.99), linear

@@ -64,7 +64,7 @@ constexpr int kMmaWarp = 8;
 constexpr int kSliceWarp = 9;
 constexpr int kProdWarp0 = 10;
 // producer warps: 6 = 3 pairs = 3 ring slots (a stage is always 48 KB; default), or 8 with the
-// single-buffered rulebook slices of the EXPERIMENTAL 4-stage variant (U3D_TN_SLICE_BUFS=1)
+// single-buffered rulebook slices of the 4-stage variant (U3D_TN_SLICE_BUFS=1: measured slower)
 constexpr int threads_of(int n_prod) { return (kProdWarp0 + n_prod) * 32; }   // 512 / 576
 constexpr int kMaxK = 27;
 

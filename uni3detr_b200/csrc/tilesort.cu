@@ -152,8 +152,8 @@ k_nbr_permute(const int32_t* __restrict__ nbr, int nbr_stride, const int32_t* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// Grouped variant (EXPERIMENTAL in round 1: written after the GPU budget was spent, not yet run on
-// hardware; reached only through u3d_rulebook_sort_tiles_grouped / U3D_SORT_GROUP): bucket by
+// Grouped variant (validated in round 2; reached through u3d_rulebook_sort_tiles_grouped and the n_groups > 1 form of
+// u3d_rulebook_subm_sorted / U3D_SORT_GROUP; measured neutral on the step, not the default): bucket by
 // signature INSIDE groups of consecutive scenes, so that the gathers of a tile stay within a few
 // scenes' feature rows (L2 resident on the wide levels at batch 32, where the global order loses:
 // 64->64 0.348 -> 0.404 ms). CPU estimate of the useful slot fraction on 8 scenes, stage 2:
@@ -380,7 +380,7 @@ extern "C" size_t u3d_tile_sort_grouped_scratch_ints(int cap, int n_groups) {
   return (size_t)(cap > 0 ? cap : 1) + (size_t)(n_groups + 1) + 2 * (size_t)kKeyBins * (size_t)(n_groups > 0 ? n_groups : 1);
 }
 
-// EXPERIMENTAL (see the grouped kernels above): u3d_rulebook_sort_tiles with the signature buckets kept
+// u3d_rulebook_sort_tiles with the signature buckets kept
 // inside groups of `scenes_per_group` consecutive scenes. coors: (cap,4) int32 [b,z,y,x] of the OUTPUT rows
 // (scene-major); n_groups = ceil(B / scenes_per_group).
 extern "C" int u3d_rulebook_sort_tiles_grouped(const int32_t* nbr, int nbr_stride, const int32_t* coors,

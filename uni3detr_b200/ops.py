@@ -290,7 +290,7 @@ def rulebook_sort_tiles(nbr, n_out, cap, coors=None, n_scenes=0, scenes_per_grou
     """Tile scheduling for the tensor-core conv: returns a SORTED Rulebook (27, cap) whose slots group
     rows with similar neighbour masks (`.slot_row[s]` = output row of slot s, `.tile_mask` per 128
     slots); see csrc/tilesort.cu. Inputs: the natural-order table and its device row count.
-    EXPERIMENTAL: with `coors` (the output rows' (cap,4) coordinates), `n_scenes` and
+    With `coors` (the output rows' (cap,4) coordinates), `n_scenes` and
     `scenes_per_group` > 0 the buckets stay inside groups of consecutive scenes."""
     lib = _lib.load()
     K = nbr.shape[0]
@@ -551,7 +551,7 @@ def launch_count():
 
 # ---------------------------------------------------------------- input pre-stage (experimental) ----
 def points_prepare(raw, raw_off, B, use_dim, shift_height=False, pc_range=None):
-    """EXPERIMENTAL (not yet run on hardware, see csrc/points.cu). LoadPointsFromFile column select
+    """Input pre-stage (csrc/points.cu; validated on hardware in round 2). LoadPointsFromFile column select
     (+ shift_height) and PointsRangeFilter on the device. raw (Ntot, load_dim) f32, raw_off (B+1) int32.
     Returns (points (Ntot, C) with the kept rows packed scene by scene, out_off (B+1) int32, floor_z (B))."""
     lib = _lib.load()
@@ -576,7 +576,7 @@ def points_prepare(raw, raw_off, B, use_dim, shift_height=False, pc_range=None):
 
 
 def points_gather(points, choices):
-    """EXPERIMENTAL. PointSample with host-drawn indices: points[choices] on the device."""
+    """PointSample with host-drawn indices: points[choices] on the device."""
     lib = _lib.load()
     _req(points, torch.float32, "points")
     _req(choices, torch.int32, "choices")

@@ -1,4 +1,4 @@
-"""Device input pre-stage built from the reference's `test_pipeline` dicts (EXPERIMENTAL, round 1).
+"""Device input pre-stage built from the reference's `test_pipeline` dicts (round 1; validated on hardware in round 2).
 
 `PointsPreStage(cfg.test_pipeline)` reads the `LoadPointsFromFile`, `PointsRangeFilter` and `PointSample`
 entries of the reference config (same `type=` names and keys: coord_type, load_dim, use_dim, shift_height,
@@ -8,7 +8,7 @@ no per-sample numpy round trip. Image / formatting entries (`DefaultFormatBundle
 `MultiScaleFlipAug3D` with its identity test-time transforms) carry no point arithmetic and are skipped;
 `LoadPointsFromMultiSweeps` (nuScenes) is not covered yet.
 
-Not on the benchmarked path and not yet run on hardware: see csrc/points.cu.
+Not on the benchmarked path (the bench starts from points already in the model's format): see csrc/points.cu.
 """
 import numpy as np
 import torch
