@@ -205,7 +205,9 @@ def fps_tie_key(n, tie_block=1024):
     block winner: two tied candidates meet at the level of the lowest bit in which their thread ids differ and the
     one with that bit clear survives, i.e. the smallest BIT-REVERSED thread id wins, then the lowest k.
     (mmcv/ops/csrc/common/cuda/furthest_point_sample_cuda_kernel.cuh - recalled, the source is not vendored;
-    literal restatement: fps_block_reference below.) tie_block=0: plain lowest index."""
+    literal restatement: fps_block_reference below.) The kernel's launcher takes the exponent as
+    int(log(n) / log(2.0)) in double precision, which equals floor(log2 n) for every n up to 2^20 including the exact
+    powers of two (tests/test_oracle.py). tie_block=0: plain lowest index."""
     k = np.arange(n, dtype=np.int64)
     if not tie_block or n == 0:
         return k

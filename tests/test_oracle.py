@@ -185,6 +185,10 @@ def test_fps_tie_order_matches_block_reduction():
             cand = np.nonzero(temp == temp.max())[0]
             assert int(cand[np.argmin(key[cand])]) == want, (n, cap, trial)
     np.testing.assert_array_equal(G.fps_tie_key(10, 0), np.arange(10))
+    # the reference launcher's exponent int(log(n) / log(2.0)) (double) == floor(log2 n), exact powers of two included
+    import math
+    for n in list(range(1, 5000)) + [2 ** k + d for k in range(12, 21) for d in (-1, 0, 1)]:
+        assert int(math.log(float(n)) / math.log(2.0)) == int(np.floor(np.log2(n))) == n.bit_length() - 1, n
 
 
 def test_fps_stride_quirk_view():
