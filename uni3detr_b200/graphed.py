@@ -31,6 +31,12 @@ class GraphedForward:
         # the device-side get_bboxes (per-class NMS ...) rides in the same graph when the config's
         # post-processing is one the device path implements; otherwise the graph ends at the top-k
         self.postprocess = bool(postprocess) and (pp is None or pp.get("type") == "nms")
+        # fixed shapes, replayed forever: let cuDNN time its engines for every dense conv during the warm-up instead of
+        # trusting the heuristic pick (torch.backends.cudnn.benchmark; the capture below re-uses the cached choices).
+        # U3D_CUDNN_BENCHMARK=0 keeps the heuristics.
+        import os
+        if os.environ.get("U3D_CUDNN_BENCHMARK", "1") != "0":
+            torch.backends.cudnn.benchmark = True
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):       # warm-up: cuDNN plans, weight packing, allocator pools
